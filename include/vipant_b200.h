@@ -1,0 +1,150 @@
+/*
+ * vipant_b200 -- C-ABI of the B200-native InfoNCE / retrieval-scoring hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every
+ * entry point replaces a span of the reference's PyTorch code in
+ *   /root/reference/cvap/module/decoder/loss_head.py        (cited per function)
+ * and is what a binding on the reference side calls (ctypes stub: INTEGRATION.md;
+ * the in-tree Python mirror of the reference's loss-head API is vipant_b200/loss_head.py).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - matrices are row-major, leading dimension in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it:
+ *     no allocation, no host synchronisation, no global state besides the error string;
+ *   - scratch memory is caller-owned, sized by the matching *_workspace_bytes query;
+ *   - return value: 0 ok, <0 invalid argument (VPA_E_*), >0 a cudaError_t;
+ *     vpa_last_error_string() describes the last non-zero return of the calling thread;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute
+ *     entry point returns an error.
+ */
+#ifndef VIPANT_B200_H_
+#define VIPANT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPA_VERSION 100 /* 0.1.0 */
+
+/* element types of user-facing feature matrices */
+#define VPA_F32 0
+#define VPA_BF16 1
+#define VPA_F16 2
+
+/* arithmetic of the similarity contraction */
+#define VPA_PREC_BF16_TC 0   /* bf16 operands, fp32 accumulate, tcgen05 tensor cores (TMA + TMEM)   */
+#define VPA_PREC_FP32_SIMT 1 /* fp32 FFMA; "fp32 mode" parity bars, any D % 4 == 0                    */
+
+#define VPA_E_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported D ...) */
+#define VPA_E_WORKSPACE (-2)   /* workspace too small */
+#define VPA_E_UNSUPPORTED (-3) /* shape/precision combination not supported by this build */
+#define VPA_E_NO_DEVICE (-4)   /* no sm_100 device / driver entry point missing */
+
+int vpa_version(void);
+const char* vpa_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------
+ * L2 normalisation + cast.  Replaces  x / x.norm(dim=-1, keepdim=True)
+ *   loss_head.py:271-273 (CELossHead.forward), :38-40 (LossHead.infer); no epsilon, a zero
+ *   row yields NaN exactly as the reference does.
+ * vpa_normalize_cast: one matrix.  Any of y_bf16 / y_f32 / inv_norm may be NULL.
+ *   already_normalized != 0 reproduces the `normalized=True` entry condition (:271): the
+ *   values are only cast, inv_norm is written as 1.
+ * vpa_normalize_pair: the fused training-path kernel: both modalities in one launch plus
+ *   diag_cos[i] = <a_i, t_i> computed from the bf16-rounded (precision 0) or fp32 rows.
+ * Requires D % 4 == 0, ld >= D, 16-byte aligned rows.
+ * ------------------------------------------------------------------------------------------ */
+int vpa_normalize_cast(const void* x, int in_dtype, int64_t rows, int D, int64_t ld,
+                       int already_normalized, void* y_bf16, float* y_f32, float* inv_norm,
+                       void* stream);
+
+int vpa_normalize_pair(const void* x1, const void* x2, int in_dtype, int64_t rows, int D,
+                       int64_t ld1, int64_t ld2, int already_normalized,
+                       void* a_bf16, void* t_bf16, float* a_f32, float* t_f32,
+                       float* inv_norm1, float* inv_norm2, float* diag_cos, int diag_from_bf16,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * InfoNCE forward.  Replaces loss_head.py:276-283 for the rows this process owns.
+ *   s        = min(exp(*logit_scale), scale_max)   (:276; scale_max <= 0 or +inf: no clamp, :254)
+ *   S        = s * A_loc . T_all^T   and   S' = s * T_loc . A_all^T   are formed tile by tile on
+ *              the tensor cores and never written to memory;
+ *   row_lse[i] = logsumexp_j S[i, j],  col_lse[i] = logsumexp_j S'[i, j],  diag[i] = s * diag_cos[i]
+ *   scale_out[0] = s, scale_out[1] = 1 if the clamp passes the gradient (exp(l) <= scale_max) else 0.
+ * a_loc/t_loc: this rank's rows_local normalised rows (rows [row_offset, row_offset+rows_local) of
+ * the global batch); a_all/t_all: all rows_global rows (== a_loc/t_loc on one GPU).  Element type:
+ * bf16 for VPA_PREC_BF16_TC (requires D % 64 == 0, D <= 512, contiguous rows ld == D),
+ * fp32 for VPA_PREC_FP32_SIMT.
+ * ------------------------------------------------------------------------------------------ */
+size_t vpa_infonce_workspace_bytes(int64_t rows_local, int64_t rows_global, int D, int precision);
+
+int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all,
+                    int precision, int64_t rows_local, int64_t rows_global, int D,
+                    int64_t row_offset, const float* logit_scale, float scale_max,
+                    const float* diag_cos, void* workspace, size_t workspace_bytes,
+                    float* row_lse, float* col_lse, float* diag, float* scale_out, void* stream);
+
+/* loss = mean_i(row_lse - diag) + mean_i(col_lse - diag) over the GLOBAL batch (:280-283: two
+ * mean-reduced cross entropies, summed).  Deterministic fixed-order reduction, one block. */
+int vpa_infonce_loss(const float* row_lse, const float* col_lse, const float* diag,
+                     int64_t rows_global, float* loss_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * InfoNCE backward (the autograd of loss_head.py:271-283, SURVEY.md section 8 closed form).
+ * Recomputes the logit tiles, forms G = (softmax_rows + softmax_cols - 2I)/B in registers and
+ * contracts it with the other modality on the tensor cores:
+ *   dx1[i] = J1_i ( g * s * sum_j G[i,j] t_j ),   dx2[i] = J2_i ( g * s * sum_j G[j,i] a_j )
+ * for the local rows, J = (I - a a^T)/||x|| the normalisation Jacobian (identity when
+ * already_normalized), g = *grad_out (the incoming dL, e.g. the AMP loss scale).
+ *   dlogit_scale[0] = g * flows * sum_{i local, j} G[i,j] S[i,j]   (this rank's share; all-reduce it)
+ * row_lse_all / col_lse_all: the GLOBAL (rows_global,) statistic vectors from the forward.
+ * x1/x2: the original (un-normalised) local rows, dtype in_dtype; dx1/dx2 same dtype and ld.
+ * ------------------------------------------------------------------------------------------ */
+int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all,
+                    int precision, int64_t rows_local, int64_t rows_global, int D,
+                    int64_t row_offset, const float* scale /* scale_out of the forward */,
+                    const float* row_lse_all, const float* col_lse_all,
+                    const float* grad_out, const void* x1, const void* x2, int in_dtype,
+                    int64_t ld1, int64_t ld2, const float* inv_norm1, const float* inv_norm2,
+                    int already_normalized, void* workspace, size_t workspace_bytes,
+                    void* dx1, void* dx2, float* dlogit_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Similarity + rank / top-k for the monitors' scoring.  Replaces, per query row,
+ *   S = Q @ K.t(); ind = S.argsort(descending=True); torch.where(ind == gt)[1]; ind[:, :k]
+ *   loss_head.py:115-117,128-130 (N==M), :139-142,156-158 (1-vs-5), :81-91,95-103
+ *   (retrieval_eval), :381-385 (zero-shot argmax).
+ * Q (N,D), K (M,D) fp32.  ranks[i,c] = #{m : S[i,m] > S[i,gt[i,c]]} + #{m < gt : S[i,m] == S[i,gt]}
+ * (position in a stable descending sort); topk_idx/topk_val: the k best keys per query,
+ * descending, lower index first on ties (k <= 32).  gt_idx may be NULL (g = 0); topk_* may be NULL
+ * (k = 0).  Similarities are fp32 FFMA dot products; S (N x M fp32) lives in the workspace.
+ * ------------------------------------------------------------------------------------------ */
+size_t vpa_sim_workspace_bytes(int64_t N, int64_t M);
+
+int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int D,
+                      int64_t ldq, int64_t ldk, const int32_t* gt_idx, int g, int k,
+                      int64_t* topk_idx, float* topk_val, int32_t* ranks,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry (the end-to-end call timed as `e2e` in bench.py): pageable or
+ * pinned HOST x1/x2 (fp32, contiguous), copies them to the device, runs normalise -> forward ->
+ * loss -> backward on `stream`, copies loss / dlogit_scale (and dx1/dx2 when non-NULL) back and
+ * synchronises the stream.  dev_scratch must hold vpa_infonce_host_scratch_bytes() bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t vpa_infonce_host_scratch_bytes(int64_t rows, int D, int precision);
+
+int vpa_infonce_step_host(const float* x1_host, const float* x2_host, int64_t rows, int D,
+                          float logit_scale, float scale_max, float grad_out, int precision,
+                          void* dev_scratch, size_t dev_scratch_bytes,
+                          float* loss_host, float* dlogit_scale_host,
+                          float* dx1_host, float* dx2_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIPANT_B200_H_ */

@@ -1,0 +1,73 @@
+"""ctypes binding of libvipant_b200.so (include/vipant_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails the caller
+gets an exception.  The library is built in-tree by ``python -m vipant_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+from . import build as _build
+
+F32, BF16, F16 = 0, 1, 2
+PREC_BF16_TC, PREC_FP32_SIMT = 0, 1
+
+# name -> (restype, argtypes); mirrors include/vipant_b200.h one to one
+_SIGNATURES = {
+    "vpa_version": (c_int, []),
+    "vpa_last_error_string": (c_char_p, []),
+    "vpa_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpa_normalize_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "vpa_infonce_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "vpa_infonce_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int64,
+                                c_void_p, c_float, c_void_p, c_void_p, c_size_t,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpa_infonce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "vpa_infonce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int64,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+                                c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpa_sim_workspace_bytes": (c_size_t, [c_int64, c_int64]),
+    "vpa_sim_rank_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vpa_infonce_host_scratch_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "vpa_infonce_step_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_int,
+                                      c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_LIB = None
+
+
+class VipantB200Error(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise VipantB200Error(
+                f"{path} not found: build it with `python -m vipant_b200.build` (needs nvcc). "
+                "vipant_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the .so does not export the symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().vpa_last_error_string()
+        raise VipantB200Error(f"{what} failed with code {code}: {msg.decode() if msg else ''}")

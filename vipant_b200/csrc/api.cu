@@ -1,0 +1,286 @@
+// extern "C" surface of libvipant_b200.so (see include/vipant_b200.h) + work planning.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vpa {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// launchers defined in the other translation units
+int normalize_cast_launch(const void* x, int in_dtype, int64_t rows, int D, int64_t ld, int already,
+                          void* y_bf16, float* y_f32, float* inv_norm, cudaStream_t st);
+int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t rows, int D, int64_t ld1,
+                          int64_t ld2, int already, void* a_bf16, void* t_bf16, float* a_f32, float* t_f32,
+                          float* inv1, float* inv2, float* diag_cos, int diag_from_bf16, cudaStream_t st);
+int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local,
+                         const float* logit_scale, float scale_cap, const float* diag_cos,
+                         float* row_lse, float* col_lse, float* diag, float* scale_out, cudaStream_t st);
+int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
+                cudaStream_t st);
+int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
+                        const float* scale, const float* grad_out, const void* x1, const void* x2,
+                        int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
+                        int already, void* dx1, void* dx2, float* dlogit_scale, cudaStream_t st);
+int sim_rank_topk_launch(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
+                         const int32_t* gt_idx, int g, int k, int64_t* topk_idx, float* topk_val,
+                         int32_t* ranks, float* S, cudaStream_t st);
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      n = v;
+    else
+      n = 148;   // B200
+    cudaGetLastError();
+  }
+  return n;
+}
+
+// Number of column chunks that minimises (waves x per-unit length) for `base_units` row-block units
+// sweeping `n_tiles` tiles; `fixed` = per-unit fixed cost in tile equivalents (X load, drain).
+static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk) {
+  const int sms = sm_count();
+  long best_cost = -1;
+  int best_c = 1;
+  const int cmax = n_tiles < 64 ? n_tiles : 64;
+  for (int c = 1; c <= cmax; ++c) {
+    const int tpc = (n_tiles + c - 1) / c;
+    const int real_c = (n_tiles + tpc - 1) / tpc;
+    const long waves = ((long)base_units * real_c + sms - 1) / sms;
+    const long cost = waves * (tpc + fixed);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = real_c; }
+  }
+  *tiles_per_chunk = (n_tiles + best_c - 1) / best_c;
+  *chunks = (n_tiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
+}
+
+SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision) {
+  SweepPlan p{};
+  if (precision == VPA_PREC_FP32_SIMT) {
+    p.rows_per_blk = 8;
+    p.n_iblk = (int)((rows_local + 7) / 8);
+    p.n_tiles = 0;
+    p.fwd_chunks = p.bwd_chunks = 1;
+    p.fwd_tiles_per_chunk = p.bwd_tiles_per_chunk = 0;
+    p.halves = 1;
+    p.n_dscale = p.n_iblk;
+    return p;
+  }
+  p.rows_per_blk = 128;
+  p.n_iblk = (int)((rows_local + 127) / 128);
+  p.n_tiles = (int)((rows_global + 127) / 128);
+  p.halves = D > 256 ? 2 : 1;
+  pick_chunks(2 * p.n_iblk, p.n_tiles, 2, &p.fwd_chunks, &p.fwd_tiles_per_chunk);
+  pick_chunks(2 * p.n_iblk * p.halves, p.n_tiles, 3, &p.bwd_chunks, &p.bwd_tiles_per_chunk);
+  p.n_dscale = p.n_iblk * p.halves * p.bwd_chunks;
+  return p;
+}
+
+Workspace carve_workspace(void* base, int64_t rows_local, int D, const SweepPlan& plan) {
+  Workspace w{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o += align_up(bytes, 256);
+    return p;
+  };
+  w.fwd_part = static_cast<float*>(take((size_t)2 * plan.fwd_chunks * rows_local * 2 * sizeof(float)));
+  w.bwd_part = static_cast<float*>(take((size_t)2 * plan.bwd_chunks * rows_local * D * sizeof(float)));
+  w.dscale_part = static_cast<float*>(take((size_t)(plan.n_dscale > 0 ? plan.n_dscale : 1) * sizeof(float)));
+  w.bytes = o;
+  return w;
+}
+
+static int check_infonce_shape(int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, int precision) {
+  VPA_CHECK_ARG(precision == VPA_PREC_BF16_TC || precision == VPA_PREC_FP32_SIMT, "bad precision %d", precision);
+  VPA_CHECK_ARG(rows_local > 0 && rows_global >= rows_local, "need 0 < rows_local <= rows_global");
+  VPA_CHECK_ARG(row_offset >= 0 && row_offset + rows_local <= rows_global, "row_offset out of range");
+  if (precision == VPA_PREC_BF16_TC) {
+    const int kb = D / 64;
+    if (D % 64 != 0 || D < 64 || D > 512 || (kb > 4 && (kb & 1)))
+      return set_error(VPA_E_UNSUPPORTED, "tensor-core path supports D in {64,128,192,256,384,512} (D=%d)", D);
+  } else {
+    if (D % 4 != 0 || D < 4 || D > 1024)
+      return set_error(VPA_E_UNSUPPORTED, "fp32 path supports D %% 4 == 0, D <= 1024 (D=%d)", D);
+  }
+  return 0;
+}
+
+}  // namespace vpa
+
+using namespace vpa;
+
+extern "C" {
+
+int vpa_version(void) { return VPA_VERSION; }
+
+const char* vpa_last_error_string(void) { return g_err; }
+
+int vpa_normalize_cast(const void* x, int in_dtype, int64_t rows, int D, int64_t ld, int already_normalized,
+                       void* y_bf16, float* y_f32, float* inv_norm, void* stream) {
+  return normalize_cast_launch(x, in_dtype, rows, D, ld, already_normalized, y_bf16, y_f32, inv_norm,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int vpa_normalize_pair(const void* x1, const void* x2, int in_dtype, int64_t rows, int D, int64_t ld1, int64_t ld2,
+                       int already_normalized, void* a_bf16, void* t_bf16, float* a_f32, float* t_f32,
+                       float* inv_norm1, float* inv_norm2, float* diag_cos, int diag_from_bf16, void* stream) {
+  return normalize_pair_launch(x1, x2, in_dtype, rows, D, ld1, ld2, already_normalized, a_bf16, t_bf16, a_f32, t_f32,
+                               inv_norm1, inv_norm2, diag_cos, diag_from_bf16, static_cast<cudaStream_t>(stream));
+}
+
+size_t vpa_infonce_workspace_bytes(int64_t rows_local, int64_t rows_global, int D, int precision) {
+  if (rows_local <= 0 || rows_global < rows_local || D <= 0) return 0;
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
+  return carve_workspace(nullptr, rows_local, D, plan).bytes;
+}
+
+int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+                    int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
+                    float scale_max, const float* diag_cos, void* workspace, size_t workspace_bytes,
+                    float* row_lse, float* col_lse, float* diag, float* scale_out, void* stream) {
+  if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
+  VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && diag_cos && row_lse && col_lse && diag && workspace,
+                "infonce_fwd: null pointer");
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
+  const Workspace ws = carve_workspace(workspace, rows_local, D, plan);
+  if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_fwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  SweepArgs a{};
+  a.x[0] = a_loc; a.y[0] = t_all; a.x[1] = t_loc; a.y[1] = a_all;
+  a.rows_local = rows_local; a.rows_global = rows_global; a.row_offset = row_offset; a.D = D;
+  a.logit_scale = logit_scale;
+  a.scale_cap = (scale_max > 0.f) ? scale_max : INFINITY;     // `cfg.scale_max or float("inf")`
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = (precision == VPA_PREC_BF16_TC) ? tc_infonce_fwd(a, ws, plan, st) : simt_infonce_fwd(a, ws, plan, st)) return e;
+  return combine_stats_launch(ws, plan, rows_local, logit_scale, a.scale_cap, diag_cos, row_lse, col_lse, diag, scale_out, st);
+}
+
+int vpa_infonce_loss(const float* row_lse, const float* col_lse, const float* diag, int64_t rows_global,
+                     float* loss_out, void* stream) {
+  VPA_CHECK_ARG(row_lse && col_lse && diag && loss_out && rows_global > 0, "infonce_loss: bad argument");
+  return loss_launch(row_lse, col_lse, diag, rows_global, loss_out, static_cast<cudaStream_t>(stream));
+}
+
+int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+                    int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* scale,
+                    const float* row_lse_all, const float* col_lse_all, const float* grad_out, const void* x1,
+                    const void* x2, int in_dtype, int64_t ld1, int64_t ld2, const float* inv_norm1,
+                    const float* inv_norm2, int already_normalized, void* workspace, size_t workspace_bytes,
+                    void* dx1, void* dx2, float* dlogit_scale, void* stream) {
+  if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
+  VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && scale && row_lse_all && col_lse_all && grad_out && dx1 && dx2 && workspace,
+                "infonce_bwd: null pointer");
+  VPA_CHECK_ARG(already_normalized || (x1 && x2 && inv_norm1 && inv_norm2), "infonce_bwd: x / inv_norm required");
+  VPA_CHECK_ARG(in_dtype == VPA_F32 || in_dtype == VPA_BF16 || in_dtype == VPA_F16, "infonce_bwd: bad dtype");
+  VPA_CHECK_ARG(ld1 >= D && ld2 >= D && ld1 % 4 == 0 && ld2 % 4 == 0, "infonce_bwd: bad leading dimension");
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
+  const Workspace ws = carve_workspace(workspace, rows_local, D, plan);
+  if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_bwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  SweepArgs a{};
+  a.x[0] = a_loc; a.y[0] = t_all; a.x[1] = t_loc; a.y[1] = a_all;
+  a.rows_local = rows_local; a.rows_global = rows_global; a.row_offset = row_offset; a.D = D;
+  a.scale = scale;
+  a.lse_x[0] = row_lse_all; a.lse_y[0] = col_lse_all;   // problem 0: rows of S
+  a.lse_x[1] = col_lse_all; a.lse_y[1] = row_lse_all;   // problem 1: columns of S
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int e = (precision == VPA_PREC_BF16_TC) ? tc_infonce_bwd(a, ws, plan, st) : simt_infonce_bwd(a, ws, plan, st)) return e;
+  return finalize_bwd_launch(ws, plan, rows_local, D, scale, grad_out, x1, x2, in_dtype, ld1, ld2, inv_norm1, inv_norm2,
+                             already_normalized, dx1, dx2, dlogit_scale, st);
+}
+
+size_t vpa_sim_workspace_bytes(int64_t N, int64_t M) {
+  if (N <= 0 || M <= 0) return 0;
+  return align_up((size_t)N * (size_t)M * sizeof(float), 256);
+}
+
+int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
+                      const int32_t* gt_idx, int g, int k, int64_t* topk_idx, float* topk_val, int32_t* ranks,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  VPA_CHECK_ARG(workspace != nullptr, "sim_rank_topk: null workspace");
+  if (vpa_sim_workspace_bytes(N, M) > workspace_bytes)
+    return set_error(VPA_E_WORKSPACE, "sim_rank_topk: workspace %zu < %zu", workspace_bytes, vpa_sim_workspace_bytes(N, M));
+  return sim_rank_topk_launch(Q, K, N, M, D, ldq, ldk, gt_idx, g, k, topk_idx, topk_val, ranks,
+                              static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+// ---- host-buffer end-to-end step ---------------------------------------------------------------------
+struct HostScratch {
+  float *x1, *x2, *af, *tf, *inv1, *inv2, *dcos, *rl, *cl, *dg, *sc, *loss, *dls, *gout, *lsc, *dx1, *dx2;
+  void *ab, *tb, *ws;
+  size_t ws_bytes, bytes;
+};
+static HostScratch carve_host(void* base, int64_t rows, int D, int precision) {
+  HostScratch h{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o += align_up(bytes, 256);
+    return p;
+  };
+  const size_t mat = (size_t)rows * D;
+  h.x1 = (float*)take(mat * 4); h.x2 = (float*)take(mat * 4);
+  h.dx1 = (float*)take(mat * 4); h.dx2 = (float*)take(mat * 4);
+  h.ab = take(mat * 2); h.tb = take(mat * 2);
+  if (precision == VPA_PREC_FP32_SIMT) { h.af = (float*)take(mat * 4); h.tf = (float*)take(mat * 4); }
+  h.inv1 = (float*)take(rows * 4); h.inv2 = (float*)take(rows * 4); h.dcos = (float*)take(rows * 4);
+  h.rl = (float*)take(rows * 4); h.cl = (float*)take(rows * 4); h.dg = (float*)take(rows * 4);
+  h.sc = (float*)take(16); h.loss = (float*)take(16); h.dls = (float*)take(16);
+  h.gout = (float*)take(16); h.lsc = (float*)take(16);
+  h.ws_bytes = vpa_infonce_workspace_bytes(rows, rows, D, precision);
+  h.ws = take(h.ws_bytes);
+  h.bytes = o;
+  return h;
+}
+
+size_t vpa_infonce_host_scratch_bytes(int64_t rows, int D, int precision) {
+  if (rows <= 0 || D <= 0) return 0;
+  return carve_host(nullptr, rows, D, precision).bytes;
+}
+
+int vpa_infonce_step_host(const float* x1_host, const float* x2_host, int64_t rows, int D, float logit_scale,
+                          float scale_max, float grad_out, int precision, void* dev_scratch,
+                          size_t dev_scratch_bytes, float* loss_host, float* dlogit_scale_host, float* dx1_host,
+                          float* dx2_host, void* stream) {
+  if (int e = check_infonce_shape(rows, rows, D, 0, precision)) return e;
+  VPA_CHECK_ARG(x1_host && x2_host && dev_scratch && loss_host, "infonce_step_host: null pointer");
+  const HostScratch h = carve_host(dev_scratch, rows, D, precision);
+  if (h.bytes > dev_scratch_bytes) return set_error(VPA_E_WORKSPACE, "infonce_step_host: scratch %zu < %zu", dev_scratch_bytes, h.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t mat = (size_t)rows * D * sizeof(float);
+  VPA_CUDA(cudaMemcpyAsync(h.x1, x1_host, mat, cudaMemcpyHostToDevice, st));
+  VPA_CUDA(cudaMemcpyAsync(h.x2, x2_host, mat, cudaMemcpyHostToDevice, st));
+  VPA_CUDA(cudaMemcpyAsync(h.lsc, &logit_scale, sizeof(float), cudaMemcpyHostToDevice, st));
+  VPA_CUDA(cudaMemcpyAsync(h.gout, &grad_out, sizeof(float), cudaMemcpyHostToDevice, st));
+  const bool tcp = precision == VPA_PREC_BF16_TC;
+  if (int e = vpa_normalize_pair(h.x1, h.x2, VPA_F32, rows, D, D, D, 0, tcp ? h.ab : nullptr, tcp ? h.tb : nullptr,
+                                 h.af, h.tf, h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
+  const void* a = tcp ? h.ab : (const void*)h.af;
+  const void* t = tcp ? h.tb : (const void*)h.tf;
+  if (int e = vpa_infonce_fwd(a, t, a, t, precision, rows, rows, D, 0, h.lsc, scale_max, h.dcos, h.ws, h.ws_bytes,
+                              h.rl, h.cl, h.dg, h.sc, st)) return e;
+  if (int e = vpa_infonce_loss(h.rl, h.cl, h.dg, rows, h.loss, st)) return e;
+  if (int e = vpa_infonce_bwd(a, t, a, t, precision, rows, rows, D, 0, h.sc, h.rl, h.cl, h.gout, h.x1, h.x2, VPA_F32,
+                              D, D, h.inv1, h.inv2, 0, h.ws, h.ws_bytes, h.dx1, h.dx2, h.dls, st)) return e;
+  VPA_CUDA(cudaMemcpyAsync(loss_host, h.loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (dlogit_scale_host) VPA_CUDA(cudaMemcpyAsync(dlogit_scale_host, h.dls, sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (dx1_host) VPA_CUDA(cudaMemcpyAsync(dx1_host, h.dx1, mat, cudaMemcpyDeviceToHost, st));
+  if (dx2_host) VPA_CUDA(cudaMemcpyAsync(dx2_host, h.dx2, mat, cudaMemcpyDeviceToHost, st));
+  VPA_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

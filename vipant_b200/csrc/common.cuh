@@ -1,0 +1,144 @@
+// Shared helpers for the vipant_b200 CUDA sources (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vipant_b200.h"
+
+namespace vpa {
+
+// ---- error plumbing (api.cu owns the thread-local string) --------------------------------
+int set_error(int code, const char* fmt, ...);
+
+#define VPA_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ::vpa::set_error(VPA_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define VPA_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::vpa::set_error((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
+  } while (0)
+
+#define VPA_LAUNCH_CHECK(name)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::vpa::set_error((int)e__, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---- device helpers ----------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 4 consecutive elements of a row, widened to fp32.
+template <int DTYPE>
+__device__ __forceinline__ float4 load4(const void* base, int64_t elem_off) {
+  if constexpr (DTYPE == VPA_F32) {
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+  } else if constexpr (DTYPE == VPA_BF16) {
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+    __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+    __nv_bfloat162 hi = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + elem_off));
+    __half2 lo = *reinterpret_cast<__half2*>(&u.x);
+    __half2 hi = *reinterpret_cast<__half2*>(&u.y);
+    float2 a = __half22float2(lo), b = __half22float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+template <int DTYPE>
+__device__ __forceinline__ void store4(void* base, int64_t elem_off, float4 v) {
+  if constexpr (DTYPE == VPA_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off) = v;
+  } else if constexpr (DTYPE == VPA_BF16) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = u;
+  } else {
+    __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + elem_off) = u;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- internal launchers (one per .cu) ----------------------------------------------------
+// Work decomposition of the two sweeps (forward statistics, backward dX).  A "unit" is one CTA's
+// work: a block of X rows swept against a contiguous chunk of 128-row Y tiles.
+struct SweepPlan {
+  int n_iblk;               // X row blocks per problem
+  int rows_per_blk;         // 128 (tensor-core path) or the SIMT row block
+  int n_tiles;              // ceil(rows_global / 128) column tiles (tensor-core path)
+  int fwd_chunks, fwd_tiles_per_chunk;
+  int bwd_chunks, bwd_tiles_per_chunk;
+  int halves;               // backward: D split into 1 or 2 accumulator halves (TMEM capacity)
+  int n_dscale;             // number of partial sums of G*cos written by the backward sweep
+};
+SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision);
+
+// Scratch layout shared by both precisions.
+struct Workspace {
+  float* fwd_part;      // [2][fwd_chunks][rows_local] float2 (m, l), base-2 units
+  float* bwd_part;      // [2][bwd_chunks][rows_local][D] fp32 partial  sum_j G_ij y_j
+  float* dscale_part;   // [n_dscale] partial  sum_ij G_ij cos_ij  (problem 0 only)
+  size_t bytes;
+};
+Workspace carve_workspace(void* base, int64_t rows_local, int D, const SweepPlan& plan);
+
+// Everything a sweep launch needs besides the plan.  Problem 0: X = A_loc, Y = T_all (rows of S);
+// problem 1: X = T_loc, Y = A_all (columns of S, transposed).  Both run in ONE launch.
+struct SweepArgs {
+  const void* x[2];            // local rows   (bf16 for the tensor-core path, fp32 for SIMT)
+  const void* y[2];            // global rows
+  int64_t rows_local, rows_global, row_offset;
+  int D;
+  const float* logit_scale;    // forward: s = min(exp(*logit_scale), scale_cap)
+  float scale_cap;
+  const float* scale;          // backward: s as written by the forward
+  const float* lse_x[2];       // backward: lse of the X rows' direction, GLOBAL vector (rows_global)
+  const float* lse_y[2];       // backward: lse of the other direction, GLOBAL vector
+};
+
+int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+int tc_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+int simt_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+int simt_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+
+}  // namespace vpa

@@ -1,0 +1,166 @@
+// Small memory-bound kernels around the two sweeps: merge of per-chunk (max, sum) statistics,
+// the scalar loss, and the backward finalisation (chunk sum, scale, normalisation Jacobian, cast).
+#include "common.cuh"
+
+namespace vpa {
+
+// ---- forward: merge chunk partials -> logsumexp (natural log), diag = s * cos, scale_out -----------
+__global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chunks, int64_t rows_local,
+                                     const float* __restrict__ logit_scale, float scale_cap,
+                                     const float* __restrict__ diag_cos, float* __restrict__ row_lse,
+                                     float* __restrict__ col_lse, float* __restrict__ diag,
+                                     float* __restrict__ scale_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float e = expf(*logit_scale);
+  const float s = fminf(e, scale_cap);
+  if (idx == 0 && scale_out) {
+    scale_out[0] = s;
+    scale_out[1] = (e <= scale_cap) ? 1.0f : 0.0f;   // torch.clamp(max=) passes grad where input <= max
+  }
+  if (idx >= 2 * rows_local) return;
+  const int p = idx >= rows_local;
+  const int64_t row = idx - (int64_t)p * rows_local;
+  const float2* base = part + (int64_t)p * n_chunks * rows_local + row;
+  float M = -INFINITY;
+  for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, base[(int64_t)c * rows_local].x);
+  float L = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    float2 ml = base[(int64_t)c * rows_local];
+    L += ml.y * exp2f(ml.x - M);
+  }
+  const float lse = (M + log2f(L)) * kLn2;
+  (p ? col_lse : row_lse)[row] = lse;
+  if (p == 0 && diag) diag[row] = s * diag_cos[row];
+}
+
+// ---- loss = mean(row_lse - diag) + mean(col_lse - diag), fixed-order fp64 reduction ---------------
+__global__ void __launch_bounds__(1024)
+loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+            const float* __restrict__ diag, int64_t B, float* __restrict__ loss) {
+  __shared__ double red[1024];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < B; i += 1024)
+    acc += ((double)row_lse[i] - (double)diag[i]) + ((double)col_lse[i] - (double)diag[i]);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)(red[0] / (double)B);
+}
+
+// ---- backward finalisation -------------------------------------------------------------------------
+constexpr int kFinWarps = 8;
+constexpr int kFinMaxVec = 8;   // D <= 1024
+
+template <int DTYPE>
+__global__ void __launch_bounds__(kFinWarps * 32)
+finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_local, int D,
+                    const float* __restrict__ scale /* [s, flows] */, const float* __restrict__ grad_out,
+                    const void* __restrict__ x1, const void* __restrict__ x2, int64_t ld1, int64_t ld2,
+                    const float* __restrict__ inv1, const float* __restrict__ inv2, int already,
+                    void* __restrict__ dx1, void* __restrict__ dx2,
+                    const float* __restrict__ dscale_part, int n_dscale, float* __restrict__ dlogit_scale) {
+  const float s = scale[0], g = grad_out[0];
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * kFinWarps + (threadIdx.x >> 5);   // (problem, row)
+  if (gw < 2 * rows_local) {
+    const int p = gw >= rows_local;
+    const int64_t row = gw - (int64_t)p * rows_local;
+    const float* pb = part + ((int64_t)p * n_chunks * rows_local + row) * D;
+    const void* x = p ? x2 : x1;
+    void* dx = p ? dx2 : dx1;
+    const int64_t ld = p ? ld2 : ld1;
+    const int nvec = D >> 2;
+    const float sg = s * g;
+    float4 v[kFinMaxVec], a[kFinMaxVec];
+    float dot = 0.f;
+    const float inv = already ? 1.0f : (p ? inv2 : inv1)[row];
+#pragma unroll
+    for (int k = 0; k < kFinMaxVec; ++k) {
+      int c = lane + 32 * k;
+      if (c < nvec) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          float4 q = __ldg(reinterpret_cast<const float4*>(pb + (int64_t)ch * rows_local * D) + c);
+          acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        acc.x *= sg; acc.y *= sg; acc.z *= sg; acc.w *= sg;
+        v[k] = acc;
+        if (!already) {
+          float4 q = load4<DTYPE>(x, row * ld + 4 * c);
+          q.x *= inv; q.y *= inv; q.z *= inv; q.w *= inv;
+          a[k] = q;
+          dot += q.x * acc.x + q.y * acc.y + q.z * acc.z + q.w * acc.w;
+        }
+      }
+    }
+    if (!already) dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < kFinMaxVec; ++k) {
+      int c = lane + 32 * k;
+      if (c < nvec) {
+        float4 o = v[k];
+        if (!already) {   // (I - a a^T) da / ||x||
+          o.x = (o.x - a[k].x * dot) * inv; o.y = (o.y - a[k].y * dot) * inv;
+          o.z = (o.z - a[k].z * dot) * inv; o.w = (o.w - a[k].w * dot) * inv;
+        }
+        store4<DTYPE>(dx, row * ld + 4 * c, o);
+      }
+    }
+  }
+  if (blockIdx.x == 0 && dlogit_scale) {   // d/dl: g * flows * s * sum G*cos, fixed-order fp64
+    __shared__ double red[kFinWarps * 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_dscale; i += kFinWarps * 32) acc += (double)dscale_part[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kFinWarps * 16; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) *dlogit_scale = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
+  }
+}
+
+int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local,
+                         const float* logit_scale, float scale_cap, const float* diag_cos,
+                         float* row_lse, float* col_lse, float* diag, float* scale_out, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t n = 2 * rows_local;
+  dim3 grid((unsigned)((n + threads - 1) / threads));
+  combine_stats_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
+                                                 rows_local, logit_scale, scale_cap, diag_cos, row_lse, col_lse,
+                                                 diag, scale_out);
+  VPA_LAUNCH_CHECK("combine_stats_kernel");
+  return 0;
+}
+
+int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
+                cudaStream_t st) {
+  loss_kernel<<<1, 1024, 0, st>>>(row_lse, col_lse, diag, B, loss);
+  VPA_LAUNCH_CHECK("loss_kernel");
+  return 0;
+}
+
+int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
+                        const float* scale, const float* grad_out, const void* x1, const void* x2,
+                        int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
+                        int already, void* dx1, void* dx2, float* dlogit_scale, cudaStream_t st) {
+  VPA_CHECK_ARG(D <= 128 * kFinMaxVec, "finalize: D=%d > %d unsupported", D, 128 * kFinMaxVec);
+  const int64_t n = 2 * rows_local;
+  dim3 grid((unsigned)((n + kFinWarps - 1) / kFinWarps)), block(kFinWarps * 32);
+#define VPA_FIN(DT)                                                                                        \
+  finalize_bwd_kernel<DT><<<grid, block, 0, st>>>(ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, grad_out, \
+                                                  x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2,         \
+                                                  ws.dscale_part, plan.n_dscale, dlogit_scale)
+  if (in_dtype == VPA_F32) VPA_FIN(VPA_F32);
+  else if (in_dtype == VPA_BF16) VPA_FIN(VPA_BF16);
+  else VPA_FIN(VPA_F16);
+#undef VPA_FIN
+  VPA_LAUNCH_CHECK("finalize_bwd_kernel");
+  return 0;
+}
+
+}  // namespace vpa

@@ -1,0 +1,163 @@
+// Fused L2-normalise + cast (HBM-bound).  Replaces `x / x.norm(dim=-1, keepdim=True)`
+// (reference loss_head.py:271-273, :38-40) and produces the bf16 tensor-core operands in the
+// same pass.  One warp per row: the row is read ONCE with 16-byte (fp32) / 8-byte (16-bit)
+// coalesced vector loads, kept in registers, reduced with shuffles, and written out.
+// Algorithmic bytes per row: D*(bytes_in + bytes_out) + 4.
+#include "common.cuh"
+
+namespace vpa {
+
+constexpr int kNormWarps = 8;      // warps (rows) per CTA
+constexpr int kMaxVec = 8;         // float4 chunks per lane kept in registers -> D <= 1024
+
+template <int DTYPE, bool IN_REGS>
+__device__ __forceinline__ void normalize_row(const void* x, int64_t ld, int64_t row, int D,
+                                              bool already, __nv_bfloat16* y_bf16, float* y_f32,
+                                              float* inv_norm, int lane, float4 (&keep)[kMaxVec],
+                                              float& inv_out) {
+  const int nvec = D >> 2;
+  const int64_t base = row * ld;
+  float ss = 0.f;
+  if constexpr (IN_REGS) {
+#pragma unroll
+    for (int v = 0; v < kMaxVec; ++v) {
+      int c = lane + 32 * v;
+      if (c < nvec) {
+        keep[v] = load4<DTYPE>(x, base + 4 * c);
+        ss += keep[v].x * keep[v].x + keep[v].y * keep[v].y + keep[v].z * keep[v].z + keep[v].w * keep[v].w;
+      }
+    }
+  } else {
+    for (int c = lane; c < nvec; c += 32) {
+      float4 q = load4<DTYPE>(x, base + 4 * c);
+      ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float nrm = already ? 1.0f : sqrtf(ss);
+  inv_out = 1.0f / nrm;
+  if (lane == 0 && inv_norm) inv_norm[row] = inv_out;
+  const int64_t obase = row * (int64_t)D;
+  auto emit = [&](int c, float4 q) {
+    if (!already) {  // true division, as the reference does (x / norm)
+      q.x = q.x / nrm; q.y = q.y / nrm; q.z = q.z / nrm; q.w = q.w / nrm;
+    }
+    if (y_f32) store4<VPA_F32>(y_f32, obase + 4 * c, q);
+    if (y_bf16) store4<VPA_BF16>(y_bf16, obase + 4 * c, q);
+    return q;
+  };
+  if constexpr (IN_REGS) {
+#pragma unroll
+    for (int v = 0; v < kMaxVec; ++v) {
+      int c = lane + 32 * v;
+      if (c < nvec) keep[v] = emit(c, keep[v]);
+    }
+  } else {
+    for (int c = lane; c < nvec; c += 32) emit(c, load4<DTYPE>(x, base + 4 * c));
+  }
+}
+
+template <int DTYPE, bool IN_REGS>
+__global__ void __launch_bounds__(kNormWarps * 32)
+normalize_cast_kernel(const void* __restrict__ x, int64_t rows, int D, int64_t ld, int already,
+                      __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32,
+                      float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 keep[kMaxVec];
+  float inv;
+  normalize_row<DTYPE, IN_REGS>(x, ld, row, D, already != 0, y_bf16, y_f32, inv_norm, lane, keep, inv);
+}
+
+// Both modalities + the diagonal cosine <a_i, t_i> in one launch (training path).
+template <int DTYPE>
+__global__ void __launch_bounds__(kNormWarps * 32)
+normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int64_t rows, int D,
+                      int64_t ld1, int64_t ld2, int already,
+                      __nv_bfloat16* __restrict__ a_bf16, __nv_bfloat16* __restrict__ t_bf16,
+                      float* __restrict__ a_f32, float* __restrict__ t_f32,
+                      float* __restrict__ inv1, float* __restrict__ inv2,
+                      float* __restrict__ diag_cos, int diag_from_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 ka[kMaxVec], kt[kMaxVec];
+  float i1, i2;
+  normalize_row<DTYPE, true>(x1, ld1, row, D, already != 0, a_bf16, a_f32, inv1, lane, ka, i1);
+  normalize_row<DTYPE, true>(x2, ld2, row, D, already != 0, t_bf16, t_f32, inv2, lane, kt, i2);
+  if (diag_cos) {
+    const int nvec = D >> 2;
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < kMaxVec; ++v) {
+      int c = lane + 32 * v;
+      if (c < nvec) {
+        float4 p = ka[v], q = kt[v];
+        if (diag_from_bf16) {  // what the tensor cores will multiply: bf16-rounded operands
+          p.x = __bfloat162float(__float2bfloat16_rn(p.x)); p.y = __bfloat162float(__float2bfloat16_rn(p.y));
+          p.z = __bfloat162float(__float2bfloat16_rn(p.z)); p.w = __bfloat162float(__float2bfloat16_rn(p.w));
+          q.x = __bfloat162float(__float2bfloat16_rn(q.x)); q.y = __bfloat162float(__float2bfloat16_rn(q.y));
+          q.z = __bfloat162float(__float2bfloat16_rn(q.z)); q.w = __bfloat162float(__float2bfloat16_rn(q.w));
+        }
+        dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) diag_cos[row] = dot;
+  }
+}
+
+static int check_rows(const void* x, int64_t rows, int D, int64_t ld, int in_dtype) {
+  VPA_CHECK_ARG(x != nullptr, "normalize: null input");
+  VPA_CHECK_ARG(rows >= 0 && D > 0 && (D % 4) == 0, "normalize: need rows >= 0, D %% 4 == 0 (D=%d)", D);
+  VPA_CHECK_ARG(ld >= D && (ld % 4) == 0, "normalize: ld must be >= D and a multiple of 4");
+  VPA_CHECK_ARG(in_dtype == VPA_F32 || in_dtype == VPA_BF16 || in_dtype == VPA_F16, "normalize: bad dtype %d", in_dtype);
+  size_t es = in_dtype == VPA_F32 ? 4 : 2;
+  VPA_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % (4 * es)) == 0, "normalize: input not %zu-byte aligned", 4 * es);
+  return 0;
+}
+
+int normalize_cast_launch(const void* x, int in_dtype, int64_t rows, int D, int64_t ld, int already,
+                          void* y_bf16, float* y_f32, float* inv_norm, cudaStream_t st) {
+  if (int e = check_rows(x, rows, D, ld, in_dtype)) return e;
+  if (rows == 0) return 0;
+  dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps)), block(kNormWarps * 32);
+  const bool in_regs = D <= 128 * kMaxVec;
+  auto* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define VPA_NORM(DT)                                                                                  \
+  if (in_regs) normalize_cast_kernel<DT, true><<<grid, block, 0, st>>>(x, rows, D, ld, already, yb, y_f32, inv_norm); \
+  else normalize_cast_kernel<DT, false><<<grid, block, 0, st>>>(x, rows, D, ld, already, yb, y_f32, inv_norm);
+  if (in_dtype == VPA_F32) { VPA_NORM(VPA_F32) }
+  else if (in_dtype == VPA_BF16) { VPA_NORM(VPA_BF16) }
+  else { VPA_NORM(VPA_F16) }
+#undef VPA_NORM
+  VPA_LAUNCH_CHECK("normalize_cast_kernel");
+  return 0;
+}
+
+int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t rows, int D, int64_t ld1,
+                          int64_t ld2, int already, void* a_bf16, void* t_bf16, float* a_f32, float* t_f32,
+                          float* inv1, float* inv2, float* diag_cos, int diag_from_bf16, cudaStream_t st) {
+  if (int e = check_rows(x1, rows, D, ld1, in_dtype)) return e;
+  if (int e = check_rows(x2, rows, D, ld2, in_dtype)) return e;
+  if (rows == 0) return 0;
+  if (D > 128 * kMaxVec) {  // rows too long for the register-resident pair kernel: three launches
+    if (int e = normalize_cast_launch(x1, in_dtype, rows, D, ld1, already, a_bf16, a_f32, inv1, st)) return e;
+    if (int e = normalize_cast_launch(x2, in_dtype, rows, D, ld2, already, t_bf16, t_f32, inv2, st)) return e;
+    return set_error(VPA_E_UNSUPPORTED, "normalize_pair: D=%d > %d needs the diag kernel (not built)", D, 128 * kMaxVec);
+  }
+  dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps)), block(kNormWarps * 32);
+  auto* ab = reinterpret_cast<__nv_bfloat16*>(a_bf16);
+  auto* tb = reinterpret_cast<__nv_bfloat16*>(t_bf16);
+  if (in_dtype == VPA_F32)
+    normalize_pair_kernel<VPA_F32><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
+  else if (in_dtype == VPA_BF16)
+    normalize_pair_kernel<VPA_BF16><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
+  else
+    normalize_pair_kernel<VPA_F16><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
+  VPA_LAUNCH_CHECK("normalize_pair_kernel");
+  return 0;
+}
+
+}  // namespace vpa

@@ -1,0 +1,265 @@
+"""Tensor-level entry points of the B200 InfoNCE / retrieval-scoring path.
+
+PyTorch is used for device memory, streams and ``torch.distributed`` only; all arithmetic runs in
+libvipant_b200.so through the C-ABI (``_cabi``).  No CPU / eager fallback exists: CPU tensors raise.
+
+Reference semantics (``/root/reference/cvap/module/decoder/loss_head.py``):
+  infonce_loss   <- CELossHead.forward :271-283 (+ autograd), global-batch semantics of the
+                    reference's `dp` mode when a process group is given
+  l2_normalize   <- :38-40 / :271-273
+  sim_rank_topk  <- the `x1s @ x2s.t()` + argsort + where pattern of :109-170, :79-107, :381-385
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+_DTYPES = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16, torch.float16: _cabi.F16}
+PRECISIONS = {"bf16": _cabi.PREC_BF16_TC, "fp32": _cabi.PREC_FP32_SIMT}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _cabi.VipantB200Error(
+                "vipant_b200 runs on an sm_100 CUDA device only (got a CPU tensor); there is no CPU fallback")
+
+
+def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    if x.dim() != 2:
+        raise ValueError(f"expected a (rows, D) matrix, got shape {tuple(x.shape)}")
+    if x.dtype not in _DTYPES:
+        x = x.float()
+    if x.stride(1) != 1 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:
+        x = x.contiguous()
+    return x
+
+
+def _resolve_precision(precision: str, D: int) -> int:
+    if precision not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+    return PRECISIONS[precision]
+
+
+def tensor_core_supported(D: int) -> bool:
+    kb = D // 64
+    return D % 64 == 0 and 64 <= D <= 512 and (kb <= 4 or kb % 2 == 0)
+
+
+def l2_normalize(x: torch.Tensor, already_normalized: bool = False) -> torch.Tensor:
+    """fp32 ``x / x.norm(dim=-1, keepdim=True)`` (no eps) via the fused normalise kernel."""
+    _require_cuda(x)
+    x = _rows2d(x)
+    rows, D = x.shape
+    out = torch.empty((rows, D), dtype=torch.float32, device=x.device)
+    if rows:
+        with torch.cuda.device(x.device):
+            _cabi.check(_cabi.lib().vpa_normalize_cast(_ptr(x), _DTYPES[x.dtype], rows, D, x.stride(0),
+                                                       int(already_normalized), None, _ptr(out), None, _stream()),
+                        "vpa_normalize_cast")
+    return out
+
+
+class _CudaKernels:
+    """The compute steps of one InfoNCE step, each a C-ABI call.  This is the only kernel set the package
+    ships; `_sharded_forward/_sharded_backward` take it as a parameter solely so that the row-sharding /
+    collective plumbing can be exercised on CPU (gloo) by the tests with a checker standing in for it."""
+
+    def normalize_pair(self, x1, x2, normalized, precision):
+        lib = _cabi.lib()
+        b, D = x1.shape
+        dev = x1.device
+        tc = precision == _cabi.PREC_BF16_TC
+        fdt = torch.bfloat16 if tc else torch.float32
+        a = torch.empty((b, D), dtype=fdt, device=dev)
+        t = torch.empty((b, D), dtype=fdt, device=dev)
+        inv = torch.empty((2, b), dtype=torch.float32, device=dev)
+        dcos = torch.empty((b,), dtype=torch.float32, device=dev)
+        _cabi.check(lib.vpa_normalize_pair(
+            _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, D, x1.stride(0), x2.stride(0), int(normalized),
+            _ptr(a) if tc else None, _ptr(t) if tc else None, None if tc else _ptr(a), None if tc else _ptr(t),
+            _ptr(inv[0]), _ptr(inv[1]), _ptr(dcos), int(tc), _stream()), "vpa_normalize_pair")
+        return a, t, inv, dcos
+
+    def forward_stats(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, dcos, precision):
+        lib = _cabi.lib()
+        b, D = a.shape
+        B = a_all.shape[0]
+        dev = a.device
+        ws_bytes = lib.vpa_infonce_workspace_bytes(b, B, D, precision)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        stats = torch.empty((3, b), dtype=torch.float32, device=dev)     # row_lse, col_lse, diag
+        scale = torch.empty((2,), dtype=torch.float32, device=dev)       # s, grad-flows flag
+        cap = float(scale_max) if scale_max else 0.0                     # 0 -> no clamp (`or inf`, :254)
+        _cabi.check(lib.vpa_infonce_fwd(
+            _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(logit_scale), cap,
+            _ptr(dcos), _ptr(ws), ws_bytes, _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(scale), _stream()),
+            "vpa_infonce_fwd")
+        return stats, scale, ws
+
+    def loss(self, stats_all):
+        B = stats_all.shape[1]
+        loss = torch.empty((), dtype=torch.float32, device=stats_all.device)
+        _cabi.check(_cabi.lib().vpa_infonce_loss(_ptr(stats_all[0]), _ptr(stats_all[1]), _ptr(stats_all[2]), B,
+                                                 _ptr(loss), _stream()), "vpa_infonce_loss")
+        return loss
+
+    def backward(self, x1, x2, a, t, a_all, t_all, inv, stats_all, scale, ws, row_offset, grad_out, normalized,
+                 precision):
+        lib = _cabi.lib()
+        b, D = a.shape
+        B = a_all.shape[0]
+        dev = a.device
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        dx1 = torch.empty_like(x1)
+        dx2 = torch.empty_like(x2)
+        dls = torch.empty((), dtype=torch.float32, device=dev)
+        _cabi.check(lib.vpa_infonce_bwd(
+            _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(scale),
+            _ptr(stats_all[0]), _ptr(stats_all[1]), _ptr(g), _ptr(x1), _ptr(x2), _DTYPES[x1.dtype],
+            dx1.stride(0), dx2.stride(0), _ptr(inv[0]), _ptr(inv[1]), int(normalized), _ptr(ws), ws.numel(),
+            _ptr(dx1), _ptr(dx2), _ptr(dls), _stream()), "vpa_infonce_bwd")
+        return dx1, dx2, dls
+
+
+_KERNELS = _CudaKernels()
+
+
+def _sharded_forward(kern, x1, x2, logit_scale, scale_max, normalized, precision, group):
+    """Row-sharded global-batch forward: rank r owns rows [r*b, (r+1)*b).
+
+    normalise locally -> all-gather the normalised features -> row logsumexp of the local x1 rows against ALL
+    x2 rows and column logsumexp of the local x2 rows against ALL x1 rows (both complete, no partial
+    statistics to reduce) -> all-gather the three (b,) statistic vectors -> identical global loss on every rank.
+    """
+    b = x1.shape[0]
+    world = dist.get_world_size(group) if group is not None else 1
+    rank = dist.get_rank(group) if group is not None else 0
+    a, t, inv, dcos = kern.normalize_pair(x1, x2, normalized, precision)
+    if world > 1:
+        a_all = torch.empty((b * world, a.shape[1]), dtype=a.dtype, device=a.device)
+        t_all = torch.empty_like(a_all)
+        dist.all_gather_into_tensor(a_all, a, group=group)
+        dist.all_gather_into_tensor(t_all, t, group=group)
+    else:
+        a_all, t_all = a, t
+    stats, scale, ws = kern.forward_stats(a, t, a_all, t_all, rank * b, logit_scale, scale_max, dcos, precision)
+    if world > 1:
+        gathered = torch.empty((world, 3, b), dtype=stats.dtype, device=stats.device)
+        dist.all_gather_into_tensor(gathered, stats.contiguous(), group=group)
+        stats_all = gathered.permute(1, 0, 2).reshape(3, b * world).contiguous()
+    else:
+        stats_all = stats
+    loss = kern.loss(stats_all)
+    saved = (x1, x2, a, t, a_all, t_all, inv, stats_all, scale)
+    return loss, saved, (ws, rank * b, world)
+
+
+def _sharded_backward(kern, saved, extra, grad_out, normalized, precision, group):
+    """dL/d(local rows): two local sweeps (x1 rows vs all x2, x2 rows vs all x1); only the replicated
+    logit_scale gradient needs a (scalar) all-reduce."""
+    x1, x2, a, t, a_all, t_all, inv, stats_all, scale = saved
+    ws, row_offset, world = extra
+    dx1, dx2, dls = kern.backward(x1, x2, a, t, a_all, t_all, inv, stats_all, scale, ws, row_offset, grad_out,
+                                  normalized, precision)
+    if world > 1:
+        dist.all_reduce(dls, group=group)
+    return dx1, dx2, dls
+
+
+class _InfoNCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
+        with torch.cuda.device(x1.device):
+            loss, saved, extra = _sharded_forward(_KERNELS, x1, x2, logit_scale, scale_max, normalized, precision, group)
+        ctx.save_for_backward(*saved)
+        ctx.cfg = (extra, normalized, precision, group)
+        ctx.set_materialize_grads(False)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if grad_out is None:
+            return None, None, None, None, None, None, None
+        extra, normalized, precision, group = ctx.cfg
+        with torch.cuda.device(ctx.saved_tensors[0].device):
+            dx1, dx2, dls = _sharded_backward(_KERNELS, ctx.saved_tensors, extra, grad_out, normalized, precision, group)
+        return dx1, dx2, dls, None, None, None, None
+
+
+def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, scale_max=None,
+                 normalized: bool = False, precision: str = "bf16",
+                 group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
+    """Symmetric InfoNCE  CE(s*a@t.T, arange) + CE(s*t@a.T, arange)  with s = min(exp(logit_scale), scale_max).
+
+    x1, x2: (b, D) CUDA tensors (fp32 / bf16 / fp16), this process's rows.  With ``group`` the loss is the
+    GLOBAL-batch loss over the concatenation of all ranks' rows in rank order (each rank must pass the same b);
+    the returned gradients are d(global loss)/d(local rows), and d/d logit_scale is all-reduced.
+    precision "bf16": tcgen05 tensor cores (needs D in {64,128,192,256,384,512}); "fp32": exact FFMA path.
+    """
+    _require_cuda(x1, x2)
+    x1, x2 = _rows2d(x1), _rows2d(x2)
+    if x1.shape != x2.shape:
+        raise ValueError(f"x1 {tuple(x1.shape)} and x2 {tuple(x2.shape)} must have the same shape")
+    if x1.dtype != x2.dtype:
+        x1, x2 = x1.float(), x2.float()
+    if x1.shape[0] == 0:
+        raise ValueError("empty batch")
+    prec = _resolve_precision(precision, x1.shape[1])
+    if prec == _cabi.PREC_BF16_TC and not tensor_core_supported(x1.shape[1]):
+        raise _cabi.VipantB200Error(f"precision='bf16' needs D in {{64,128,192,256,384,512}}, got D={x1.shape[1]}; "
+                                    "use precision='fp32'")
+    ls = logit_scale
+    if not isinstance(ls, torch.Tensor):
+        ls = torch.tensor(float(ls))
+    if ls.device != x1.device or ls.dtype != torch.float32:
+        # `scaling=False` heads keep a plain CPU tensor (loss_head.py:252); its value is copied, no grad needed
+        ls = ls.to(device=x1.device, dtype=torch.float32)
+    return _InfoNCEFunction.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group)
+
+
+def sim_rank_topk(q: torch.Tensor, k: torch.Tensor, gt: Optional[torch.Tensor] = None, topk: int = 0):
+    """Similarity ``q @ k.T`` (fp32) reduced on the fly to ranks of ground-truth columns and the top-k keys.
+
+    q (N, D), k (M, D): CUDA, converted to fp32.  gt: (N,) or (N, g<=8) integer column indices.
+    Returns (ranks int64 (N, g) or None, topk_idx int64 (N, topk) or None, topk_val fp32 or None);
+    rank = 0-based position of the column in a stable descending sort of the row.
+    """
+    _require_cuda(q, k, gt)
+    q = _rows2d(q.float())
+    k = _rows2d(k.float())
+    N, D = q.shape
+    M = k.shape[0]
+    if k.shape[1] != D:
+        raise ValueError(f"feature dims differ: {D} vs {k.shape[1]}")
+    dev = q.device
+    g = 0
+    gt32 = None
+    if gt is not None:
+        gt32 = gt.reshape(N, -1).to(device=dev, dtype=torch.int32).contiguous()
+        g = gt32.shape[1]
+    ranks = torch.empty((N, g), dtype=torch.int32, device=dev) if g else None
+    idx = torch.empty((N, topk), dtype=torch.int64, device=dev) if topk else None
+    val = torch.empty((N, topk), dtype=torch.float32, device=dev) if topk else None
+    if N:
+        lib = _cabi.lib()
+        with torch.cuda.device(dev):
+            ws_bytes = lib.vpa_sim_workspace_bytes(N, M)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.vpa_sim_rank_topk(_ptr(q), _ptr(k), N, M, D, q.stride(0), k.stride(0), _ptr(gt32), g, topk,
+                                              _ptr(idx), _ptr(val), _ptr(ranks), _ptr(ws), ws_bytes, _stream()),
+                        "vpa_sim_rank_topk")
+    return (ranks.long() if ranks is not None else None), idx, val

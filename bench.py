@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: fused InfoNCE forward+backward, global batch 32768 x 512, bf16 tensor-core mode.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dim D]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
+  normalise+cast both modalities -> [all-gather] -> forward statistics -> loss -> backward (dx1, dx2, dlogit_scale).
+metric  pairs/s = GLOBAL batch / step time   (strong scaling: the global batch is fixed at 32768, rows are
+        sharded over the N ranks, BASELINE.json configs[2])
+value   inputs already resident in HBM, CUDA-event timed, max over ranks
+e2e     the same step through the host-buffer entry (C-ABI vpa_infonce_step_host at N=1, the Python public
+        API with pinned host tensors at N>1): H2D of the embeddings and D2H of loss + gradients inside the
+        timed region
+roofline  the backward sweep kernel (tcgen05), algorithmic 6*b*B*D flops per launch / its CUDA-event time
+cpu_baseline  the oracle's torch-CPU port of the reference arithmetic on a bounded row-block sample
+--impl reference   times that CPU port as the main line (the reference itself cannot travel to the GPU box)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "InfoNCE fwd+bwd pairs/sec at 32Kx512"
+UNIT = "pairs/s"
+SEED = 1213            # the reference's default seed (configs/default.yaml:9)
+RHO = 0.3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32768, help="GLOBAL batch (rows of each modality)")
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fr:
+            p = json.load(fr)
+        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))),
+                    hbm=float(p.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_inputs(B, D, lo, hi):
+    """Rows [lo, hi) of the seeded global batch: x2 = rho*x1 + (1-rho)*randn."""
+    g = torch.Generator().manual_seed(SEED)
+    x1 = torch.randn(B, D, generator=g)
+    x2 = RHO * x1 + (1.0 - RHO) * torch.randn(B, D, generator=g)
+    return x1[lo:hi].contiguous(), x2[lo:hi].contiguous()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_block_sample(B, D, target_s=12.0, reps=None):
+    """Reference arithmetic (oracle torch-CPU port) on a bounded row block of the SAME global batch."""
+    from oracle import infonce_oracle as io
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x1, x2 = make_inputs(B, D, 0, B)
+    x1.requires_grad_(True)
+    x2.requires_grad_(True)
+    ls = torch.tensor(math.log(1 / 0.07), requires_grad=True)
+    b = min(B, 1024)
+    t0 = time.perf_counter()
+    io.infonce_port_block_step(x1, x2, ls, slice(0, b))           # warm-up + calibration
+    t_cal = time.perf_counter() - t0
+    # grow the block so that one step is ~ target_s / 3, capped by memory (4 b x B fp32 buffers live)
+    per_row = t_cal / b
+    b = int(min(B, max(b, (target_s / 3.0) / max(per_row, 1e-9))))
+    b = max(256, min(b, 8192, B) // 256 * 256) if B >= 256 else B
+    return x1, x2, ls, b, cores
+
+
+def run_cpu_steps(x1, x2, ls, b, steps):
+    from oracle import infonce_oracle as io
+    times = []
+    for _ in range(steps):
+        x1.grad = x2.grad = ls.grad = None
+        t0 = time.perf_counter()
+        io.infonce_port_block_step(x1, x2, ls, slice(0, b))
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    B, D = args.batch, args.dim
+    x1, x2, ls, b, cores = cpu_block_sample(B, D)
+    run_cpu_steps(x1, x2, ls, b, max(1, min(args.warmup, 1)))
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    times = []
+    for _ in range(steps):
+        times += run_cpu_steps(x1, x2, ls, b, 1)
+        if time.perf_counter() - t0 > 150:           # keep the whole run within a few minutes
+            break
+    ms = float(np.mean(times) * 1e3)
+    value = b / (ms * 1e-3)
+    sample = (f"row block of {b} of the {B} global rows per step (both logits blocks {b}x{B}, 2x cross entropy, autograd "
+              f"backward; 12*b*B*D executed flops = b/B of the reference's full step), fp32 torch CPU")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"InfoNCE fwd+bwd, global batch {B} x {D}, fp32 CPU reference arithmetic", "global_batch": B,
+                   "dim": D, "sample_rows": b},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (vipant_b200 has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import vipant_b200 as vb
+    from vipant_b200 import _cabi
+    lib = _cabi.lib()
+
+    B, D = args.batch, args.dim
+    assert B % world == 0, "global batch must divide by the number of ranks"
+    b = B // world
+    x1h, x2h = make_inputs(B, D, rank * b, (rank + 1) * b)
+    x1 = x1h.to(dev).requires_grad_(True)
+    x2 = x2h.to(dev).requires_grad_(True)
+    ls = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+    gout = torch.tensor(1.0, device=dev)
+    group = dist.group.WORLD if world > 1 else None
+
+    def step():
+        x1.grad = x2.grad = ls.grad = None
+        loss = vb.infonce_loss(x1, x2, ls, precision=args.precision, group=group)
+        loss.backward(gout)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        loss = step()
+    barrier()
+
+    lib.vpa_profile_enable(1)
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    prof = {}
+    for kind, name in ((0, "normalize"), (1, "fwd_sweep"), (2, "bwd_sweep")):
+        tot, n = ctypes.c_float(), ctypes.c_int()
+        lib.vpa_profile_read(kind, ctypes.byref(tot), ctypes.byref(n))
+        prof[name] = (tot.value, n.value)
+    lib.vpa_profile_enable(0)
+    loss_val = float(loss.item())
+
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = B / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers in, loss + gradients out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 10))
+        h2d = 2 * b * D * 4
+        d2h = 2 * b * D * 4 + 8
+        if world == 1:
+            prec = _cabi.PREC_BF16_TC if args.precision == "bf16" else _cabi.PREC_FP32_SIMT
+            nbytes = lib.vpa_infonce_host_scratch_bytes(B, D, prec)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            hx1, hx2 = x1h.pin_memory(), x2h.pin_memory()
+            hd1, hd2 = torch.empty_like(hx1).pin_memory(), torch.empty_like(hx2).pin_memory()
+            hl, hs = ctypes.c_float(), ctypes.c_float()
+
+            def e2e_step():
+                rc = lib.vpa_infonce_step_host(hx1.data_ptr(), hx2.data_ptr(), B, D, math.log(1 / 0.07), 0.0, 1.0, prec,
+                                               scratch.data_ptr(), nbytes, ctypes.addressof(hl), ctypes.addressof(hs),
+                                               hd1.data_ptr(), hd2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                _cabi.check(rc, "vpa_infonce_step_host")
+                return hl.value
+        else:
+            hx1, hx2 = x1h.pin_memory(), x2h.pin_memory()
+            hd1, hd2 = torch.empty_like(hx1).pin_memory(), torch.empty_like(hx2).pin_memory()
+
+            def e2e_step():
+                d1 = hx1.to(dev, non_blocking=True).requires_grad_(True)
+                d2 = hx2.to(dev, non_blocking=True).requires_grad_(True)
+                ls.grad = None
+                l = vb.infonce_loss(d1, d2, ls, precision=args.precision, group=group)
+                l.backward(gout)
+                hd1.copy_(d1.grad, non_blocking=True)
+                hd2.copy_(d2.grad, non_blocking=True)
+                return float(l.item())
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_loss = e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": B / dt.item(), "unit": UNIT, "ms_per_step": dt.item() * 1e3, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "entry": "vpa_infonce_step_host (C-ABI, pinned host buffers)" if world == 1 else
+                        "vipant_b200.infonce_loss + backward (pinned host tensors, per rank)",
+               "loss": e2e_loss}
+
+    if rank == 0:
+        pk = peaks()
+        bwd_ms, bwd_n = prof["bwd_sweep"]
+        fwd_ms, fwd_n = prof["fwd_sweep"]
+        nrm_ms, nrm_n = prof["normalize"]
+        roofline = None
+        if bwd_n:
+            flops = 6.0 * b * B * D                         # S recompute + dX1 + dX2 contractions
+            ach = flops / (bwd_ms / bwd_n * 1e-3) / 1e12
+            roofline = {"kernel": "sweep_kernel<BWD> (tcgen05)", "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
+                        "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+                        "algorithmic_flops_per_launch": flops, "avg_launch_ms": bwd_ms / bwd_n, "launches": bwd_n}
+        step_flops = 8.0 * b * B * D
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"InfoNCE fwd+bwd (CELossHead), global batch {B} x {D}, {args.precision} mode, "
+                                   f"rows sharded over {world} rank(s)", "global_batch": B, "dim": D, "rows_per_rank": b,
+                       "parallelism": f"row-shard x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                       "l2": "no explicit flush: inputs + operands + partials per step exceed the 126 MB L2",
+                       "seed": SEED, "rho": RHO},
+            "loss": loss_val,
+            "step_tflops_algorithmic_8B2D": step_flops / (ms_step * 1e-3) / 1e12,
+            "step_frac_of_peak": step_flops / (ms_step * 1e-3) / 1e12 / pk["tflops"],
+            "kernel_ms": {"normalize_pair": nrm_ms / max(nrm_n, 1), "fwd_sweep": fwd_ms / max(fwd_n, 1),
+                          "bwd_sweep": bwd_ms / max(bwd_n, 1)},
+            "normalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 2) + 12 * b) / (nrm_ms / max(nrm_n, 1) * 1e-3) / 1e9 if nrm_n else None,
+                              "peak_gbs": pk["hbm"]},
+            "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": 6 * args.steps,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cx1, cx2, cls_, cb, cores = cpu_block_sample(B, D)
+            times = run_cpu_steps(cx1, cx2, cls_, cb, 2)
+            v = cb / float(np.mean(times))
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"row block of {cb} of the {B} global rows x2 steps (torch fp32 CPU port of "
+                                              f"loss_head.py:271-283 + autograd; 12*b*B*D flops = b/B of a full step)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,18 @@ extern "C" {
 int vpa_version(void);
 const char* vpa_last_error_string(void);
 
+/* Opt-in launch timing for measurement (bench.py): when enabled, the library brackets its dominant kernels
+ * with CUDA events on the launch stream.  kind: 0 normalise, 1 forward sweep, 2 backward sweep, 3 similarity,
+ * 4 rank/top-k.  vpa_profile_read synchronises on the recorded events, returns the summed kernel time and the
+ * number of launches since the last read, and resets the counter.  Off by default; not thread-safe. */
+#define VPA_PROF_NORMALIZE 0
+#define VPA_PROF_FWD_SWEEP 1
+#define VPA_PROF_BWD_SWEEP 2
+#define VPA_PROF_SIM 3
+#define VPA_PROF_RANK 4
+int vpa_profile_enable(int on);
+int vpa_profile_read(int kind, float* total_ms, int* launches);
+
 /* ------------------------------------------------------------------------------------------
  * L2 normalisation + cast.  Replaces  x / x.norm(dim=-1, keepdim=True)
  *   loss_head.py:271-273 (CELossHead.forward), :38-40 (LossHead.infer); no epsilon, a zero

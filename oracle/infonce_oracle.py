@@ -174,3 +174,30 @@ def make_pair(B, D=512, rho=0.3, seed=1213, dtype="float32"):
     x1 = torch.randn(B, D, generator=g)
     x2 = rho * x1 + (1.0 - rho) * torch.randn(B, D, generator=g)
     return x1.numpy().astype(dtype), x2.numpy().astype(dtype)
+
+
+def infonce_port_block_step(x1, x2, logit_scale, rows, scale_max=None, normalized=False):
+    """One rank's share of a global-batch step in the reference's CPU arithmetic (torch fp32 + autograd).
+
+    The reference forms the full B x B logits twice (loss_head.py:277-278); a bounded SAMPLE of that work is
+    the row block `rows` (a slice): logits of those x1 rows against all x2 rows and of those x2 rows against
+    all x1 rows, both cross entropies, and autograd backward -- 12*b*B*D executed flops, exactly b/B of the
+    reference's 12*B^2*D.  Used only by bench.py's cpu_baseline / --impl reference legs.
+    Returns the (partial) loss tensor after calling backward().
+    """
+    import torch
+
+    if not normalized:
+        a = x1 / x1.norm(dim=-1, keepdim=True)
+        t = x2 / x2.norm(dim=-1, keepdim=True)
+    else:
+        a, t = x1, x2
+    s = logit_scale.exp().clamp(max=(scale_max or float("inf")))
+    labels = torch.arange(rows.start, rows.stop)
+    l12 = (s * a[rows]) @ t.t()
+    l21 = (s * t[rows]) @ a.t()
+    ce = torch.nn.functional.cross_entropy
+    loss = ce(l12, labels, reduction="sum") + ce(l21, labels, reduction="sum")
+    loss = loss / x1.shape[0]
+    loss.backward()
+    return loss

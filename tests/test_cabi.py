@@ -1,0 +1,85 @@
+"""The C-ABI library loads on a CPU-only machine and exports every symbol include/vipant_b200.h declares.
+
+No compute call is made here (there is no GPU); argument validation paths that return before touching the
+device ARE exercised, because they are part of the drop-in contract (errors are codes, never exceptions/aborts).
+"""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from vipant_b200 import _cabi, build
+
+HEADER = os.path.join(ROOT, "include", "vipant_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()          # no-op when up to date; nvcc cross-compiles sm_100a without a GPU
+    return _cabi.lib()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vpa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_cabi.EXPORTED_SYMBOLS)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    raw = ctypes.CDLL(_cabi.library_path())
+    for name in declared_symbols():
+        assert hasattr(raw, name), f"{name} declared in include/vipant_b200.h but not exported"
+
+
+def test_version(lib):
+    assert lib.vpa_version() == 100
+
+
+def test_only_c_symbols_are_public():
+    """The boundary is extern "C": no torch / C++-mangled API symbols are exported by name vpa_*."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _cabi.library_path()], capture_output=True, text=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if l.strip()]
+    assert all(n in names for n in declared_symbols())
+    assert not any("torch" in n or "c10" in n for n in names)
+
+
+def test_workspace_queries_are_pure(lib):
+    assert lib.vpa_infonce_workspace_bytes(0, 0, 512, 0) == 0
+    assert lib.vpa_infonce_workspace_bytes(512, 512, 512, 0) > 0
+    assert lib.vpa_infonce_workspace_bytes(512, 512, 512, 1) > 0
+    assert lib.vpa_sim_workspace_bytes(975, 4875) >= 975 * 4875 * 4
+    assert lib.vpa_sim_workspace_bytes(0, 10) == 0
+    assert lib.vpa_infonce_host_scratch_bytes(64, 512, 0) > 2 * 64 * 512 * 4
+
+
+def test_invalid_arguments_return_codes_not_crashes(lib):
+    # null pointers / bad shapes are rejected before any device work
+    assert lib.vpa_normalize_cast(None, 0, 4, 512, 512, 0, None, None, None, None) == -1
+    assert b"null" in lib.vpa_last_error_string()
+    one = ctypes.c_float(0.0)
+    p = ctypes.addressof(one)
+    assert lib.vpa_normalize_cast(p, 0, 4, 510, 510, 0, None, None, None, None) == -1       # D % 4
+    assert lib.vpa_normalize_cast(p, 7, 4, 512, 512, 0, None, None, None, None) == -1       # dtype
+    assert lib.vpa_infonce_loss(None, None, None, 8, None, None) == -1
+    # D = 96 is not covered by the tensor-core tiling -> UNSUPPORTED (-3), fp32 path accepts it
+    rc = lib.vpa_infonce_fwd(p, p, p, p, 0, 8, 8, 96, 0, p, 0.0, p, p, 1 << 20, p, p, p, p, None)
+    assert rc == -3
+    rc = lib.vpa_infonce_fwd(p, p, p, p, 0, 8, 4, 512, 0, p, 0.0, p, p, 1 << 20, p, p, p, p, None)
+    assert rc == -1                                                                          # rows_global < rows_local
+    rc = lib.vpa_infonce_fwd(p, p, p, p, 0, 512, 512, 512, 0, p, 0.0, p, p, 16, p, p, p, p, None)
+    assert rc == -2                                                                          # workspace too small
+    assert lib.vpa_sim_rank_topk(p, p, 4, 4, 512, 512, 512, None, 0, 1, None, None, None, p, 0, None) == -2
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_LIB", None)
+    monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.VipantB200Error, match="no CPU or PyTorch fallback"):
+        _cabi.lib()

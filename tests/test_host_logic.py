@@ -1,0 +1,177 @@
+"""Host-side mirror of the reference loss-head API (vipant_b200/loss_head.py), CPU only.
+
+Covers what does not need a GPU: construction / registry / checkpoint keys, the no-CPU-fallback contract, the
+report-string arithmetic fed with the reference's golden ranks, and the row-sharded multi-process plumbing
+(world_size 2, gloo) with an oracle-backed checker standing in for the CUDA kernel set.
+"""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden
+import vipant_b200 as vb
+from vipant_b200 import _cabi, functional as F_
+from oracle import infonce_oracle as io
+from oracle.reference_loader import Cfg
+
+
+def test_registry_and_ctor_contract():
+    head = vb.build_loss_head(Cfg(name="CELossHead", scaling=True, scale_max=None))
+    assert isinstance(head, vb.CELossHead) and isinstance(head, vb.LossHead)
+    assert head.normalized is True and head.reduce is False
+    assert isinstance(head.logit_scale, torch.nn.Parameter) and head.logit_scale.shape == ()
+    assert head.logit_scale.item() == pytest.approx(math.log(1 / 0.07), rel=1e-6)
+    assert list(head.state_dict().keys()) == ["logit_scale"]          # checkpoint key (cvap/model/cvap.py:112)
+    assert head.scale_max == float("inf")
+    assert vb.CELossHead(Cfg(scaling=True, scale_max=0)).scale_max == float("inf")      # `or inf` (:254)
+    assert vb.CELossHead(Cfg(scaling=True, scale_max=100.0)).scale_max == 100.0
+    fixed = vb.CELossHead(Cfg(scaling=False, scale_max=None))
+    assert not isinstance(fixed.logit_scale, torch.nn.Parameter) and fixed.logit_scale.item() == 0.0
+    assert list(fixed.state_dict().keys()) == []
+    with pytest.raises(KeyError):
+        vb.build_loss_head(Cfg(name="NoSuchHead"))
+
+
+def test_copy_state_dict_roundtrip():
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None))
+    head.copy_state_dict({"logit_scale": torch.tensor(4.6052), "unrelated": torch.zeros(3)})
+    assert head.logit_scale.item() == pytest.approx(4.6052)
+    head2 = vb.CELossHead(Cfg(scaling=True, scale_max=None))
+    head2.load_state_dict(head.state_dict())
+    assert head2.logit_scale.item() == pytest.approx(4.6052)
+
+
+def test_no_cpu_fallback():
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None)).train()
+    with pytest.raises(_cabi.VipantB200Error, match="no CPU fallback"):
+        head(torch.randn(8, 64), torch.randn(8, 64))
+    head.eval()
+    with pytest.raises(_cabi.VipantB200Error, match="no CPU fallback"):
+        head(torch.randn(8, 64), torch.randn(8, 64))
+    with pytest.raises(_cabi.VipantB200Error):
+        vb.sim_rank_topk(torch.randn(4, 64), torch.randn(5, 64), topk=1)
+
+
+def test_composites_build_the_fused_head():
+    val = vb.build_loss_head(Cfg(name="VALCELossHead", scaling=True, scale_max=None, va=False, lv=False, al=True))
+    assert val.loss_head_va is None and val.loss_head_lv is None and isinstance(val.loss_head_al, vb.CELossHead)
+    assert val.stats(nstep=1) == "al 0.000"
+    va = vb.build_loss_head(Cfg(name="VACELossHead", scaling=True, scale_max=None, vp=True, ap=False, va=True, vv=False,
+                                aa=False, vp_w=1., ap_w=1., va_w=1., vv_w=1., aa_w=1.))
+    assert isinstance(va.loss_head_vp, vb.CELossHead) and va.loss_head_ap is None
+    assert sorted(k for k in va.state_dict()) == ["loss_head_va.logit_scale", "loss_head_vp.logit_scale"]
+
+
+def test_report_strings_from_golden_ranks(strings):
+    g = load_golden("retrieval_1v5")
+    r12 = torch.from_numpy(g["r12"].astype(np.int64))
+    r21 = torch.from_numpy(g["r21"].astype(np.int64))
+    ref_lines = strings["retrieval_1v5"].split("\nREFERENCE\n")[1]
+    assert vb.LossHead._retrieval_eval_from_ranks(r12, r21) == ref_lines
+    assert vb.LossHead.retrieval_metrics(r21.float(), msg="T->A") == ref_lines.split("\n")[1]
+
+
+def test_install_into_reference():
+    from oracle import reference_loader as rl
+    if not rl.available():
+        pytest.skip("reference tree not mounted (GPU box)")
+    ref = rl.load_reference_loss_head()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_copy_for_install", ref.__file__)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    vb.install_into_reference(mod)
+    head = mod.build_loss_head(Cfg(name="CELossHead", scaling=True, scale_max=None))
+    assert type(head) is vb.CELossHead
+    comp = mod.build_loss_head(Cfg(name="VALCELossHead", scaling=True, scale_max=None, va=False, lv=False, al=True))
+    assert type(comp) is vb.VALCELossHead
+
+
+# ------------------------------------------------------------------- multi-process plumbing on gloo
+class _CheckerKernels:
+    """fp64 torch-CPU stand-in for functional._CudaKernels (same method contract), test-only: lets the
+    all-gather / row-offset / scalar all-reduce logic of _sharded_forward/_sharded_backward run on gloo."""
+
+    def normalize_pair(self, x1, x2, normalized, precision):
+        x1, x2 = x1.double(), x2.double()
+        if normalized:
+            n1, n2 = torch.ones(len(x1), dtype=torch.float64), torch.ones(len(x2), dtype=torch.float64)
+            a, t = x1, x2
+        else:
+            n1, n2 = x1.norm(dim=-1), x2.norm(dim=-1)
+            a, t = x1 / n1[:, None], x2 / n2[:, None]
+        return a, t, torch.stack([1 / n1, 1 / n2]), (a * t).sum(-1)
+
+    def forward_stats(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, dcos, precision):
+        s, flows = io.effective_scale(float(logit_scale), scale_max)
+        stats = torch.stack([torch.logsumexp(s * a @ t_all.T, 1), torch.logsumexp(s * t @ a_all.T, 1), s * dcos])
+        return stats, torch.tensor([s, float(flows)], dtype=torch.float64), None
+
+    def loss(self, stats_all):
+        return ((stats_all[0] - stats_all[2]).mean() + (stats_all[1] - stats_all[2]).mean())
+
+    def backward(self, x1, x2, a, t, a_all, t_all, inv, stats_all, scale, ws, row_offset, grad_out, normalized, precision):
+        s, flows = float(scale[0]), float(scale[1])
+        B, b = a_all.shape[0], a.shape[0]
+        idx = torch.arange(b)
+        S = s * a @ t_all.T
+        G = torch.exp(S - stats_all[0][row_offset:row_offset + b, None]) + torch.exp(S - stats_all[1][None, :])
+        G[idx, idx + row_offset] -= 2.0
+        G *= float(grad_out) / B
+        da = s * G @ t_all
+        dls = (G * S).sum() * flows
+        St = s * t @ a_all.T
+        Gt = torch.exp(St - stats_all[1][row_offset:row_offset + b, None]) + torch.exp(St - stats_all[0][None, :])
+        Gt[idx, idx + row_offset] -= 2.0
+        Gt *= float(grad_out) / B
+        dt = s * Gt @ a_all
+        if not normalized:
+            da = (da - a * (a * da).sum(-1, keepdim=True)) * inv[0][:, None]
+            dt = (dt - t * (t * dt).sum(-1, keepdim=True)) * inv[1][:, None]
+        return da, dt, dls
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, B, D, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x1n, x2n = io.make_pair(B, D, 0.3, 21)
+        b = B // world
+        x1 = torch.from_numpy(x1n[rank * b:(rank + 1) * b])
+        x2 = torch.from_numpy(x2n[rank * b:(rank + 1) * b])
+        ls = torch.tensor(math.log(1 / 0.07))
+        kern = _CheckerKernels()
+        loss, saved, extra = F_._sharded_forward(kern, x1, x2, ls, None, False, 0, dist.group.WORLD)
+        dx1, dx2, dls = F_._sharded_backward(kern, saved, extra, torch.tensor(2.0), False, 0, dist.group.WORLD)
+        out[rank] = (float(loss), dx1.numpy(), dx2.numpy(), float(dls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_row_sharded_plumbing_gloo(world):
+    B, D = 48, 32
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, D, out), nprocs=world, join=True)
+    x1n, x2n = io.make_pair(B, D, 0.3, 21)
+    ref = io.infonce_closed_form(x1n, x2n, float(np.float32(math.log(1 / 0.07))), grad_output=2.0)
+    b = B // world
+    for r in range(world):
+        loss, dx1, dx2, dls = out[r]
+        assert loss == pytest.approx(ref.loss, rel=1e-10)                      # same GLOBAL loss on every rank
+        assert dls == pytest.approx(ref.dlogit_scale, rel=1e-9)                # all-reduced scalar
+        np.testing.assert_allclose(dx1, ref.dx1[r * b:(r + 1) * b], atol=1e-12)
+        np.testing.assert_allclose(dx2, ref.dx2[r * b:(r + 1) * b], atol=1e-12)

@@ -17,6 +17,33 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- opt-in launch timing ---------------------------------------------------------------------------
+constexpr int kProfSlots = 512;
+struct ProfState {
+  bool on = false;
+  cudaEvent_t ev[PROF_KINDS][kProfSlots][2];
+  bool made[PROF_KINDS][kProfSlots];
+  int n[PROF_KINDS];
+};
+static ProfState g_prof;
+
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n[kind] >= kProfSlots) return;
+  const int i = g_prof.n[kind];
+  if (!g_prof.made[kind][i]) {
+    if (cudaEventCreate(&g_prof.ev[kind][i][0]) != cudaSuccess || cudaEventCreate(&g_prof.ev[kind][i][1]) != cudaSuccess) return;
+    g_prof.made[kind][i] = true;
+  }
+  cudaEventRecord(g_prof.ev[kind][i][0], st);
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n[kind] >= kProfSlots) return;
+  const int i = g_prof.n[kind];
+  if (!g_prof.made[kind][i]) return;
+  cudaEventRecord(g_prof.ev[kind][i][1], st);
+  g_prof.n[kind] = i + 1;
+}
+
 // launchers defined in the other translation units
 int normalize_cast_launch(const void* x, int in_dtype, int64_t rows, int D, int64_t ld, int already,
                           void* y_bf16, float* y_f32, float* inv_norm, cudaStream_t st);
@@ -129,6 +156,27 @@ extern "C" {
 int vpa_version(void) { return VPA_VERSION; }
 
 const char* vpa_last_error_string(void) { return g_err; }
+
+int vpa_profile_enable(int on) {
+  g_prof.on = on != 0;
+  for (int k = 0; k < PROF_KINDS; ++k) g_prof.n[k] = 0;
+  return 0;
+}
+
+int vpa_profile_read(int kind, float* total_ms, int* launches) {
+  VPA_CHECK_ARG(kind >= 0 && kind < PROF_KINDS && total_ms && launches, "profile_read: bad argument");
+  float tot = 0.f;
+  for (int i = 0; i < g_prof.n[kind]; ++i) {
+    VPA_CUDA(cudaEventSynchronize(g_prof.ev[kind][i][1]));
+    float ms = 0.f;
+    VPA_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[kind][i][0], g_prof.ev[kind][i][1]));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *launches = g_prof.n[kind];
+  g_prof.n[kind] = 0;
+  return 0;
+}
 
 int vpa_normalize_cast(const void* x, int in_dtype, int64_t rows, int D, int64_t ld, int already_normalized,
                        void* y_bf16, float* y_f32, float* inv_norm, void* stream) {

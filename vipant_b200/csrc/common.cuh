@@ -32,6 +32,12 @@ int set_error(int code, const char* fmt, ...);
       return ::vpa::set_error((int)e__, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+// ---- opt-in launch timing (vpa_profile_*): CUDA events recorded on the launch stream around the
+// dominant kernels; used by bench.py for the roofline numbers, off by default (no cost, no state).
+enum { PROF_NORMALIZE = 0, PROF_FWD_SWEEP = 1, PROF_BWD_SWEEP = 2, PROF_SIM = 3, PROF_RANK = 4, PROF_KINDS = 5 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+
 // ---- device helpers ----------------------------------------------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

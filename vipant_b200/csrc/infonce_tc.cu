@@ -548,7 +548,9 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
     attr_set[MODE] = true;
   }
   dim3 grid(2 * P.units_per_problem), block(kThreads);
+  prof_begin(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
   sweep_kernel<MODE><<<grid, block, L.total, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  prof_end(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
   VPA_LAUNCH_CHECK(bwd ? "sweep_kernel<BWD>" : "sweep_kernel<FWD>");
   return 0;
 }

@@ -150,12 +150,14 @@ int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t 
   dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps)), block(kNormWarps * 32);
   auto* ab = reinterpret_cast<__nv_bfloat16*>(a_bf16);
   auto* tb = reinterpret_cast<__nv_bfloat16*>(t_bf16);
+  prof_begin(PROF_NORMALIZE, st);
   if (in_dtype == VPA_F32)
     normalize_pair_kernel<VPA_F32><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
   else if (in_dtype == VPA_BF16)
     normalize_pair_kernel<VPA_BF16><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
   else
     normalize_pair_kernel<VPA_F16><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
+  prof_end(PROF_NORMALIZE, st);
   VPA_LAUNCH_CHECK("normalize_pair_kernel");
   return 0;
 }

@@ -123,12 +123,16 @@ int sim_rank_topk_launch(const float* Q, const float* K, int64_t N, int64_t M, i
     const unsigned want = (unsigned)((4 * 148 + gx - 1) / gx);
     if (gy > want) gy = want;
     if (gy < 1) gy = 1;
+    prof_begin(PROF_SIM, st);
     sim_store_kernel<<<dim3(gx, gy), kSimThreads, smem, st>>>(Q, K, N, M, D, ldq, ldk, S);
+    prof_end(PROF_SIM, st);
     VPA_LAUNCH_CHECK("sim_store_kernel");
   }
   if (g > 0 || k > 0) {
     const unsigned gx = (unsigned)((N + kRankWarps - 1) / kRankWarps);
+    prof_begin(PROF_RANK, st);
     rank_topk_kernel<<<gx, kRankWarps * 32, 0, st>>>(S, N, M, gt_idx, g, k, topk_idx, topk_val, ranks);
+    prof_end(PROF_RANK, st);
     VPA_LAUNCH_CHECK("rank_topk_kernel");
   }
   return 0;

@@ -158,9 +158,9 @@ def _sharded_forward(kern, x1, x2, logit_scale, scale_max, normalized, precision
         a_all, t_all = a, t
     stats, scale, ws = kern.forward_stats(a, t, a_all, t_all, rank * b, logit_scale, scale_max, dcos, precision)
     if world > 1:
-        gathered = torch.empty((world, 3, b), dtype=stats.dtype, device=stats.device)
+        gathered = torch.empty((world * 3, b), dtype=stats.dtype, device=stats.device)
         dist.all_gather_into_tensor(gathered, stats.contiguous(), group=group)
-        stats_all = gathered.permute(1, 0, 2).reshape(3, b * world).contiguous()
+        stats_all = gathered.view(world, 3, b).permute(1, 0, 2).reshape(3, b * world).contiguous()
     else:
         stats_all = stats
     loss = kern.loss(stats_all)

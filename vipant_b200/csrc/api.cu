@@ -1,6 +1,7 @@
 // extern "C" surface of libvipant_b200.so (see include/vipant_b200.h) + work planning.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -111,9 +112,15 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
   p.n_iblk = (int)((rows_local + 127) / 128);
   p.n_tiles = (int)((rows_global + 127) / 128);
   p.halves = D > 256 ? 2 : 1;
-  pick_chunks(2 * p.n_iblk, p.n_tiles, 2, &p.fwd_chunks, &p.fwd_tiles_per_chunk);
-  pick_chunks(2 * p.n_iblk * p.halves, p.n_tiles, 3, &p.bwd_chunks, &p.bwd_tiles_per_chunk);
-  p.n_dscale = p.n_iblk * p.halves * p.bwd_chunks;
+  p.cluster = p.n_iblk >= 2 ? 2 : 1;      // measured on B200 at B=32768: 2 is best (4 strands SMs, 1 doubles L2 reads)
+  if (const char* e = getenv("VPA_CLUSTER")) {       // tuning knob for measurements: 1, 2 or 4
+    const int c = atoi(e);
+    if (c == 1 || c == 2 || c == 4) p.cluster = c;
+  }
+  const int padded = (p.n_iblk + p.cluster - 1) / p.cluster * p.cluster;
+  pick_chunks(2 * padded, p.n_tiles, 2, &p.fwd_chunks, &p.fwd_tiles_per_chunk);
+  pick_chunks(2 * padded * p.halves, p.n_tiles, 3, &p.bwd_chunks, &p.bwd_tiles_per_chunk);
+  p.n_dscale = padded * p.halves * p.bwd_chunks;
   return p;
 }
 

@@ -116,6 +116,7 @@ struct SweepPlan {
   int bwd_chunks, bwd_tiles_per_chunk;
   int halves;               // backward: D split into 1 or 2 accumulator halves (TMEM capacity)
   int n_dscale;             // number of partial sums of G*cos written by the backward sweep
+  int cluster;              // tensor-core path: CTAs per cluster sharing one multicast Y stream (1, 2 or 4)
 };
 SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision);
 

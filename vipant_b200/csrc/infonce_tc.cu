@@ -49,8 +49,9 @@ struct Problem {
 
 struct Params {
   Problem p[2];
-  int units_per_problem;    // n_iblk * halves * n_chunks
+  int units_per_problem;    // CTAs per problem = n_igroups * cluster * halves * n_chunks
   int n_iblk, halves, n_chunks, tiles_per_chunk, n_tiles;
+  int cluster, n_igroups;   // CTAs per cluster (1, 2 or 4) sweeping the SAME Y tiles; row-block groups
   int D, kboxes;            // kboxes = D / 64
   int stages;
   const float* logit_scale; // FWD
@@ -71,25 +72,40 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.
+// Bounded wait: a protocol bug must abort the kernel (trap) instead of hanging the GPU.  try_wait suspends
+// the thread in hardware for a bounded time, so the loop body runs rarely; the bound is an iteration count
+// (no clock reads or integer division on the critical path of the single-thread issue loops).
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("vipant_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  asm volatile("trap;");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s
-      printf("vipant_b200: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      asm volatile("trap;");
-    }
-  }
+  if (mbar_try(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity))
+    if (++spins > (1u << 24)) mbar_timeout(bar, parity);
+}
+// true for exactly one lane of a converged warp (the lane that issues the asynchronous instructions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -97,6 +113,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+// One slice of a box, written to the same shared-memory offset of every CTA in `mask`; each destination
+// CTA's mbarrier (same offset) receives the complete_tx for the bytes that landed in ITS shared memory.
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -125,6 +160,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // mbarrier arrive when every previously issued MMA of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Same, arriving on the barrier at this offset in every CTA of `mask` (frees a multicast ring stage).
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base + t).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -198,15 +238,21 @@ sweep_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CU
   const SmemLayout L = smem_layout(MODE, P.kboxes, P.stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- unit decode: chunk-major so that concurrently running CTAs stream the same Y tiles (L2 reuse)
+  // ---- unit decode.  The `cluster` CTAs of a cluster own consecutive row blocks and sweep the SAME Y tiles
+  // (same problem / chunk / half): every Y box is fetched from L2 once per cluster (each CTA loads 1/cluster
+  // of it and multicasts), which divides the L2 -> SM traffic -- the measured bound of the v1 kernel -- by `cluster`.
   int u = blockIdx.x;
   const int prob = u >= P.units_per_problem;
-  u -= prob * P.units_per_problem;
-  const int per_chunk = P.n_iblk * P.halves;
-  const int chunk = u / per_chunk;
-  const int rem = u - chunk * per_chunk;
-  const int iblk = rem / P.halves;
-  const int half = rem - iblk * P.halves;
+  u -= prob * P.units_per_problem;           // CTA index within the problem (also the dscale slot)
+  const int crank = P.cluster > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << P.cluster) - 1u);
+  const int cl = u / P.cluster;              // cluster index within the problem
+  const int per_chunk = P.n_igroups * P.halves;
+  const int chunk = cl / per_chunk;
+  const int rem = cl - chunk * per_chunk;
+  const int igroup = rem / P.halves;
+  const int half = rem - igroup * P.halves;
+  const int iblk = igroup * P.cluster + crank;   // may be >= n_iblk in the last group: rows masked, TMA zero-fills
   const Problem& pb = P.p[prob];
   const CUtensorMap* mapx = prob ? &mx1 : &mx0;
   const CUtensorMap* mapy = prob ? &my1 : &my0;
@@ -228,7 +274,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CU
     mbar_init(bar(B_GFULL), kEpiThreads);
     mbar_init(bar(B_GEMPTY), 1);
     mbar_init(bar(B_DXFULL), 1);
-    for (int s = 0; s < P.stages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
+    for (int s = 0; s < P.stages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), P.cluster); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(mapx);
     prefetch_tmap(mapy);
@@ -237,84 +283,106 @@ sweep_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CU
   if (warp == 1) tmem_alloc(sbase + L.tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (P.cluster > 1) cluster_sync_all();     // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =========================== TMA producer (one lane) ===========================
-    if (lane == 0) {
+    // =========================== TMA producer: converged warp, one elected lane issues ===========================
+    const bool leader = elect_one();
+    if (leader) {
       mbar_arrive_expect_tx(bar(B_XFULL), P.kboxes * kBoxBytes);
       for (int kb = 0; kb < P.kboxes; ++kb)
         tma_load_2d(sbase + L.x + kb * kBoxBytes, mapx, kb * kBoxK, iblk * kBM, bar(B_XFULL));
-      int it = 0;
-      auto push = [&](int c0, int c1) {
-        const int s = it % P.stages;
-        mbar_wait(ring_empty(s), ((it / P.stages) & 1) ^ 1);
-        mbar_arrive_expect_tx(ring_full(s), kBoxBytes);
-        tma_load_2d(sbase + L.ring + s * kBoxBytes, mapy, c0, c1, ring_full(s));
-        ++it;
-      };
-      for (int j = 0; j < nt; ++j) {
-        for (int kb = 0; kb < P.kboxes; ++kb) push(kb * kBoxK, (tile0 + j) * kBN);                 // S(j)
-        if (MODE == MODE_BWD && j >= 1)
-          for (int hb = 0; hb < hboxes; ++hb) push((half * hboxes + hb) * kBoxK, (tile0 + j - 1) * kBN);  // dX(j-1)
-      }
-      if (MODE == MODE_BWD)
-        for (int hb = 0; hb < hboxes; ++hb) push((half * hboxes + hb) * kBoxK, (tile0 + nt - 1) * kBN);
     }
+    const int slice_rows = kBN / P.cluster;            // this CTA's share of every Y box
+    const int row_shift = crank * slice_rows;
+    const uint32_t ring0 = sbase + L.ring + (uint32_t)row_shift * 128u;
+    int stage = 0;
+    uint32_t phase = 0;
+    auto push = [&](int c0, int c1) {
+      mbar_wait(ring_empty(stage), phase ^ 1);       // every CTA of the cluster has drained this stage
+      if (leader) {
+        mbar_arrive_expect_tx(ring_full(stage), kBoxBytes);
+        if (P.cluster > 1)
+          tma_load_2d_mcast(ring0 + stage * kBoxBytes, mapy, c0, c1 + row_shift, ring_full(stage), cmask);
+        else
+          tma_load_2d(ring0 + stage * kBoxBytes, mapy, c0, c1, ring_full(stage));
+      }
+      if (++stage == P.stages) { stage = 0; phase ^= 1; }
+    };
+    const int d0 = half * hboxes * kBoxK;
+    for (int j = 0; j < nt; ++j) {
+      const int r = (tile0 + j) * kBN;
+      for (int kb = 0; kb < P.kboxes; ++kb) push(kb * kBoxK, r);                               // S(j)
+      if (MODE == MODE_BWD && j >= 1)
+        for (int hb = 0; hb < hboxes; ++hb) push(d0 + hb * kBoxK, r - kBN);                     // dX(j-1)
+    }
+    if (MODE == MODE_BWD)
+      for (int hb = 0; hb < hboxes; ++hb) push(d0 + hb * kBoxK, (tile0 + nt - 1) * kBN);
   } else if (warp == 1) {
-    // =========================== MMA issuer (one lane) ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);      // S: both operands K-major
-      constexpr uint32_t idesc_dx = make_idesc(kBM, 64, 0, 1);      // dX: A = G K-major, B = Y MN-major, N = 64
-      int it = 0;
-      mbar_wait(bar(B_XFULL), 0);
+    // =========================== MMA issuer: converged warp, one elected lane issues ===========================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);      // S: both operands K-major
+    constexpr uint32_t idesc_dx = make_idesc(kBM, 64, 0, 1);      // dX: A = G K-major, B = Y MN-major, N = 64
+    // descriptor templates; only the 14-bit start-address field (units of 16 B) changes per instruction
+    const uint64_t dk = make_desc(sbase, 16, 1024);               // K-major SW128 operand at smem base
+    const uint64_t dmn = make_desc(sbase, kBoxBytes, 1024);       // MN-major SW128 operand at smem base
+    const uint32_t ring_u = (L.ring) >> 4, x_u = (L.x) >> 4, g_u = (L.g) >> 4;
+    constexpr uint32_t box_u = kBoxBytes >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    auto release = [&](int st) {        // the stage may be refilled once EVERY CTA of the cluster has consumed it
+      if (P.cluster > 1) umma_commit_mcast(ring_empty(st), cmask);
+      else umma_commit(ring_empty(st));
+    };
+    mbar_wait(bar(B_XFULL), 0);
+    tc_fence_after();
+    auto issue_dx = [&](int t) {
+      mbar_wait(bar(B_GFULL), t & 1);
       tc_fence_after();
-      auto issue_dx = [&](int t) {
-        mbar_wait(bar(B_GFULL), t & 1);
+      for (int hb = 0; hb < hboxes; ++hb) {
+        mbar_wait(ring_full(stage), phase);
         tc_fence_after();
-        for (int hb = 0; hb < hboxes; ++hb) {
-          const int s = it % P.stages;
-          mbar_wait(ring_full(s), (it / P.stages) & 1);
-          tc_fence_after();
-          const uint32_t ybox = sbase + L.ring + s * kBoxBytes;
+        if (leader) {
+          const uint64_t db0 = dmn + (uint64_t)(ring_u + stage * box_u);
 #pragma unroll
           for (int kk = 0; kk < kBN / 16; ++kk) {   // K = 16 rows of Y (j) per instruction
-            const uint64_t da = make_desc(sbase + L.g + (kk >> 2) * kBoxBytes + (kk & 3) * 32, 16, 1024);
-            const uint64_t db = make_desc(ybox + kk * 2048, kBoxBytes, 1024);
-            umma_f16(tmem_base + 256 + hb * 64, da, db, idesc_dx, (t > 0 || kk > 0) ? 1u : 0u);
+            const uint64_t da = dk + (uint64_t)(g_u + (kk >> 2) * box_u + (kk & 3) * 2);
+            umma_f16(tmem_base + 256 + hb * 64, da, db0 + (uint64_t)(kk * 128), idesc_dx, (t > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(ring_empty(s));
-          ++it;
+          release(stage);
+          if (hb == hboxes - 1) umma_commit(bar(B_GEMPTY));
         }
-        umma_commit(bar(B_GEMPTY));
-      };
-      for (int j = 0; j < nt; ++j) {
-        const int b = j & 1;
-        mbar_wait(bar(B_TEMPTY0 + b), ((j >> 1) & 1) ^ 1);
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+      }
+    };
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      mbar_wait(bar(B_TEMPTY0 + b), ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < P.kboxes; ++kb) {
+        mbar_wait(ring_full(stage), phase);
         tc_fence_after();
-        for (int kb = 0; kb < P.kboxes; ++kb) {
-          const int s = it % P.stages;
-          mbar_wait(ring_full(s), (it / P.stages) & 1);
-          tc_fence_after();
-          const uint32_t xbox = sbase + L.x + kb * kBoxBytes;
-          const uint32_t ybox = sbase + L.ring + s * kBoxBytes;
+        if (leader) {
+          const uint64_t da0 = dk + (uint64_t)(x_u + kb * box_u);
+          const uint64_t db0 = dk + (uint64_t)(ring_u + stage * box_u);
 #pragma unroll
-          for (int k = 0; k < kBoxK / 16; ++k) {
-            const uint64_t da = make_desc(xbox + k * 32, 16, 1024);
-            const uint64_t db = make_desc(ybox + k * 32, 16, 1024);
-            umma_f16(tmem_base + b * kBN, da, db, idesc_s, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(ring_empty(s));
-          ++it;
+          for (int k = 0; k < kBoxK / 16; ++k)
+            umma_f16(tmem_base + b * kBN, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_s, (kb > 0 || k > 0) ? 1u : 0u);
+          release(stage);
+          if (kb == P.kboxes - 1) umma_commit(bar(B_TFULL0 + b));
         }
-        umma_commit(bar(B_TFULL0 + b));
-        if (MODE == MODE_BWD && j >= 1) issue_dx(j - 1);
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1; }
       }
-      if (MODE == MODE_BWD) {
-        issue_dx(nt - 1);
-        umma_commit(bar(B_DXFULL));
-      }
+      if (MODE == MODE_BWD && j >= 1) issue_dx(j - 1);
+    }
+    if (MODE == MODE_BWD) {
+      issue_dx(nt - 1);
+      if (leader) umma_commit(bar(B_DXFULL));
+      __syncwarp();
     }
   } else {
     // =========================== epilogue warps (128 threads, thread = row) ===========================
@@ -449,7 +517,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CU
         const float v = warp_sum(dsc);
         if (lane == 0) red[sub] = v;
         epi_bar_sync();
-        if (et == 0) pb.dscale[u] = (half == 0) ? ((red[0] + red[1]) + (red[2] + red[3])) : 0.f;
+        if (et == 0) pb.dscale[u] = (half == 0) ? ((red[0] + red[1]) + (red[2] + red[3])) : 0.f;   // u: CTA slot
       }
     }
   }
@@ -459,6 +527,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (P.cluster > 1) cluster_sync_all();     // no CTA exits while a peer may still multicast into it / arrive on it
 }
 
 // ---------------------------------------------------------------- host side
@@ -479,12 +548,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // [rows][D] bf16 row-major, box = 128 rows x 64 elements, 128-byte swizzle, zero fill out of bounds.
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D) {
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(VPA_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)D * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBoxK, (cuuint32_t)kBM};
+  cuuint32_t box[2] = {(cuuint32_t)kBoxK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -508,8 +577,8 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
                   "operands must be 16-byte aligned");
   CUtensorMap maps[4];
   for (int p = 0; p < 2; ++p) {
-    if (int e = make_map(&maps[2 * p + 0], a.x[p], a.rows_local, a.D)) return e;
-    if (int e = make_map(&maps[2 * p + 1], a.y[p], a.rows_global, a.D)) return e;
+    if (int e = make_map(&maps[2 * p + 0], a.x[p], a.rows_local, a.D, kBM)) return e;
+    if (int e = make_map(&maps[2 * p + 1], a.y[p], a.rows_global, a.D, kBN / plan.cluster)) return e;
   }
   Params P{};
   const bool bwd = MODE == MODE_BWD;
@@ -518,7 +587,9 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.n_chunks = bwd ? plan.bwd_chunks : plan.fwd_chunks;
   P.tiles_per_chunk = bwd ? plan.bwd_tiles_per_chunk : plan.fwd_tiles_per_chunk;
   P.n_tiles = plan.n_tiles;
-  P.units_per_problem = P.n_iblk * P.halves * P.n_chunks;
+  P.cluster = plan.cluster;
+  P.n_igroups = (P.n_iblk + P.cluster - 1) / P.cluster;
+  P.units_per_problem = P.n_igroups * P.cluster * P.halves * P.n_chunks;
   P.D = a.D;
   P.kboxes = a.D / 64;
   P.stages = pick_stages(MODE, P.kboxes);
@@ -547,9 +618,20 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
     VPA_CUDA(cudaFuncSetAttribute(sweep_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set[MODE] = true;
   }
-  dim3 grid(2 * P.units_per_problem), block(kThreads);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * P.units_per_problem);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = P.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   prof_begin(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
-  sweep_kernel<MODE><<<grid, block, L.total, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  VPA_CUDA(cudaLaunchKernelEx(&cfg, sweep_kernel<MODE>, maps[0], maps[1], maps[2], maps[3], P));
   prof_end(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
   VPA_LAUNCH_CHECK(bwd ? "sweep_kernel<BWD>" : "sweep_kernel<FWD>");
   return 0;

@@ -80,8 +80,8 @@ static int sm_count() {
 
 // Number of column chunks that minimises (waves x per-unit length) for `base_units` row-block units
 // sweeping `n_tiles` tiles; `fixed` = per-unit fixed cost in tile equivalents (X load, drain).
-static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk) {
-  const int sms = sm_count();
+static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int sms_per_unit = 1) {
+  const int sms = sm_count() / sms_per_unit;
   long best_cost = -1;
   int best_c = 1;
   const int cmax = n_tiles < 64 ? n_tiles : 64;
@@ -109,6 +109,20 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
     return p;
   }
   p.rows_per_blk = 128;
+  p.impl = (D == 256 || D == 512) ? 1 : 0;
+  if (const char* e = getenv("VPA_TC_IMPL")) p.impl = (atoi(e) == 1 && (D == 256 || D == 512)) ? 1 : 0;   // A/B knob
+  if (p.impl == 1) {
+    p.cluster = 2;
+    p.halves = 1;
+    p.n_iblk = (int)((rows_local + 127) / 128);
+    p.pair_fwd_iblk = (int)((rows_local + 255) / 256);
+    p.pair_bwd_iblk = (int)((rows_local + 127) / 128);
+    p.n_tiles = (int)((rows_global + 255) / 256);
+    pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
+    pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 1, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
+    p.n_dscale = 2 * p.pair_bwd_iblk * p.bwd_chunks;
+    return p;
+  }
   p.n_iblk = (int)((rows_local + 127) / 128);
   p.n_tiles = (int)((rows_global + 127) / 128);
   p.halves = D > 256 ? 2 : 1;
@@ -220,7 +234,8 @@ int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, con
   a.logit_scale = logit_scale;
   a.scale_cap = (scale_max > 0.f) ? scale_max : INFINITY;     // `cfg.scale_max or float("inf")`
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int e = (precision == VPA_PREC_BF16_TC) ? tc_infonce_fwd(a, ws, plan, st) : simt_infonce_fwd(a, ws, plan, st)) return e;
+  if (int e = (precision == VPA_PREC_BF16_TC) ? (plan.impl == 1 ? pair_infonce_fwd(a, ws, plan, st) : tc_infonce_fwd(a, ws, plan, st))
+                                              : simt_infonce_fwd(a, ws, plan, st)) return e;
   return combine_stats_launch(ws, plan, rows_local, logit_scale, a.scale_cap, diag_cos, row_lse, col_lse, diag, scale_out, st);
 }
 
@@ -252,7 +267,8 @@ int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, con
   a.lse_x[0] = row_lse_all; a.lse_y[0] = col_lse_all;   // problem 0: rows of S
   a.lse_x[1] = col_lse_all; a.lse_y[1] = row_lse_all;   // problem 1: columns of S
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int e = (precision == VPA_PREC_BF16_TC) ? tc_infonce_bwd(a, ws, plan, st) : simt_infonce_bwd(a, ws, plan, st)) return e;
+  if (int e = (precision == VPA_PREC_BF16_TC) ? (plan.impl == 1 ? pair_infonce_bwd(a, ws, plan, st) : tc_infonce_bwd(a, ws, plan, st))
+                                              : simt_infonce_bwd(a, ws, plan, st)) return e;
   return finalize_bwd_launch(ws, plan, rows_local, D, scale, grad_out, x1, x2, in_dtype, ld1, ld2, inv_norm1, inv_norm2,
                              already_normalized, dx1, dx2, dlogit_scale, st);
 }

@@ -117,6 +117,9 @@ struct SweepPlan {
   int halves;               // backward: D split into 1 or 2 accumulator halves (TMEM capacity)
   int n_dscale;             // number of partial sums of G*cos written by the backward sweep
   int cluster;              // tensor-core path: CTAs per cluster sharing one multicast Y stream (1, 2 or 4)
+  int impl;                 // tensor-core path: 0 = single-CTA kernels (infonce_tc.cu), 1 = CTA-pair kernels (infonce_pair.cu)
+  int pair_fwd_iblk;        // pair kernels: 256-row blocks (forward) / 128-row blocks (backward); n_tiles counts 256-row tiles
+  int pair_bwd_iblk;
 };
 SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision);
 
@@ -145,6 +148,8 @@ struct SweepArgs {
 
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int tc_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 

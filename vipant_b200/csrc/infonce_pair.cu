@@ -1,0 +1,618 @@
+// InfoNCE sweeps on CTA PAIRS (tcgen05 cta_group::2): two SMs of one TPC execute every MMA together, each
+// holding half of the B operand, so the shared-memory operand traffic per SM drops below the 128 B/clk the
+// tensor core can read -- the bound of the single-CTA kernel (infonce_tc.cu, tensor pipe 51 % active, ncu).
+//
+// forward (MODE_FWD)   pair = 256 X rows (128 per CTA, resident in shared memory), tile = 256 Y rows:
+//     S = X . Y^T      UMMA M=256 N=256 K=16, fp32 in TMEM (128 lanes x 256 columns per CTA, double-buffered);
+//     epilogue warps keep an online (max, sum exp2) per row -> per-chunk partial statistics.
+// backward (MODE_BWD)  pair = 128 X rows (64 per CTA).  UMMA M=128 in cta_group::2 puts 64 rows in each CTA
+//     with the N columns folded over the two lane halves (lanes 0-63: columns [0,N/2), lanes 64-127: [N/2,N)),
+//     so a 64 x 512 fp32 dX accumulator needs only 256 TMEM columns per CTA and leaves 2 x 128 columns for a
+//     double-buffered 64 x 256 logit tile: S recompute and the dX contraction run in ONE sweep with NO
+//     duplicated work (the single-CTA kernel recomputes S once per D-half):
+//       S_ij = X_i . Y_j^T                          (32 x UMMA M128 N256 K16 per 256-row tile)
+//       G_ij = (exp(S-lse_x) + exp(S-lse_y) - 2 delta)/B   in registers -> bf16 -> shared memory (K-major SW128)
+//       dX_i += G_ij . Y_j                          (2 x 16 x UMMA M128 N256 K16, B operand = Y MN-major)
+// Both "problems" (A against T, T against A) run in one launch.  Work per step at D = 512:
+// forward 4 B^2 D flops (S and S^T), backward 8 B^2 D; the B x B logits only ever exist as TMEM tiles.
+//
+// Reference semantics: loss_head.py:277-283 (logits + 2 x cross entropy) and its autograd.
+#include <cuda.h>
+
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace vpa {
+namespace pr {
+
+constexpr int kBN = 256;                      // Y rows per tile (UMMA N of the S product); 128 loaded by each CTA
+constexpr int kBoxK = 64;                     // bf16 elements per 128-byte swizzle row
+constexpr int kYBox = 128 * 128;              // one TMA box of Y: [128 rows][64 elems] = 16 KB
+constexpr int kStage = 2 * kYBox;             // ring stage: two boxes (32 KB)
+constexpr int kStages = 3;
+constexpr int kThreads = 192;                 // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2..5: epilogue
+constexpr uint32_t kSmemLimit = 232448;
+
+enum { MODE_FWD = 0, MODE_BWD = 1 };
+
+struct Problem {
+  int n_x, n_y;
+  int diag_offset;
+  const float* lse_x;
+  const float* lse_y;
+  float* out;               // FWD: float2[n_chunks][n_x]; BWD: float[n_chunks][n_x][D]
+  float* dscale;            // BWD problem 0: one partial per CTA; nullptr otherwise
+};
+
+struct Params {
+  Problem p[2];
+  int pairs_per_problem;    // n_iblk * n_chunks
+  int n_iblk, n_chunks, tiles_per_chunk, n_tiles;
+  int D, kboxes, nblk;      // kboxes = D / 64; nblk = D / 256 accumulator blocks (BWD)
+  const float* logit_scale;
+  float scale_cap;
+  const float* scale;
+  float inv_B, ln_B;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (cluster address), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("vipant_b200(pair): mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity))
+    if (++spins > (1u << 21)) mbar_timeout(bar, parity);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+// TMA load executed by either CTA of the pair into ITS shared memory; the bytes are accounted on the
+// LEADER CTA's mbarrier (`leader_bar` is a shared::cluster address).
+__device__ __forceinline__ void tma_load_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] . B[smem] over the CTA pair, issued by ONE thread of the leader CTA.
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, 128B swizzle (see infonce_tc.cu::make_desc)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- shared-memory carve-up (identical in both CTAs)
+template <int MODE>
+struct Cfg {
+  static constexpr int RC = (MODE == MODE_FWD) ? 128 : 64;     // X rows per CTA
+  static constexpr int RP = 2 * RC;                            // X rows per pair
+  static constexpr int XBox = RC * 128;                        // one [RC rows][64 elems] box
+};
+struct SmemLayout {
+  uint32_t x, g, ring, cl, red, bars, tmem_slot, total;
+};
+template <int MODE>
+__host__ __device__ inline SmemLayout smem_layout(int kboxes) {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.x = o; o += kboxes * Cfg<MODE>::XBox;
+  L.g = o; o += (MODE == MODE_BWD) ? 2 * 32768 : 0;            // two G buffers: [64 rows][256 j] bf16 each
+  L.ring = o; o += kStages * kStage;
+  L.cl = o; o += 256 * 4;
+  L.red = o; o += 64;
+  L.bars = o; o += 32 * 8;
+  L.tmem_slot = o; o += 16;
+  L.total = o + 1024;
+  return L;
+}
+// barrier indices
+enum { B_XFULL = 0, B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_GFULL0, B_GFULL1, B_GEMPTY0, B_GEMPTY1, B_DXFULL,
+       B_RFULL, B_REMPTY = B_RFULL + kStages, B_COUNT = B_REMPTY + kStages };
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
+            const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1, const Params P) {
+  using C = Cfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const SmemLayout L = smem_layout<MODE>(P.kboxes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
+  const bool is_leader = crank == 0;
+
+  int u = blockIdx.x >> 1;                             // pair index
+  const int prob = u >= P.pairs_per_problem;
+  u -= prob * P.pairs_per_problem;
+  const int chunk = u / P.n_iblk;
+  const int iblk = u - chunk * P.n_iblk;
+  const Problem& pb = P.p[prob];
+  const CUtensorMap* mapx = prob ? &mx1 : &mx0;
+  const CUtensorMap* mapy = prob ? &my1 : &my0;
+  const int tile0 = chunk * P.tiles_per_chunk;
+  const int nt = min(P.tiles_per_chunk, P.n_tiles - tile0);
+  const int row0 = iblk * C::RP + (int)crank * C::RC;   // first local X row of this CTA
+
+  const uint32_t bar0 = sbase + L.bars;
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  auto lbar = [&](int i) { return mapa(bar0 + 8u * i, 0); };      // the leader's copy (cluster address)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sptr + L.tmem_slot);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(B_XFULL), 1);
+    mbar_init(bar(B_TFULL0), 1);
+    mbar_init(bar(B_TFULL1), 1);
+    mbar_init(bar(B_TEMPTY0), 8);        // one arrival per epilogue warp of BOTH CTAs (leader's copy is used)
+    mbar_init(bar(B_TEMPTY1), 8);
+    mbar_init(bar(B_GFULL0), 8);
+    mbar_init(bar(B_GFULL1), 8);
+    mbar_init(bar(B_GEMPTY0), 1);
+    mbar_init(bar(B_GEMPTY1), 1);
+    mbar_init(bar(B_DXFULL), 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(B_RFULL + s), 1); mbar_init(bar(B_REMPTY + s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prefetch_tmap(mapx);
+    prefetch_tmap(mapy);
+  }
+  if (warp == 1) tmem_alloc2(sbase + L.tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer (both CTAs; each fills ITS half of every operand) ===========================
+    const bool elected = elect_one();
+    if (elected) {
+      if (is_leader) mbar_arrive_expect_tx(bar(B_XFULL), 2 * P.kboxes * C::XBox);
+      const uint32_t xf = lbar(B_XFULL);
+      for (int kb = 0; kb < P.kboxes; ++kb) tma_load_2sm(sbase + L.x + kb * C::XBox, mapx, kb * kBoxK, row0, xf);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    // one ring stage = two boxes at (c0a, r), (c0b, r)
+    auto push = [&](int c0a, int c0b, int r) {
+      mbar_wait(bar(B_REMPTY + stage), phase ^ 1);
+      if (elected) {
+        if (is_leader) mbar_arrive_expect_tx(bar(B_RFULL + stage), 2 * kStage);
+        const uint32_t fb = lbar(B_RFULL + stage);
+        const uint32_t dst = sbase + L.ring + stage * kStage;
+        tma_load_2sm(dst, mapy, c0a, r, fb);
+        tma_load_2sm(dst + kYBox, mapy, c0b, r, fb);
+      }
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    };
+    auto push_dx = [&](int t) {       // Y rows of tile t as the MN-major B operand: this CTA's 128 of every 256 d columns
+      for (int jh = 0; jh < 2; ++jh)
+        for (int nb = 0; nb < P.nblk; ++nb) {
+          const int d0 = nb * 256 + (int)crank * 128;
+          push(d0, d0 + 64, (tile0 + t) * kBN + jh * 128);
+        }
+    };
+    for (int j = 0; j < nt; ++j) {
+      const int r = (tile0 + j) * kBN + (int)crank * 128;      // this CTA's half of the tile's Y rows
+      for (int kb = 0; kb < P.kboxes; kb += 2) push(kb * kBoxK, (kb + 1) * kBoxK, r);
+      if (MODE == MODE_BWD && j >= 1) push_dx(j - 1);
+    }
+    if (MODE == MODE_BWD) push_dx(nt - 1);
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA only) ===========================
+    if (is_leader) {
+      const bool elected = elect_one();
+      constexpr uint32_t idesc_s = make_idesc(C::RP, kBN, 0, 0);
+      constexpr uint32_t idesc_dx = make_idesc(128, 256, 0, 1);
+      const uint64_t dk = make_desc(sbase, 16, 1024);            // K-major SW128 operand template
+      const uint64_t dmn = make_desc(sbase, kYBox, 1024);        // MN-major: two 64-column atoms, 16 KB apart
+      const uint32_t ring_u = L.ring >> 4, x_u = L.x >> 4, g_u = L.g >> 4;
+      constexpr uint32_t xbox_u = C::XBox >> 4, ybox_u = kYBox >> 4, stage_u = kStage >> 4;
+      const uint32_t s_cols = (MODE == MODE_FWD) ? 256u : 128u;  // TMEM columns of one S buffer
+      int stage = 0;
+      uint32_t phase = 0;
+      mbar_wait(bar(B_XFULL), 0);
+      tc_fence_after();
+      auto issue_dx = [&](int t) {
+        const int g = t & 1;
+        mbar_wait(bar(B_GFULL0 + g), (t >> 1) & 1);
+        tc_fence_after();
+        for (int jh = 0; jh < 2; ++jh)
+          for (int nb = 0; nb < P.nblk; ++nb) {
+            mbar_wait(bar(B_RFULL + stage), phase);
+            tc_fence_after();
+            if (elected) {
+              const uint64_t db0 = dmn + (uint64_t)(ring_u + stage * stage_u);
+              const uint64_t da0 = dk + (uint64_t)(g_u + g * 2048 + jh * 1024);       // G buffer g, boxes 2*jh, 2*jh+1 (8 KB each)
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)       // 16 Y rows (j) per instruction
+                umma2_f16(tmem_base + 256 + nb * 128, da0 + (uint64_t)((kk >> 2) * 512 + (kk & 3) * 2), db0 + (uint64_t)(kk * 128),
+                          idesc_dx, (t > 0 || jh > 0 || kk > 0) ? 1u : 0u);
+              umma2_commit(bar(B_REMPTY + stage));
+              if (jh == 1 && nb == P.nblk - 1) umma2_commit(bar(B_GEMPTY0 + g));
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+      };
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        mbar_wait(bar(B_TEMPTY0 + b), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < P.kboxes; kb += 2) {
+          mbar_wait(bar(B_RFULL + stage), phase);
+          tc_fence_after();
+          if (elected) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint64_t da0 = dk + (uint64_t)(x_u + (kb + h) * xbox_u);
+              const uint64_t db0 = dk + (uint64_t)(ring_u + stage * stage_u + h * ybox_u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma2_f16(tmem_base + b * s_cols, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc_s,
+                          (kb > 0 || h > 0 || k > 0) ? 1u : 0u);
+            }
+            umma2_commit(bar(B_REMPTY + stage));
+            if (kb + 2 >= P.kboxes) umma2_commit(bar(B_TFULL0 + b));
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (MODE == MODE_BWD && j >= 1) issue_dx(j - 1);
+      }
+      if (MODE == MODE_BWD) {
+        issue_dx(nt - 1);
+        if (elected) umma2_commit(bar(B_DXFULL));
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== epilogue warps (128 threads per CTA) ===========================
+    const int sub = warp & 3;                         // TMEM sub-partition (lanes 32*sub .. +32) this warp may access
+    const uint32_t t_lane = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const int et = threadIdx.x - 64;                  // 0..127
+    if (MODE == MODE_FWD) {
+      const int row = row0 + sub * 32 + lane;         // lane = row (128 rows per CTA)
+      const bool row_ok = row < pb.n_x;
+      const float s2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
+        tc_fence_after();
+        const int col0 = (tile0 + j) * kBN;
+        const bool edge = col0 + kBN > pb.n_y;
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + b * 256 + c * 32, r);
+          tmem_ld_wait();
+          if (edge) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col0 + c * 32 + e >= pb.n_y) r[e] = 0xff800000u;   // -inf
+          }
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) cmax = fmaxf(cmax, __uint_as_float(r[e]));
+          const float mn = fmaxf(m, cmax * s2);
+          if (mn != -INFINITY) {
+            l *= ex2_approx(m - mn);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              a0 += ex2_approx(fmaf(__uint_as_float(r[e + 0]), s2, -mn));
+              a1 += ex2_approx(fmaf(__uint_as_float(r[e + 1]), s2, -mn));
+              a2 += ex2_approx(fmaf(__uint_as_float(r[e + 2]), s2, -mn));
+              a3 += ex2_approx(fmaf(__uint_as_float(r[e + 3]), s2, -mn));
+            }
+            l += (a0 + a1) + (a2 + a3);
+            m = mn;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lbar(B_TEMPTY0 + b));
+      }
+      if (row_ok) reinterpret_cast<float2*>(pb.out)[(int64_t)chunk * pb.n_x + row] = make_float2(m, l);
+    } else {
+      // 2x2 TMEM layout of M=128 cta_group::2: lanes 0-63 hold this CTA's 64 rows x columns [0,128) of the tile,
+      // lanes 64-127 the same rows x columns [128,256).
+      const int r_in = (sub & 1) * 32 + lane;         // row within the CTA's 64
+      const int jh = sub >> 1;                        // which 128-column half of the tile this thread owns
+      const int row = row0 + r_in;
+      const bool row_ok = row < pb.n_x;
+      const float s2 = P.scale[0] * kLog2e;
+      const float lb = P.ln_B;
+      const float rl2 = row_ok ? (pb.lse_x[pb.diag_offset + row] + lb) * kLog2e : INFINITY;
+      const int dcol = row + pb.diag_offset;
+      float* cl_s = reinterpret_cast<float*>(sptr + L.cl);
+      float dsc = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        const int col0 = (tile0 + j) * kBN;
+        epi_bar_sync();                               // everyone is done reading the previous tile's column lse
+        for (int q = et; q < kBN; q += 128) {
+          const int cj = col0 + q;
+          cl_s[q] = (cj < pb.n_y) ? (pb.lse_y[cj] + lb) * kLog2e : INFINITY;   // +inf masks columns past n_y
+        }
+        epi_bar_sync();
+        mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
+        tc_fence_after();
+        const int cbase = col0 + jh * 128;
+        const bool has_diag = row_ok && dcol >= cbase && dcol < cbase + 128;
+        uint8_t* gbuf = sptr + L.g + b * 32768;       // G buffer = tile parity
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + b * 128 + c * 32, r);
+          tmem_ld_wait();
+          uint32_t packed[16];
+          const float4* cl4 = reinterpret_cast<const float4*>(cl_s + jh * 128 + c * 32);
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 cl = cl4[e4];
+            const float clv[4] = {cl.x, cl.y, cl.z, cl.w};
+            float gv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float acc = __uint_as_float(r[e4 * 4 + q]);
+              float g = ex2_approx(fmaf(acc, s2, -rl2)) + ex2_approx(fmaf(acc, s2, -clv[q]));
+              if (clv[q] == INFINITY) g = 0.f;
+              gv[q] = g;
+            }
+            if (has_diag) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (cbase + c * 32 + e4 * 4 + q == dcol) gv[q] -= 2.0f * P.inv_B;
+            }
+            if (!row_ok) { gv[0] = gv[1] = gv[2] = gv[3] = 0.f; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dsc = fmaf(gv[q], __uint_as_float(r[e4 * 4 + q]), dsc);
+            packed[e4 * 2 + 0] = pack_bf16x2(gv[0], gv[1]);
+            packed[e4 * 2 + 1] = pack_bf16x2(gv[2], gv[3]);
+          }
+          if (c == 0 && j >= 2) mbar_wait(bar(B_GEMPTY0 + b), ((j >> 1) - 1) & 1);   // dX(j-2) has consumed this G buffer
+          // K-major SW128: box (64 j columns, 8 KB) = jh*2 + (c >> 1); row = r_in; 16-byte chunk index XOR (row & 7)
+          uint8_t* gbox = gbuf + (jh * 2 + (c >> 1)) * 8192 + r_in * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk16 = ((c & 1) * 4 + q) ^ (r_in & 7);
+            *reinterpret_cast<uint4*>(gbox + chunk16 * 16) =
+                make_uint4(packed[q * 4 + 0], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();               // generic-proxy writes of G -> visible to the tensor cores
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(lbar(B_TEMPTY0 + b));
+          mbar_arrive_cluster(lbar(B_GFULL0 + b));
+        }
+      }
+      // ---- drain dX: TMEM -> registers -> fp32 partial.  Block nb: lanes 0-63 = d [nb*256, +128), 64-127 = d [nb*256+128, +128)
+      mbar_wait(bar(B_DXFULL), 0);
+      tc_fence_after();
+      float* orow = pb.out + ((int64_t)chunk * pb.n_x + row) * P.D;
+      for (int nb = 0; nb < P.nblk; ++nb) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_lane + 256 + nb * 128 + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* dst = orow + nb * 256 + jh * 128 + c * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<uint4*>(dst)[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+          }
+        }
+      }
+      if (pb.dscale) {                      // fixed-order block reduction of sum G*cos
+        float* red = reinterpret_cast<float*>(sptr + L.red);
+        const float v = warp_sum(dsc);
+        if (lane == 0) red[sub] = v;
+        epi_bar_sync();
+        if (et == 0) pb.dscale[blockIdx.x - prob * 2 * P.pairs_per_problem] = (red[0] + red[1]) + (red[2] + red[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // neither CTA frees TMEM / exits while the pair may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_error(VPA_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBoxK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VPA_E_INVALID, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+template <int MODE>
+static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
+  VPA_CHECK_ARG(a.D == 256 || a.D == 512, "pair kernels need D in {256, 512} (D=%d)", a.D);
+  VPA_CHECK_ARG(a.rows_global < (1ll << 30), "rows_global too large");
+  CUtensorMap maps[4];
+  for (int p = 0; p < 2; ++p) {
+    if (int e = make_map(&maps[2 * p + 0], a.x[p], a.rows_local, a.D, Cfg<MODE>::RC)) return e;
+    if (int e = make_map(&maps[2 * p + 1], a.y[p], a.rows_global, a.D, 128)) return e;
+  }
+  Params P{};
+  const bool bwd = MODE == MODE_BWD;
+  P.n_iblk = bwd ? plan.pair_bwd_iblk : plan.pair_fwd_iblk;
+  P.n_chunks = bwd ? plan.bwd_chunks : plan.fwd_chunks;
+  P.tiles_per_chunk = bwd ? plan.bwd_tiles_per_chunk : plan.fwd_tiles_per_chunk;
+  P.n_tiles = plan.n_tiles;
+  P.pairs_per_problem = P.n_iblk * P.n_chunks;
+  P.D = a.D;
+  P.kboxes = a.D / 64;
+  P.nblk = a.D / 256;
+  P.logit_scale = a.logit_scale;
+  P.scale_cap = a.scale_cap;
+  P.scale = a.scale;
+  P.inv_B = 1.0f / (float)a.rows_global;
+  P.ln_B = logf((float)a.rows_global);
+  for (int p = 0; p < 2; ++p) {
+    P.p[p].n_x = (int)a.rows_local;
+    P.p[p].n_y = (int)a.rows_global;
+    P.p[p].diag_offset = (int)a.row_offset;
+    P.p[p].lse_x = a.lse_x[p];
+    P.p[p].lse_y = a.lse_y[p];
+    if (bwd) {
+      P.p[p].out = ws.bwd_part + (int64_t)p * P.n_chunks * a.rows_local * a.D;
+      P.p[p].dscale = p == 0 ? ws.dscale_part : nullptr;
+    } else {
+      P.p[p].out = ws.fwd_part + (int64_t)p * P.n_chunks * a.rows_local * 2;
+      P.p[p].dscale = nullptr;
+    }
+  }
+  const SmemLayout L = smem_layout<MODE>(P.kboxes);
+  if (L.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", L.total);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[MODE]) {
+    VPA_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    attr_set[MODE] = true;
+  }
+  dim3 grid(2 * 2 * P.pairs_per_problem), block(kThreads);
+  prof_begin(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
+  pair_kernel<MODE><<<grid, block, L.total, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  prof_end(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
+  VPA_LAUNCH_CHECK(bwd ? "pair_kernel<BWD>" : "pair_kernel<FWD>");
+  return 0;
+}
+
+}  // namespace pr
+
+int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
+  return pr::launch<pr::MODE_FWD>(a, ws, plan, st);
+}
+int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
+  return pr::launch<pr::MODE_BWD>(a, ws, plan, st);
+}
+
+}  // namespace vpa

@@ -77,7 +77,7 @@ def test_ragged_shapes(precision, B, D):
     tol = TOL[precision]
     assert abs(loss - ref.loss) <= tol["loss"] * max(abs(ref.loss), 1e-2)
     if B == 1:      # a single pair has zero loss and zero gradient: absolute check
-        assert np.abs(dx1).max() <= 1e-6 and np.abs(dx2).max() <= 1e-6 and abs(dls) <= 1e-6
+        assert np.abs(dx1).max() <= 1e-5 and np.abs(dx2).max() <= 1e-5 and abs(dls) <= 1e-5
         return
     assert rel(dx1, ref.dx1) <= tol["grad"] and rel(dx2, ref.dx2) <= tol["grad"]
     assert abs(dls - ref.dlogit_scale) <= tol["grad"] * max(abs(ref.dlogit_scale), 1e-3)

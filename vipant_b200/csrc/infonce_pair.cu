@@ -31,7 +31,8 @@ constexpr int kBoxK = 64;                     // bf16 elements per 128-byte swiz
 constexpr int kYBox = 128 * 128;              // one TMA box of Y: [128 rows][64 elems] = 16 KB
 constexpr int kStage = 2 * kYBox;             // ring stage: two boxes (32 KB)
 constexpr int kStages = 3;
-constexpr int kThreads = 192;                 // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2..5: epilogue
+constexpr int kThreadsFwd = 192;              // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2..5: epilogue
+constexpr int kThreadsBwd = 320;              // backward: 8 epilogue warps (two per TMEM sub-partition / scheduler)
 constexpr uint32_t kSmemLimit = 232448;
 
 enum { MODE_FWD = 0, MODE_BWD = 1 };
@@ -79,15 +80,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// arrive on a barrier that may live in the peer CTA (cluster address), release at cluster scope
+// arrive on a barrier that may live in the peer CTA (cluster address).  Default (.release.cta) semantics, as
+// CUTLASS' umma_arrive_2x1SM_sm0: what is handed over is TMEM (ordered by tcgen05.fence) and shared memory
+// already published with fence.proxy.async; cluster-scope release/acquire costs an ERRBAR / CCTL.IVALL per
+// arrive / wait (15 % of the forward kernel's samples in ncu).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
       : "r"(bar), "r"(parity)
@@ -163,7 +167,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 // Shared-memory matrix descriptor, 128B swizzle (see infonce_tc.cu::make_desc)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -209,7 +214,7 @@ enum { B_XFULL = 0, B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_GFULL0, B_GFULL1
        B_RFULL, B_REMPTY = B_RFULL + kStages, B_COUNT = B_REMPTY + kStages };
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd, 1)
 pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
             const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1, const Params P) {
   using C = Cfg<MODE>;
@@ -242,10 +247,11 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     mbar_init(bar(B_XFULL), 1);
     mbar_init(bar(B_TFULL0), 1);
     mbar_init(bar(B_TFULL1), 1);
-    mbar_init(bar(B_TEMPTY0), 8);        // one arrival per epilogue warp of BOTH CTAs (leader's copy is used)
-    mbar_init(bar(B_TEMPTY1), 8);
-    mbar_init(bar(B_GFULL0), 8);
-    mbar_init(bar(B_GFULL1), 8);
+    constexpr int kEpiWarps2 = (MODE == MODE_FWD) ? 8 : 16;    // epilogue warps of BOTH CTAs (the leader's copy is used)
+    mbar_init(bar(B_TEMPTY0), kEpiWarps2);
+    mbar_init(bar(B_TEMPTY1), kEpiWarps2);
+    mbar_init(bar(B_GFULL0), kEpiWarps2);
+    mbar_init(bar(B_GFULL1), kEpiWarps2);
     mbar_init(bar(B_GEMPTY0), 1);
     mbar_init(bar(B_GEMPTY1), 1);
     mbar_init(bar(B_DXFULL), 1);
@@ -415,67 +421,89 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       if (row_ok) reinterpret_cast<float2*>(pb.out)[(int64_t)chunk * pb.n_x + row] = make_float2(m, l);
     } else {
       // 2x2 TMEM layout of M=128 cta_group::2: lanes 0-63 hold this CTA's 64 rows x columns [0,128) of the tile,
-      // lanes 64-127 the same rows x columns [128,256).
+      // lanes 64-127 the same rows x columns [128,256).  Eight epilogue warps: two per sub-partition (and per
+      // scheduler), each owning 64 of the thread's 128 columns -- a single warp per scheduler is latency-bound
+      // (ncu: 4.3 cycles per issued instruction).
       const int r_in = (sub & 1) * 32 + lane;         // row within the CTA's 64
-      const int jh = sub >> 1;                        // which 128-column half of the tile this thread owns
+      const int jh = sub >> 1;                        // which 128-column half of the tile this lane quadrant holds
+      const int ch = (warp - 2) >> 2;                 // which 64 of those 128 columns this warp processes
       const int row = row0 + r_in;
       const bool row_ok = row < pb.n_x;
+      const bool rows_full = row0 + C::RC <= pb.n_x;  // CTA-uniform
       const float s2 = P.scale[0] * kLog2e;
       const float lb = P.ln_B;
       const float rl2 = row_ok ? (pb.lse_x[pb.diag_offset + row] + lb) * kLog2e : INFINITY;
       const int dcol = row + pb.diag_offset;
+      const int dwarp0 = row0 + (sub & 1) * 32 + pb.diag_offset;     // diagonal columns of this warp: [dwarp0, dwarp0 + 32)
+      const bool want_dsc = pb.dscale != nullptr;
       float* cl_s = reinterpret_cast<float*>(sptr + L.cl);
       float dsc = 0.f;
+      const int etb = threadIdx.x - 64;               // 0..255
+      auto load_cl = [&](int t) {                     // column lse of tile t for shared-memory slot etb (base-2, + log2 B)
+        const int cj = (tile0 + t) * kBN + etb;
+        return (cj < pb.n_y) ? (pb.lse_y[cj] + lb) * kLog2e : INFINITY;          // +inf masks columns past n_y
+      };
+      float cl_next = load_cl(0);
       for (int j = 0; j < nt; ++j) {
         const int b = j & 1;
         const int col0 = (tile0 + j) * kBN;
-        epi_bar_sync();                               // everyone is done reading the previous tile's column lse
-        for (int q = et; q < kBN; q += 128) {
-          const int cj = col0 + q;
-          cl_s[q] = (cj < pb.n_y) ? (pb.lse_y[cj] + lb) * kLog2e : INFINITY;   // +inf masks columns past n_y
-        }
-        epi_bar_sync();
+        epi_bar_sync<256>();                          // everyone is done reading the previous tile's column lse
+        cl_s[etb] = cl_next;
+        epi_bar_sync<256>();
+        if (j + 1 < nt) cl_next = load_cl(j + 1);     // prefetch: its latency hides behind this tile's math
         mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
         tc_fence_after();
-        const int cbase = col0 + jh * 128;
-        const bool has_diag = row_ok && dcol >= cbase && dcol < cbase + 128;
+        const bool full = rows_full && (col0 + kBN <= pb.n_y);      // no masking needed anywhere in this tile
         uint8_t* gbuf = sptr + L.g + b * 32768;       // G buffer = tile parity
+        if (j >= 2) mbar_wait(bar(B_GEMPTY0 + b), ((j >> 1) - 1) & 1);   // dX(j-2) has consumed this G buffer
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = ch * 2 + cc;                  // 32-column chunk within the 128
+          const int cstart = col0 + jh * 128 + c * 32;
           uint32_t r[32];
           tmem_ld32(t_lane + b * 128 + c * 32, r);
           tmem_ld_wait();
           uint32_t packed[16];
           const float4* cl4 = reinterpret_cast<const float4*>(cl_s + jh * 128 + c * 32);
+          const bool diag_here = dwarp0 < cstart + 32 && dwarp0 + 32 > cstart;    // warp-uniform
+          if (full && !diag_here) {
 #pragma unroll
-          for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 cl = cl4[e4];
-            const float clv[4] = {cl.x, cl.y, cl.z, cl.w};
-            float gv[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float acc = __uint_as_float(r[e4 * 4 + q]);
-              float g = ex2_approx(fmaf(acc, s2, -rl2)) + ex2_approx(fmaf(acc, s2, -clv[q]));
-              if (clv[q] == INFINITY) g = 0.f;
-              gv[q] = g;
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 cl = cl4[e4];
+              const float a0 = __uint_as_float(r[e4 * 4 + 0]), a1 = __uint_as_float(r[e4 * 4 + 1]);
+              const float a2 = __uint_as_float(r[e4 * 4 + 2]), a3 = __uint_as_float(r[e4 * 4 + 3]);
+              const float g0 = ex2_approx(fmaf(a0, s2, -rl2)) + ex2_approx(fmaf(a0, s2, -cl.x));
+              const float g1 = ex2_approx(fmaf(a1, s2, -rl2)) + ex2_approx(fmaf(a1, s2, -cl.y));
+              const float g2 = ex2_approx(fmaf(a2, s2, -rl2)) + ex2_approx(fmaf(a2, s2, -cl.z));
+              const float g3 = ex2_approx(fmaf(a3, s2, -rl2)) + ex2_approx(fmaf(a3, s2, -cl.w));
+              if (want_dsc) dsc = fmaf(g0, a0, fmaf(g1, a1, fmaf(g2, a2, fmaf(g3, a3, dsc))));
+              packed[e4 * 2 + 0] = pack_bf16x2(g0, g1);
+              packed[e4 * 2 + 1] = pack_bf16x2(g2, g3);
             }
-            if (has_diag) {
+          } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (cbase + c * 32 + e4 * 4 + q == dcol) gv[q] -= 2.0f * P.inv_B;
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 cl = cl4[e4];
+              const float clv[4] = {cl.x, cl.y, cl.z, cl.w};
+              float gv[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float acc = __uint_as_float(r[e4 * 4 + q]);
+                float g = ex2_approx(fmaf(acc, s2, -rl2)) + ex2_approx(fmaf(acc, s2, -clv[q]));
+                if (clv[q] == INFINITY || !row_ok) g = 0.f;
+                if (cstart + e4 * 4 + q == dcol && row_ok) g -= 2.0f * P.inv_B;
+                gv[q] = g;
+                dsc = fmaf(g, acc, dsc);
+              }
+              packed[e4 * 2 + 0] = pack_bf16x2(gv[0], gv[1]);
+              packed[e4 * 2 + 1] = pack_bf16x2(gv[2], gv[3]);
             }
-            if (!row_ok) { gv[0] = gv[1] = gv[2] = gv[3] = 0.f; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dsc = fmaf(gv[q], __uint_as_float(r[e4 * 4 + q]), dsc);
-            packed[e4 * 2 + 0] = pack_bf16x2(gv[0], gv[1]);
-            packed[e4 * 2 + 1] = pack_bf16x2(gv[2], gv[3]);
           }
-          if (c == 0 && j >= 2) mbar_wait(bar(B_GEMPTY0 + b), ((j >> 1) - 1) & 1);   // dX(j-2) has consumed this G buffer
-          // K-major SW128: box (64 j columns, 8 KB) = jh*2 + (c >> 1); row = r_in; 16-byte chunk index XOR (row & 7)
-          uint8_t* gbox = gbuf + (jh * 2 + (c >> 1)) * 8192 + r_in * 128;
+          // K-major SW128: box (64 j columns, 8 KB) = jh*2 + ch; row = r_in; 16-byte chunk index XOR (row & 7)
+          uint8_t* gbox = gbuf + (jh * 2 + ch) * 8192 + r_in * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int chunk16 = ((c & 1) * 4 + q) ^ (r_in & 7);
+            const int chunk16 = (cc * 4 + q) ^ (r_in & 7);
             *reinterpret_cast<uint4*>(gbox + chunk16 * 16) =
                 make_uint4(packed[q * 4 + 0], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
           }
@@ -494,7 +522,8 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       float* orow = pb.out + ((int64_t)chunk * pb.n_x + row) * P.D;
       for (int nb = 0; nb < P.nblk; ++nb) {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = ch * 2 + cc;
           uint32_t r[32];
           tmem_ld32(t_lane + 256 + nb * 128 + c * 32, r);
           tmem_ld_wait();
@@ -506,12 +535,14 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
           }
         }
       }
-      if (pb.dscale) {                      // fixed-order block reduction of sum G*cos
+      if (want_dsc) {                       // fixed-order block reduction of sum G*cos
         float* red = reinterpret_cast<float*>(sptr + L.red);
         const float v = warp_sum(dsc);
-        if (lane == 0) red[sub] = v;
-        epi_bar_sync();
-        if (et == 0) pb.dscale[blockIdx.x - prob * 2 * P.pairs_per_problem] = (red[0] + red[1]) + (red[2] + red[3]);
+        if (lane == 0) red[warp - 2] = v;
+        epi_bar_sync<256>();
+        if (etb == 0)
+          pb.dscale[blockIdx.x - prob * 2 * P.pairs_per_problem] =
+              ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
       }
     }
   }
@@ -598,7 +629,7 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
     VPA_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set[MODE] = true;
   }
-  dim3 grid(2 * 2 * P.pairs_per_problem), block(kThreads);
+  dim3 grid(2 * 2 * P.pairs_per_problem), block(bwd ? kThreadsBwd : kThreadsFwd);
   prof_begin(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
   pair_kernel<MODE><<<grid, block, L.total, st>>>(maps[0], maps[1], maps[2], maps[3], P);
   prof_end(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);

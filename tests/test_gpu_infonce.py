@@ -75,7 +75,8 @@ def test_ragged_shapes(precision, B, D):
     ref = io.infonce_closed_form(x1n, x2n, grad_output=0.5)
     loss, dx1, dx2, dls = run(x1n, x2n, precision, grad_output=0.5)
     tol = TOL[precision]
-    assert abs(loss - ref.loss) <= tol["loss"] * max(abs(ref.loss), 1e-2)
+    # tiny batches: the loss is a small difference of O(10) logsumexps, so the relative bar gets an absolute floor
+    assert abs(loss - ref.loss) <= tol["loss"] * max(abs(ref.loss), 1.0)
     if B == 1:      # a single pair has zero loss and zero gradient: absolute check
         assert np.abs(dx1).max() <= 1e-5 and np.abs(dx2).max() <= 1e-5 and abs(dls) <= 1e-5
         return

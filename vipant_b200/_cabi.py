@@ -48,7 +48,8 @@ class VipantB200Error(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library; VIPANT_B200_LIB selects another build of the same C-ABI (A/B measurements only)."""
+    return os.environ.get("VIPANT_B200_LIB") or _build.LIB_PATH
 
 
 def lib() -> ctypes.CDLL:

@@ -202,11 +202,11 @@ __host__ __device__ inline SmemLayout smem_layout(int kboxes) {
   L.x = o; o += kboxes * Cfg<MODE>::XBox;
   L.g = o; o += (MODE == MODE_BWD) ? 2 * 32768 : 0;            // two G buffers: [64 rows][256 j] bf16 each
   L.ring = o; o += kStages * kStage;
-  L.cl = o; o += 256 * 4;
+  L.cl = o; o += 2 * 256 * 4;                                  // column lse of the current / next tile
   L.red = o; o += 64;
   L.bars = o; o += 32 * 8;
   L.tmem_slot = o; o += 16;
-  L.total = o + 1024;
+  L.total = o;                                                 // + alignment pad of the dynamic base (checked in the kernel)
   return L;
 }
 // barrier indices
@@ -222,6 +222,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
+  if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
   const bool is_leader = crank == 0;
@@ -439,18 +440,18 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       float* cl_s = reinterpret_cast<float*>(sptr + L.cl);
       float dsc = 0.f;
       const int etb = threadIdx.x - 64;               // 0..255
-      auto load_cl = [&](int t) {                     // column lse of tile t for shared-memory slot etb (base-2, + log2 B)
+      auto load_cl = [&](int t) {                     // raw column lse of tile t for shared-memory slot etb; +inf masks columns past n_y
         const int cj = (tile0 + t) * kBN + etb;
-        return (cj < pb.n_y) ? (pb.lse_y[cj] + lb) * kLog2e : INFINITY;          // +inf masks columns past n_y
+        return (cj < pb.n_y) ? __ldg(pb.lse_y + cj) : INFINITY;
       };
-      float cl_next = load_cl(0);
+      float cl_raw = load_cl(0);
       for (int j = 0; j < nt; ++j) {
         const int b = j & 1;
         const int col0 = (tile0 + j) * kBN;
-        epi_bar_sync<256>();                          // everyone is done reading the previous tile's column lse
-        cl_s[etb] = cl_next;
+        float* clb = cl_s + b * 256;                  // double-buffered: one barrier per tile
+        clb[etb] = (cl_raw + lb) * kLog2e;            // base-2, + log2 B
+        if (j + 1 < nt) cl_raw = load_cl(j + 1);      // prefetch (raw: nothing depends on it until the next tile)
         epi_bar_sync<256>();
-        if (j + 1 < nt) cl_next = load_cl(j + 1);     // prefetch: its latency hides behind this tile's math
         mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
         tc_fence_after();
         const bool full = rows_full && (col0 + kBN <= pb.n_y);      // no masking needed anywhere in this tile
@@ -464,7 +465,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
           tmem_ld32(t_lane + b * 128 + c * 32, r);
           tmem_ld_wait();
           uint32_t packed[16];
-          const float4* cl4 = reinterpret_cast<const float4*>(cl_s + jh * 128 + c * 32);
+          const float4* cl4 = reinterpret_cast<const float4*>(clb + jh * 128 + c * 32);
           const bool diag_here = dwarp0 < cstart + 32 && dwarp0 + 32 > cstart;    // warp-uniform
           if (full && !diag_here) {
 #pragma unroll
@@ -624,6 +625,7 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   }
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (L.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", L.total);
+  const uint32_t dyn_smem = kSmemLimit;     // the layout plus whatever pad aligns the dynamic base to 1024 B
   static bool attr_set[2] = {false, false};
   if (!attr_set[MODE]) {
     VPA_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -631,7 +633,7 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   }
   dim3 grid(2 * 2 * P.pairs_per_problem), block(bwd ? kThreadsBwd : kThreadsFwd);
   prof_begin(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
-  pair_kernel<MODE><<<grid, block, L.total, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  pair_kernel<MODE><<<grid, block, dyn_smem, st>>>(maps[0], maps[1], maps[2], maps[3], P);
   prof_end(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
   VPA_LAUNCH_CHECK(bwd ? "pair_kernel<BWD>" : "pair_kernel<FWD>");
   return 0;

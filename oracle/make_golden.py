@@ -204,12 +204,58 @@ def gen_retrieval(ref):
         json.dump(strings, fw, indent=1)
 
 
+def gold_file_case(n=120, nclass=7, D=64, seed=1213):
+    """N == M retrieval with a gold file (LossHead.report :177-238): ids, class labels and features."""
+    g = torch.Generator().manual_seed(seed)
+    labels = torch.randint(0, nclass, (n,), generator=g)
+    centers = torch.randn(nclass, D, generator=g)
+    a = 0.35 * centers[labels] + torch.randn(n, D, generator=g)
+    t = 0.35 * centers[labels] + 0.25 * a + torch.randn(n, D, generator=g)
+    ids = [f"clip{i:04d}" for i in range(n)]
+    lines = [json.dumps({"id": ids[i], "labels": [f"class {int(labels[i])}", "x"]}) for i in range(n)]
+    return a.numpy(), t.numpy(), ids, lines
+
+
+def gen_gold_report(ref):
+    """Per-class P@1 / R@1 / mAP / mAR line of LossHead.report(gold_file=...) (:177-238)."""
+    import tempfile
+    a, t, ids, lines = gold_file_case()
+    an, tn = ro.normalize(a.astype(np.float64)), ro.normalize(t.astype(np.float64))
+    S = an @ tn.T
+    srt = np.sort(S, axis=1)
+    srt_t = np.sort(S.T, axis=1)
+    margin = float(min((srt[:, -1] - srt[:, -2]).min(), (srt_t[:, -1] - srt_t[:, -2]).min()))
+    assert margin >= 1e-5, margin          # nearest neighbour unambiguous in both directions
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fw:
+        fw.write("\n".join(lines) + "\n")
+        path = fw.name
+    head = ref.CELossHead(Cfg(scaling=True, scale_max=None))
+    head.eval()
+    for i in range(0, len(ids), 50):
+        head(torch.from_numpy(a[i:i + 50]), torch.from_numpy(t[i:i + 50]), normalized=False, names=ids[i:i + 50])
+    rep = head.report(gold_file=path)
+    os.unlink(path)
+    with open(os.path.join(OUT, "report_strings.json")) as fr:
+        strings = json.load(fr)
+    strings["retrieval_nn_goldfile"] = rep
+    with open(os.path.join(OUT, "report_strings.json"), "w") as fw:
+        json.dump(strings, fw, indent=1)
+    np.savez_compressed(os.path.join(OUT, "retrieval_goldfile.npz"), top1_12=S.argmax(1).astype(np.int32),
+                        top1_21=S.T.argmax(1).astype(np.int32), input_checksum=np.float64(checksum(a, t)),
+                        margin=np.float64(margin))
+    print("gold-file report:", repr(rep))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = load_reference_loss_head()
+    if "--gold-only" in sys.argv:
+        gen_gold_report(ref)
+        return
     gen_infonce(ref)
     gen_retrieval(ref)
+    gen_gold_report(ref)
 
 
 if __name__ == "__main__":

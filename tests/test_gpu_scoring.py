@@ -139,3 +139,17 @@ def test_rank_topk_semantics_and_edges():
     S = (qn.double() @ kn.double().T).numpy()
     assert np.array_equal(r.cpu().numpy(), ro.rank_of(S, gt.numpy()))
     assert np.array_equal(idx.cpu().numpy(), ro.topk(S, 7)[0])
+
+
+def test_report_with_gold_file(strings, tmp_path):
+    """N == M retrieval report with a gold file: per-class P@1/R@1/mAP/mAR line + t1/t5 line, byte-identical."""
+    import vipant_b200 as vb
+    from oracle.make_golden import gold_file_case
+    a, t, ids, lines = gold_file_case()
+    path = tmp_path / "gold.json"
+    path.write_text("\n".join(lines) + "\n")
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None)).cuda().eval()
+    with torch.no_grad():
+        for i in range(0, len(ids), 50):
+            head(torch.from_numpy(a[i:i + 50]).cuda(), torch.from_numpy(t[i:i + 50]).cuda(), normalized=False, names=ids[i:i + 50])
+    assert head.report(gold_file=str(path)) == strings["retrieval_nn_goldfile"]

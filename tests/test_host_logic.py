@@ -175,3 +175,19 @@ def test_row_sharded_plumbing_gloo(world):
         assert dls == pytest.approx(ref.dlogit_scale, rel=1e-9)                # all-reduced scalar
         np.testing.assert_allclose(dx1, ref.dx1[r * b:(r + 1) * b], atol=1e-12)
         np.testing.assert_allclose(dx2, ref.dx2[r * b:(r + 1) * b], atol=1e-12)
+
+
+def test_gold_file_class_stats_match_reference(strings, tmp_path):
+    """LossHead.report(gold_file=...) per-class line (reference :177-238) from nearest-neighbour indices."""
+    from oracle.make_golden import gold_file_case
+    a, t, ids, lines = gold_file_case()
+    g = load_golden("retrieval_goldfile")
+    path = tmp_path / "gold.json"
+    path.write_text("\n".join(lines) + "\n")
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None))
+    head.ids = list(ids)
+    by_class, by_sample = head._gold_cluster(str(path), len(ids))
+    msg_12 = head._class_stats(torch.from_numpy(g["top1_12"].astype(np.int64)), by_class, by_sample, len(ids), "I->A")
+    msg_21 = head._class_stats(torch.from_numpy(g["top1_21"].astype(np.int64)), by_class, by_sample, len(ids), "A->I")
+    expected = strings["retrieval_nn_goldfile"].split("\n")[1]
+    assert f"{msg_12} {msg_21}" == expected

@@ -314,11 +314,16 @@ def main():
         fwd_ms, fwd_n = prof["fwd_sweep"]
         nrm_ms, nrm_n = prof["normalize"]
         roofline = None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+        if os.path.exists(tpath) and B == 32768 and D == 512 and world == 1:
+            with open(tpath) as fr:
+                traffic = json.load(fr).get("bwd_sweep_dram_bytes")
         if bwd_n:
             flops = 6.0 * b * B * D                         # S recompute + dX1 + dX2 contractions
             ach = flops / (bwd_ms / bwd_n * 1e-3) / 1e12
-            roofline = {"kernel": "sweep_kernel<BWD> (tcgen05)", "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
-                        "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"],
+            roofline = {"kernel": "pair_kernel<BWD> (tcgen05 cta_group::2)", "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
+                        "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": bwd_ms / bwd_n, "launches": bwd_n}
         step_flops = 8.0 * b * B * D
         line = {

@@ -249,7 +249,10 @@ def sim_rank_topk(q: torch.Tensor, k: torch.Tensor, gt: Optional[torch.Tensor] =
     g = 0
     gt32 = None
     if gt is not None:
-        gt32 = gt.reshape(N, -1).to(device=dev, dtype=torch.int32).contiguous()
+        gt2 = gt[:, None] if gt.dim() == 1 else gt           # (N,) or (N, g); N may be 0
+        if gt2.dim() != 2 or gt2.shape[0] != N:
+            raise ValueError(f"gt must have shape (N,) or (N, g) with N={N}, got {tuple(gt.shape)}")
+        gt32 = gt2.to(device=dev, dtype=torch.int32).contiguous()
         g = gt32.shape[1]
     ranks = torch.empty((N, g), dtype=torch.int32, device=dev) if g else None
     idx = torch.empty((N, topk), dtype=torch.int64, device=dev) if topk else None

@@ -44,7 +44,7 @@ RHO = 0.3
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="GLOBAL batch (rows of each modality)")
@@ -87,6 +87,7 @@ class ClockSampler:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)          # warm the query path
         except Exception:
             self.nv = None
 
@@ -111,7 +112,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -246,7 +247,7 @@ def main():
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     prof = {}
-    for kind, name in ((0, "normalize"), (1, "fwd_sweep"), (2, "bwd_sweep")):
+    for kind, name in ((0, "normalize"), (1, "fwd_sweep"), (2, "bwd_sweep"), (5, "fwd_general_gated"), (6, "finalize")):
         tot, n = ctypes.c_float(), ctypes.c_int()
         lib.vpa_profile_read(kind, ctypes.byref(tot), ctypes.byref(n))
         prof[name] = (tot.value, n.value)
@@ -339,10 +340,14 @@ def main():
             "step_tflops_algorithmic_8B2D": step_flops / (ms_step * 1e-3) / 1e12,
             "step_frac_of_peak": step_flops / (ms_step * 1e-3) / 1e12 / pk["tflops"],
             "kernel_ms": {"normalize_pair": nrm_ms / max(nrm_n, 1), "fwd_sweep": fwd_ms / max(fwd_n, 1),
-                          "bwd_sweep": bwd_ms / max(bwd_n, 1)},
+                          "bwd_sweep": bwd_ms / max(bwd_n, 1),
+                          "fwd_general_gated_off": prof["fwd_general_gated"][0] / max(prof["fwd_general_gated"][1], 1),
+                          "finalize_bwd": prof["finalize"][0] / max(prof["finalize"][1], 1)},
+            "finalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 4 + 4)) / (prof["finalize"][0] / max(prof["finalize"][1], 1) * 1e-3) / 1e9
+                             if prof["finalize"][1] else None, "peak_gbs": pk["hbm"]},
             "normalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 2) + 12 * b) / (nrm_ms / max(nrm_n, 1) * 1e-3) / 1e9 if nrm_n else None,
                               "peak_gbs": pk["hbm"]},
-            "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": 6 * args.steps,
+            "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * args.steps,
         }
         if not args.no_cpu_baseline and world == 1:
             cx1, cx2, cls_, cb, cores = cpu_block_sample(B, D)

@@ -48,14 +48,15 @@ int vpa_version(void);
 const char* vpa_last_error_string(void);
 
 /* Opt-in launch timing for measurement (bench.py): when enabled, the library brackets its dominant kernels
- * with CUDA events on the launch stream.  kind: 0 normalise, 1 forward sweep, 2 backward sweep, 3 similarity,
- * 4 rank/top-k.  vpa_profile_read synchronises on the recorded events, returns the summed kernel time and the
+ * with CUDA events on the launch stream.  kind: VPA_PROF_* below.  vpa_profile_read synchronises on the recorded events, returns the summed kernel time and the
  * number of launches since the last read, and resets the counter.  Off by default; not thread-safe. */
 #define VPA_PROF_NORMALIZE 0
 #define VPA_PROF_FWD_SWEEP 1
 #define VPA_PROF_BWD_SWEEP 2
 #define VPA_PROF_SIM 3
 #define VPA_PROF_RANK 4
+#define VPA_PROF_FWD_GENERAL 5 /* the exact two-sweep forward when the single-pass one is also enqueued */
+#define VPA_PROF_FINALIZE 6
 int vpa_profile_enable(int on);
 int vpa_profile_read(int kind, float* total_ms, int* launches);
 
@@ -99,6 +100,25 @@ int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, con
                     int64_t row_offset, const float* logit_scale, float scale_max,
                     const float* diag_cos, void* workspace, size_t workspace_bytes,
                     float* row_lse, float* col_lse, float* diag, float* scale_out, void* stream);
+
+/* The same forward split around the one exchange step of a row-sharded batch (north star: "a small all-reduce
+ * combines the column statistics").  While s * log2(e) <= 62 (s <= 43; every exp2(S*s2 - s2) is a normal fp32 number)
+ * the tensor-core path sweeps S ONCE: row sums for the local rows and, for every column, the sum over the LOCAL rows,
+ * reduced in fixed order to col_sum[VPA_COLSUM_SPLIT][rows_global].  The caller all-reduces (SUM) col_sum over the
+ * ranks and calls _finish, which turns the sums into row_lse / col_lse / diag of the local rows.  For larger s (decided
+ * on the device, no host sync) the exact two-sweep kernel runs instead and col_sum is zero / ignored.
+ * vpa_infonce_fwd == _sweep + _finish with an internal col_sum; when rows_local < rows_global it always takes the
+ * exact two-sweep route (no exchange needed). */
+#define VPA_COLSUM_SPLIT 8
+size_t vpa_infonce_colsum_floats(int64_t rows_global);
+int vpa_infonce_fwd_sweep(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all,
+                          int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
+                          const float* logit_scale, float scale_max, void* workspace, size_t workspace_bytes,
+                          float* col_sum, void* stream);
+int vpa_infonce_fwd_finish(int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
+                           const float* logit_scale, float scale_max, const float* diag_cos, void* workspace,
+                           size_t workspace_bytes, const float* col_sum, float* row_lse, float* col_lse,
+                           float* diag, float* scale_out, void* stream);
 
 /* loss = mean_i(row_lse - diag) + mean_i(col_lse - diag) over the GLOBAL batch (:280-283: two
  * mean-reduced cross entropies, summed).  Deterministic fixed-order reduction, one block. */

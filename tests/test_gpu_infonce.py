@@ -84,6 +84,18 @@ def test_ragged_shapes(precision, B, D):
     assert abs(dls - ref.dlogit_scale) <= tol["grad"] * max(abs(ref.dlogit_scale), 1e-3)
 
 
+@pytest.mark.parametrize("s", [5.0, 42.9, 43.2, 60.0, 120.0])
+def test_forward_regimes(s):
+    """The tensor-core forward picks, ON THE DEVICE, the single-pass kernel (s*log2e <= 62, i.e. s <= 42.97) or the
+    exact two-sweep kernel; both sides of the switch and a temperature far above it must meet the same bars."""
+    x1n, x2n = io.make_pair(777, 512, 0.05, 17)         # weakly aligned pairs: the loss stays O(1) at every temperature
+    ref = io.infonce_closed_form(x1n, x2n, math.log(s))
+    loss, dx1, dx2, dls = run(x1n, x2n, "bf16", logit_scale=math.log(s))
+    assert abs(loss - ref.loss) <= 1e-3 * max(abs(ref.loss), 0.1)
+    assert rel(dx1, ref.dx1) <= 1e-2 and rel(dx2, ref.dx2) <= 1e-2
+    assert abs(dls - ref.dlogit_scale) <= 1e-2 * abs(ref.dlogit_scale)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_half_inputs(dtype):
     """Encoders under autocast hand over 16-bit features; gradients come back in the same dtype."""
@@ -150,11 +162,16 @@ def test_row_shard_offsets_single_gpu():
     prec = _cabi.PREC_BF16_TC
     a_all, t_all, inv, dcos = K.normalize_pair(x1, x2, False, prec)
     b = B // R
-    stats, wss, scales = [], [], []
+    stats, wss, scales, colsums = [], [], [], []
     for r in range(R):
         sl = slice(r * b, (r + 1) * b)
-        st, sc, ws = K.forward_stats(a_all[sl], t_all[sl], a_all, t_all, r * b, ls, None, dcos[sl], prec)
-        stats.append(st); wss.append(ws); scales.append(sc)
+        cs, ws = K.forward_sweep(a_all[sl], t_all[sl], a_all, t_all, r * b, ls, None, prec)
+        wss.append(ws); colsums.append(cs)
+    col_sum = torch.stack(colsums).sum(0)                       # what the all-reduce produces
+    for r in range(R):
+        sl = slice(r * b, (r + 1) * b)
+        st, sc = K.forward_finish(b, B, D, r * b, ls, None, dcos[sl], prec, wss[r], col_sum)
+        stats.append(st); scales.append(sc)
     stats_all = torch.cat(stats, dim=1).contiguous()
     loss = K.loss(stats_all).item()
     assert abs(loss - full.loss) <= 1e-3 * abs(full.loss)

@@ -108,10 +108,19 @@ class _CheckerKernels:
             a, t = x1 / n1[:, None], x2 / n2[:, None]
         return a, t, torch.stack([1 / n1, 1 / n2]), (a * t).sum(-1)
 
-    def forward_stats(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, dcos, precision):
-        s, flows = io.effective_scale(float(logit_scale), scale_max)
-        stats = torch.stack([torch.logsumexp(s * a @ t_all.T, 1), torch.logsumexp(s * t @ a_all.T, 1), s * dcos])
-        return stats, torch.tensor([s, float(flows)], dtype=torch.float64), None
+    def forward_sweep(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, precision):
+        # single-pass regime: row sums are local, column sums are partial over the ranks -> all-reduced by the caller
+        s, _ = io.effective_scale(float(logit_scale), scale_max)
+        S = s * a @ t_all.T
+        col_sum = torch.zeros((8, a_all.shape[0]), dtype=torch.float64)
+        col_sum[0] = torch.exp(S - s).sum(0)
+        return col_sum, (torch.logsumexp(S, 1), s)
+
+    def forward_finish(self, b, B, D, row_offset, logit_scale, scale_max, dcos, precision, ws, col_sum):
+        row_lse, s = ws
+        _, flows = io.effective_scale(float(logit_scale), scale_max)
+        col_lse = s + torch.log(col_sum.sum(0))[row_offset:row_offset + b]
+        return torch.stack([row_lse, col_lse, s * dcos]), torch.tensor([s, float(flows)], dtype=torch.float64)
 
     def loss(self, stats_all):
         return ((stats_all[0] - stats_all[2]).mean() + (stats_all[1] - stats_all[2]).mean())

@@ -51,9 +51,12 @@ int normalize_cast_launch(const void* x, int in_dtype, int64_t rows, int D, int6
 int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t rows, int D, int64_t ld1,
                           int64_t ld2, int already, void* a_bf16, void* t_bf16, float* a_f32, float* t_f32,
                           float* inv1, float* inv2, float* diag_cos, int diag_from_bf16, cudaStream_t st);
-int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local,
-                         const float* logit_scale, float scale_cap, const float* diag_cos,
-                         float* row_lse, float* col_lse, float* diag, float* scale_out, cudaStream_t st);
+int colsum_reduce_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_global, const float* logit_scale,
+                         float scale_cap, float* colsum, cudaStream_t st);
+int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int64_t rows_global,
+                         int64_t row_offset, const float* logit_scale, float scale_cap, const float* diag_cos,
+                         int fast, const float* colsum, float* row_lse, float* col_lse, float* diag, float* scale_out,
+                         cudaStream_t st);
 int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
                 cudaStream_t st);
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
@@ -102,7 +105,7 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
     p.rows_per_blk = 8;
     p.n_iblk = (int)((rows_local + 7) / 8);
     p.n_tiles = 0;
-    p.fwd_chunks = p.bwd_chunks = 1;
+    p.fwd_chunks = p.bwd_chunks = p.fwd1_chunks = 1;
     p.fwd_tiles_per_chunk = p.bwd_tiles_per_chunk = 0;
     p.halves = 1;
     p.n_dscale = p.n_iblk;
@@ -121,8 +124,13 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
     pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
     pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 1, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
     p.n_dscale = 2 * p.pair_bwd_iblk * p.bwd_chunks;
+    p.fast_fwd = 1;
+    if (const char* e = getenv("VPA_FAST_FWD")) p.fast_fwd = atoi(e) != 0;          // A/B knob
+    pick_chunks(p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2);
+    p.n_rowgroups = p.pair_fwd_iblk * 8;
     return p;
   }
+  p.fwd1_chunks = 1;
   p.n_iblk = (int)((rows_local + 127) / 128);
   p.n_tiles = (int)((rows_global + 127) / 128);
   p.halves = D > 256 ? 2 : 1;
@@ -138,7 +146,7 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
   return p;
 }
 
-Workspace carve_workspace(void* base, int64_t rows_local, int D, const SweepPlan& plan) {
+Workspace carve_workspace(void* base, int64_t rows_local, int64_t rows_global, int D, const SweepPlan& plan) {
   Workspace w{};
   size_t o = 0;
   auto take = [&](size_t bytes) {
@@ -146,9 +154,12 @@ Workspace carve_workspace(void* base, int64_t rows_local, int D, const SweepPlan
     o += align_up(bytes, 256);
     return p;
   };
-  w.fwd_part = static_cast<float*>(take((size_t)2 * plan.fwd_chunks * rows_local * 2 * sizeof(float)));
+  const int fchunks = plan.fwd_chunks > plan.fwd1_chunks ? plan.fwd_chunks : plan.fwd1_chunks;
+  w.fwd_part = static_cast<float*>(take((size_t)2 * fchunks * rows_local * 2 * sizeof(float)));
   w.bwd_part = static_cast<float*>(take((size_t)2 * plan.bwd_chunks * rows_local * D * sizeof(float)));
   w.dscale_part = static_cast<float*>(take((size_t)(plan.n_dscale > 0 ? plan.n_dscale : 1) * sizeof(float)));
+  w.colsum = static_cast<float*>(take((size_t)kColSumSplit * rows_global * sizeof(float)));
+  w.colpart = plan.fast_fwd ? static_cast<float*>(take((size_t)plan.n_rowgroups * rows_global * sizeof(float))) : nullptr;
   w.bytes = o;
   return w;
 }
@@ -215,28 +226,78 @@ int vpa_normalize_pair(const void* x1, const void* x2, int in_dtype, int64_t row
 size_t vpa_infonce_workspace_bytes(int64_t rows_local, int64_t rows_global, int D, int precision) {
   if (rows_local <= 0 || rows_global < rows_local || D <= 0) return 0;
   const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
-  return carve_workspace(nullptr, rows_local, D, plan).bytes;
+  return carve_workspace(nullptr, rows_local, rows_global, D, plan).bytes;
 }
 
-int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
-                    int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
-                    float scale_max, const float* diag_cos, void* workspace, size_t workspace_bytes,
-                    float* row_lse, float* col_lse, float* diag, float* scale_out, void* stream) {
+size_t vpa_infonce_colsum_floats(int64_t rows_global) { return rows_global > 0 ? (size_t)kColSumSplit * (size_t)rows_global : 0; }
+
+static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+                          int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
+                          float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, bool allow_fast,
+                          cudaStream_t st) {
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
-  VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && diag_cos && row_lse && col_lse && diag && workspace,
-                "infonce_fwd: null pointer");
+  VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && workspace, "infonce_fwd_sweep: null pointer");
   const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
-  const Workspace ws = carve_workspace(workspace, rows_local, D, plan);
+  const Workspace ws = carve_workspace(workspace, rows_local, rows_global, D, plan);
   if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_fwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
   SweepArgs a{};
   a.x[0] = a_loc; a.y[0] = t_all; a.x[1] = t_loc; a.y[1] = a_all;
   a.rows_local = rows_local; a.rows_global = rows_global; a.row_offset = row_offset; a.D = D;
   a.logit_scale = logit_scale;
   a.scale_cap = (scale_max > 0.f) ? scale_max : INFINITY;     // `cfg.scale_max or float("inf")`
+  float* cs = col_sum ? col_sum : ws.colsum;
+  VPA_CUDA(cudaMemsetAsync(cs, 0, (size_t)kColSumSplit * rows_global * sizeof(float), st));
+  if (precision != VPA_PREC_BF16_TC) return simt_infonce_fwd(a, ws, plan, st);
+  if (plan.impl != 1) return tc_infonce_fwd(a, ws, plan, st);
+  const bool fast = plan.fast_fwd && allow_fast;
+  if (int e = pair_infonce_fwd(a, ws, plan, fast, st)) return e;
+  if (fast) return colsum_reduce_launch(ws, plan, rows_global, logit_scale, a.scale_cap, cs, st);
+  return 0;
+}
+
+static int fwd_finish_impl(int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
+                           const float* logit_scale, float scale_max, const float* diag_cos, void* workspace,
+                           size_t workspace_bytes, const float* col_sum, bool allow_fast, float* row_lse, float* col_lse,
+                           float* diag, float* scale_out, cudaStream_t st) {
+  if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
+  VPA_CHECK_ARG(logit_scale && diag_cos && row_lse && col_lse && diag && workspace, "infonce_fwd_finish: null pointer");
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
+  const Workspace ws = carve_workspace(workspace, rows_local, rows_global, D, plan);
+  if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_fwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
+  const bool fast = precision == VPA_PREC_BF16_TC && plan.impl == 1 && plan.fast_fwd && allow_fast;
+  const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
+  return combine_stats_launch(ws, plan, rows_local, rows_global, row_offset, logit_scale, cap, diag_cos, fast ? 1 : 0,
+                              col_sum ? col_sum : ws.colsum, row_lse, col_lse, diag, scale_out, st);
+}
+
+int vpa_infonce_fwd_sweep(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+                          int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
+                          float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, void* stream) {
+  VPA_CHECK_ARG(col_sum != nullptr, "infonce_fwd_sweep: null col_sum");
+  return fwd_sweep_impl(a_loc, t_loc, a_all, t_all, precision, rows_local, rows_global, D, row_offset, logit_scale, scale_max,
+                        workspace, workspace_bytes, col_sum, true, static_cast<cudaStream_t>(stream));
+}
+
+int vpa_infonce_fwd_finish(int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
+                           const float* logit_scale, float scale_max, const float* diag_cos, void* workspace,
+                           size_t workspace_bytes, const float* col_sum, float* row_lse, float* col_lse, float* diag,
+                           float* scale_out, void* stream) {
+  VPA_CHECK_ARG(col_sum != nullptr, "infonce_fwd_finish: null col_sum");
+  return fwd_finish_impl(precision, rows_local, rows_global, D, row_offset, logit_scale, scale_max, diag_cos, workspace,
+                         workspace_bytes, col_sum, true, row_lse, col_lse, diag, scale_out, static_cast<cudaStream_t>(stream));
+}
+
+int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+                    int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
+                    float scale_max, const float* diag_cos, void* workspace, size_t workspace_bytes,
+                    float* row_lse, float* col_lse, float* diag, float* scale_out, void* stream) {
+  // Without a cross-rank reduction in between, the single-pass forward is only complete for an unsharded batch.
+  const bool allow_fast = rows_local == rows_global;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (int e = (precision == VPA_PREC_BF16_TC) ? (plan.impl == 1 ? pair_infonce_fwd(a, ws, plan, st) : tc_infonce_fwd(a, ws, plan, st))
-                                              : simt_infonce_fwd(a, ws, plan, st)) return e;
-  return combine_stats_launch(ws, plan, rows_local, logit_scale, a.scale_cap, diag_cos, row_lse, col_lse, diag, scale_out, st);
+  if (int e = fwd_sweep_impl(a_loc, t_loc, a_all, t_all, precision, rows_local, rows_global, D, row_offset, logit_scale,
+                             scale_max, workspace, workspace_bytes, nullptr, allow_fast, st)) return e;
+  return fwd_finish_impl(precision, rows_local, rows_global, D, row_offset, logit_scale, scale_max, diag_cos, workspace,
+                         workspace_bytes, nullptr, allow_fast, row_lse, col_lse, diag, scale_out, st);
 }
 
 int vpa_infonce_loss(const float* row_lse, const float* col_lse, const float* diag, int64_t rows_global,
@@ -258,7 +319,7 @@ int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, con
   VPA_CHECK_ARG(in_dtype == VPA_F32 || in_dtype == VPA_BF16 || in_dtype == VPA_F16, "infonce_bwd: bad dtype");
   VPA_CHECK_ARG(ld1 >= D && ld2 >= D && ld1 % 4 == 0 && ld2 % 4 == 0, "infonce_bwd: bad leading dimension");
   const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
-  const Workspace ws = carve_workspace(workspace, rows_local, D, plan);
+  const Workspace ws = carve_workspace(workspace, rows_local, rows_global, D, plan);
   if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_bwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
   SweepArgs a{};
   a.x[0] = a_loc; a.y[0] = t_all; a.x[1] = t_loc; a.y[1] = a_all;

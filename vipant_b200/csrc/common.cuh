@@ -34,7 +34,8 @@ int set_error(int code, const char* fmt, ...);
 
 // ---- opt-in launch timing (vpa_profile_*): CUDA events recorded on the launch stream around the
 // dominant kernels; used by bench.py for the roofline numbers, off by default (no cost, no state).
-enum { PROF_NORMALIZE = 0, PROF_FWD_SWEEP = 1, PROF_BWD_SWEEP = 2, PROF_SIM = 3, PROF_RANK = 4, PROF_KINDS = 5 };
+enum { PROF_NORMALIZE = 0, PROF_FWD_SWEEP = 1, PROF_BWD_SWEEP = 2, PROF_SIM = 3, PROF_RANK = 4, PROF_FWD_GENERAL = 5,
+       PROF_FINALIZE = 6, PROF_KINDS = 7 };
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);
 
@@ -120,7 +121,11 @@ struct SweepPlan {
   int impl;                 // tensor-core path: 0 = single-CTA kernels (infonce_tc.cu), 1 = CTA-pair kernels (infonce_pair.cu)
   int pair_fwd_iblk;        // pair kernels: 256-row blocks (forward) / 128-row blocks (backward); n_tiles counts 256-row tiles
   int pair_bwd_iblk;
+  int fast_fwd;             // pair kernels: the single-pass forward (one S sweep, both statistics) is available
+  int fwd1_chunks, fwd1_tiles_per_chunk;
+  int n_rowgroups;          // single-pass forward: 32-row groups of column partial sums (8 per 256-row block)
 };
+constexpr int kColSumSplit = 8;   // column sums are reduced to [kColSumSplit][rows_global] (fixed order) before any all-reduce
 SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision);
 
 // Scratch layout shared by both precisions.
@@ -128,9 +133,11 @@ struct Workspace {
   float* fwd_part;      // [2][fwd_chunks][rows_local] float2 (m, l), base-2 units
   float* bwd_part;      // [2][bwd_chunks][rows_local][D] fp32 partial  sum_j G_ij y_j
   float* dscale_part;   // [n_dscale] partial  sum_ij G_ij cos_ij  (problem 0 only)
+  float* colsum;        // [kColSumSplit][rows_global] column sums (internal copy for the unsharded one-call forward)
+  float* colpart;       // single-pass forward: [n_rowgroups][rows_global] column sums per 32-row group
   size_t bytes;
 };
-Workspace carve_workspace(void* base, int64_t rows_local, int D, const SweepPlan& plan);
+Workspace carve_workspace(void* base, int64_t rows_local, int64_t rows_global, int D, const SweepPlan& plan);
 
 // Everything a sweep launch needs besides the plan.  Problem 0: X = A_loc, Y = T_all (rows of S);
 // problem 1: X = T_loc, Y = A_all (columns of S, transposed).  Both run in ONE launch.
@@ -148,7 +155,8 @@ struct SweepArgs {
 
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int tc_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
-int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
+int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, bool fast, cudaStream_t st);
+float pair_fast_s2_limit();
 int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);

@@ -35,7 +35,8 @@ constexpr int kThreadsFwd = 192;              // warp 0: TMA, warp 1: MMA issue 
 constexpr int kThreadsBwd = 320;              // backward: 8 epilogue warps (two per TMEM sub-partition / scheduler)
 constexpr uint32_t kSmemLimit = 232448;
 
-enum { MODE_FWD = 0, MODE_BWD = 1 };
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FWD1 = 2 };
+constexpr float kFastS2Limit = 62.0f;     // single-pass forward valid while 2*s*log2(e) stays inside the fp32 exponent range
 
 struct Problem {
   int n_x, n_y;
@@ -55,6 +56,8 @@ struct Params {
   float scale_cap;
   const float* scale;
   float inv_B, ln_B;
+  int gate;                 // 0: always run; 1: run only if s*log2e <= kFastS2Limit; 2: run only if it is larger
+  float* colpart;           // FWD1: float[n_iblk*8][n_y] column sums of exp2(S*s2 - s2) per 32-row group
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -188,7 +191,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // ---------------------------------------------------------------- shared-memory carve-up (identical in both CTAs)
 template <int MODE>
 struct Cfg {
-  static constexpr int RC = (MODE == MODE_FWD) ? 128 : 64;     // X rows per CTA
+  static constexpr int RC = (MODE == MODE_BWD) ? 64 : 128;     // X rows per CTA
   static constexpr int RP = 2 * RC;                            // X rows per pair
   static constexpr int XBox = RC * 128;                        // one [RC rows][64 elems] box
 };
@@ -223,6 +226,10 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
+  if (P.gate != 0) {       // regime gate on the DEVICE value of the temperature (no host sync): uniform over the grid
+    const float gs2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
+    if ((P.gate == 1) != (gs2 <= kFastS2Limit)) return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
   const bool is_leader = crank == 0;
@@ -313,7 +320,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       const uint64_t dmn = make_desc(sbase, kYBox, 1024);        // MN-major: two 64-column atoms, 16 KB apart
       const uint32_t ring_u = L.ring >> 4, x_u = L.x >> 4, g_u = L.g >> 4;
       constexpr uint32_t xbox_u = C::XBox >> 4, ybox_u = kYBox >> 4, stage_u = kStage >> 4;
-      const uint32_t s_cols = (MODE == MODE_FWD) ? 256u : 128u;  // TMEM columns of one S buffer
+      const uint32_t s_cols = (MODE == MODE_BWD) ? 128u : 256u;  // TMEM columns of one S buffer
       int stage = 0;
       uint32_t phase = 0;
       mbar_wait(bar(B_XFULL), 0);
@@ -420,6 +427,60 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive_cluster(lbar(B_TEMPTY0 + b));
       }
       if (row_ok) reinterpret_cast<float2*>(pb.out)[(int64_t)chunk * pb.n_x + row] = make_float2(m, l);
+    } else if (MODE == MODE_FWD1) {
+      // Single-pass forward: ONE sweep of S yields both statistics.  With s*log2e <= 62 every term exp2(S*s2 - s2)
+      // (cos <= 1) is a normal fp32 number, so a fixed reference replaces the online maximum and the SAME exponential
+      // serves the row sums (thread-local) and the column sums (32x32 butterfly over the lanes of a warp, one value per
+      // lane, written as per-32-row-group partials).  Eight epilogue warps: two per lane quadrant, 128 columns each.
+      const int ch = (warp - 2) >> 2;                 // which 128 of the tile's 256 columns
+      const int row = row0 + sub * 32 + lane;         // lane = row (128 rows per CTA)
+      const bool row_ok = row < pb.n_x;
+      const bool rows_full = row0 + C::RC <= pb.n_x;
+      const float s2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
+      float* cp = P.colpart + (int64_t)(iblk * 8 + (int)crank * 4 + sub) * pb.n_y;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        const int b = j & 1;
+        mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
+        tc_fence_after();
+        const int col0 = (tile0 + j) * kBN;
+        const bool full = rows_full && (col0 + kBN <= pb.n_y);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = ch * 4 + cc;
+          const int cstart = col0 + c * 32;
+          uint32_t r[32];
+          tmem_ld32(t_lane + b * 256 + c * 32, r);
+          tmem_ld_wait();
+          float e[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) e[k] = ex2_approx(fmaf(__uint_as_float(r[k]), s2, -s2));
+          if (!full) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (!row_ok || cstart + k >= pb.n_y) e[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) { l0 += e[k]; l1 += e[k + 1]; l2 += e[k + 2]; l3 += e[k + 3]; }
+          // column sums over the warp's 32 rows: after the butterfly lane L holds column cstart + L
+#pragma unroll
+          for (int n = 16; n >= 1; n >>= 1) {
+            const bool up = (lane & n) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float keep = up ? e[i + n] : e[i];
+              const float send = up ? e[i] : e[i + n];
+              e[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+            }
+          }
+          if (cstart + lane < pb.n_y) cp[cstart + lane] = e[0];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lbar(B_TEMPTY0 + b));
+      }
+      // two warps (ch = 0, 1) hold halves of each row's sum: slot [chunk][ch][row] of a float2-per-row array
+      if (row_ok) reinterpret_cast<float*>(pb.out)[((int64_t)chunk * pb.n_x + row) * 2 + ch] = (l0 + l1) + (l2 + l3);
     } else {
       // 2x2 TMEM layout of M=128 cta_group::2: lanes 0-63 hold this CTA's 64 rows x columns [0,128) of the tile,
       // lanes 64-127 the same rows x columns [128,256).  Eight epilogue warps: two per sub-partition (and per
@@ -586,7 +647,7 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int b
 }
 
 template <int MODE>
-static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
+static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int gate, cudaStream_t st) {
   VPA_CHECK_ARG(a.D == 256 || a.D == 512, "pair kernels need D in {256, 512} (D=%d)", a.D);
   VPA_CHECK_ARG(a.rows_global < (1ll << 30), "rows_global too large");
   CUtensorMap maps[4];
@@ -596,9 +657,10 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   }
   Params P{};
   const bool bwd = MODE == MODE_BWD;
+  const bool fwd1 = MODE == MODE_FWD1;
   P.n_iblk = bwd ? plan.pair_bwd_iblk : plan.pair_fwd_iblk;
-  P.n_chunks = bwd ? plan.bwd_chunks : plan.fwd_chunks;
-  P.tiles_per_chunk = bwd ? plan.bwd_tiles_per_chunk : plan.fwd_tiles_per_chunk;
+  P.n_chunks = bwd ? plan.bwd_chunks : (fwd1 ? plan.fwd1_chunks : plan.fwd_chunks);
+  P.tiles_per_chunk = bwd ? plan.bwd_tiles_per_chunk : (fwd1 ? plan.fwd1_tiles_per_chunk : plan.fwd_tiles_per_chunk);
   P.n_tiles = plan.n_tiles;
   P.pairs_per_problem = P.n_iblk * P.n_chunks;
   P.D = a.D;
@@ -609,6 +671,8 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.scale = a.scale;
   P.inv_B = 1.0f / (float)a.rows_global;
   P.ln_B = logf((float)a.rows_global);
+  P.gate = gate;
+  P.colpart = ws.colpart;
   for (int p = 0; p < 2; ++p) {
     P.p[p].n_x = (int)a.rows_local;
     P.p[p].n_y = (int)a.rows_global;
@@ -626,26 +690,33 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (L.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", L.total);
   const uint32_t dyn_smem = kSmemLimit;     // the layout plus whatever pad aligns the dynamic base to 1024 B
-  static bool attr_set[2] = {false, false};
+  static bool attr_set[3] = {false, false, false};
   if (!attr_set[MODE]) {
     VPA_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     attr_set[MODE] = true;
   }
-  dim3 grid(2 * 2 * P.pairs_per_problem), block(bwd ? kThreadsBwd : kThreadsFwd);
-  prof_begin(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
+  // FWD1 sweeps one problem only (local x1 rows against all x2 rows)
+  dim3 grid((fwd1 ? 1 : 2) * 2 * P.pairs_per_problem), block(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd);
+  const int kind = bwd ? PROF_BWD_SWEEP : (fwd1 ? PROF_FWD_SWEEP : (gate == 2 ? PROF_FWD_GENERAL : PROF_FWD_SWEEP));
+  prof_begin(kind, st);
   pair_kernel<MODE><<<grid, block, dyn_smem, st>>>(maps[0], maps[1], maps[2], maps[3], P);
-  prof_end(bwd ? PROF_BWD_SWEEP : PROF_FWD_SWEEP, st);
-  VPA_LAUNCH_CHECK(bwd ? "pair_kernel<BWD>" : "pair_kernel<FWD>");
+  prof_end(kind, st);
+  VPA_LAUNCH_CHECK(bwd ? "pair_kernel<BWD>" : (fwd1 ? "pair_kernel<FWD1>" : "pair_kernel<FWD>"));
   return 0;
 }
 
 }  // namespace pr
 
-int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
-  return pr::launch<pr::MODE_FWD>(a, ws, plan, st);
+// Forward.  With `fast` the single-pass kernel (valid while s*log2e <= 62) and the exact two-problem kernel are
+// both enqueued; each checks the DEVICE value of the temperature and returns at once when it is not its regime.
+int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, bool fast, cudaStream_t st) {
+  if (!fast) return pr::launch<pr::MODE_FWD>(a, ws, plan, 0, st);
+  if (int e = pr::launch<pr::MODE_FWD1>(a, ws, plan, 1, st)) return e;
+  return pr::launch<pr::MODE_FWD>(a, ws, plan, 2, st);
 }
 int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
-  return pr::launch<pr::MODE_BWD>(a, ws, plan, st);
+  return pr::launch<pr::MODE_BWD>(a, ws, plan, 0, st);
 }
+float pair_fast_s2_limit() { return pr::kFastS2Limit; }
 
 }  // namespace vpa

@@ -4,10 +4,35 @@
 
 namespace vpa {
 
+// ---- single-pass forward: column sums per 32-row group -> [kColSumSplit][B] (fixed order) ----------------
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ colpart, int n_groups, int64_t B, float* __restrict__ colsum,
+                     const float* __restrict__ logit_scale, float scale_cap, float s2_limit) {
+  if (fminf(expf(*logit_scale), scale_cap) * kLog2e > s2_limit) return;     // not the single-pass regime
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= B) return;
+  const int per = (n_groups + kColSumSplit - 1) / kColSumSplit;
+  const int g0 = blockIdx.y * per, g1 = min(n_groups, g0 + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int g = g0;
+  for (; g + 4 <= g1; g += 4) {
+    a0 += __ldg(colpart + (int64_t)(g + 0) * B + j);
+    a1 += __ldg(colpart + (int64_t)(g + 1) * B + j);
+    a2 += __ldg(colpart + (int64_t)(g + 2) * B + j);
+    a3 += __ldg(colpart + (int64_t)(g + 3) * B + j);
+  }
+  for (; g < g1; ++g) a0 += __ldg(colpart + (int64_t)g * B + j);
+  colsum[(int64_t)blockIdx.y * B + j] = (a0 + a1) + (a2 + a3);
+}
+
 // ---- forward: merge chunk partials -> logsumexp (natural log), diag = s * cos, scale_out -----------
-__global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chunks, int64_t rows_local,
-                                     const float* __restrict__ logit_scale, float scale_cap,
-                                     const float* __restrict__ diag_cos, float* __restrict__ row_lse,
+// general regime: part = float2 (max, sum) per (problem, chunk, row), base-2 units.
+// single-pass regime (fast != 0 and s*log2e <= s2_limit): part[0] = two half row sums per (chunk, row) against the
+// fixed reference s2; column sums come from colsum[kColSumSplit][B] (already summed over ranks by the caller).
+__global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chunks, int n_chunks_fast, int64_t rows_local,
+                                     int64_t rows_global, int64_t row_offset, const float* __restrict__ logit_scale,
+                                     float scale_cap, const float* __restrict__ diag_cos, int fast, float s2_limit,
+                                     const float* __restrict__ colsum, float* __restrict__ row_lse,
                                      float* __restrict__ col_lse, float* __restrict__ diag,
                                      float* __restrict__ scale_out) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,15 +45,30 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
   if (idx >= 2 * rows_local) return;
   const int p = idx >= rows_local;
   const int64_t row = idx - (int64_t)p * rows_local;
-  const float2* base = part + (int64_t)p * n_chunks * rows_local + row;
-  float M = -INFINITY;
-  for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, base[(int64_t)c * rows_local].x);
-  float L = 0.f;
-  for (int c = 0; c < n_chunks; ++c) {
-    float2 ml = base[(int64_t)c * rows_local];
-    L += ml.y * exp2f(ml.x - M);
+  float lse;
+  if (fast && s * kLog2e <= s2_limit) {
+    const float s2 = s * kLog2e;
+    float L = 0.f;
+    if (p == 0) {
+      for (int c = 0; c < n_chunks_fast; ++c) {
+        const float2 h = part[(int64_t)c * rows_local + row];
+        L += h.x + h.y;
+      }
+    } else {
+      for (int g = 0; g < kColSumSplit; ++g) L += colsum[(int64_t)g * rows_global + row_offset + row];
+    }
+    lse = (s2 + log2f(L)) * kLn2;
+  } else {
+    const float2* base = part + (int64_t)p * n_chunks * rows_local + row;
+    float M = -INFINITY;
+    for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, base[(int64_t)c * rows_local].x);
+    float L = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      float2 ml = base[(int64_t)c * rows_local];
+      L += ml.y * exp2f(ml.x - M);
+    }
+    lse = (M + log2f(L)) * kLn2;
   }
-  const float lse = (M + log2f(L)) * kLn2;
   (p ? col_lse : row_lse)[row] = lse;
   if (p == 0 && diag) diag[row] = s * diag_cos[row];
 }
@@ -54,8 +94,8 @@ loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse
 constexpr int kFinWarps = 8;
 constexpr int kFinMaxVec = 8;   // D <= 1024
 
-template <int DTYPE>
-__global__ void __launch_bounds__(kFinWarps * 32)
+template <int DTYPE, int NV>
+__global__ void __launch_bounds__(kFinWarps * 32, 3)
 finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_local, int D,
                     const float* __restrict__ scale /* [s, flows] */, const float* __restrict__ grad_out,
                     const void* __restrict__ x1, const void* __restrict__ x2, int64_t ld1, int64_t ld2,
@@ -74,22 +114,32 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
     const int64_t ld = p ? ld2 : ld1;
     const int nvec = D >> 2;
     const float sg = s * g;
-    float4 v[kFinMaxVec], a[kFinMaxVec];
+    float4 v[NV], a[NV];
     float dot = 0.f;
     const float inv = already ? 1.0f : (p ? inv2 : inv1)[row];
+    // all loads of the row (first chunk partial + x) are issued before anything depends on them
 #pragma unroll
-    for (int k = 0; k < kFinMaxVec; ++k) {
-      int c = lane + 32 * k;
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < nvec) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ch = 0; ch < n_chunks; ++ch) {
+        v[k] = __ldg(reinterpret_cast<const float4*>(pb) + c);
+        if (!already) a[k] = load4<DTYPE>(x, row * ld + 4 * c);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        float4 acc = v[k];
+        for (int ch = 1; ch < n_chunks; ++ch) {
           float4 q = __ldg(reinterpret_cast<const float4*>(pb + (int64_t)ch * rows_local * D) + c);
           acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
         }
         acc.x *= sg; acc.y *= sg; acc.z *= sg; acc.w *= sg;
         v[k] = acc;
         if (!already) {
-          float4 q = load4<DTYPE>(x, row * ld + 4 * c);
+          float4 q = a[k];
           q.x *= inv; q.y *= inv; q.z *= inv; q.w *= inv;
           a[k] = q;
           dot += q.x * acc.x + q.y * acc.y + q.z * acc.z + q.w * acc.w;
@@ -98,7 +148,7 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
     }
     if (!already) dot = warp_sum(dot);
 #pragma unroll
-    for (int k = 0; k < kFinMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       int c = lane + 32 * k;
       if (c < nvec) {
         float4 o = v[k];
@@ -124,14 +174,25 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
   }
 }
 
-int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local,
-                         const float* logit_scale, float scale_cap, const float* diag_cos,
-                         float* row_lse, float* col_lse, float* diag, float* scale_out, cudaStream_t st) {
+int colsum_reduce_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_global, const float* logit_scale,
+                         float scale_cap, float* colsum, cudaStream_t st) {
+  dim3 grid((unsigned)((rows_global + 255) / 256), kColSumSplit);
+  colsum_reduce_kernel<<<grid, 256, 0, st>>>(ws.colpart, plan.n_rowgroups, rows_global, colsum, logit_scale, scale_cap,
+                                             pair_fast_s2_limit());
+  VPA_LAUNCH_CHECK("colsum_reduce_kernel");
+  return 0;
+}
+
+int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int64_t rows_global,
+                         int64_t row_offset, const float* logit_scale, float scale_cap, const float* diag_cos,
+                         int fast, const float* colsum, float* row_lse, float* col_lse, float* diag, float* scale_out,
+                         cudaStream_t st) {
   const int threads = 256;
   const int64_t n = 2 * rows_local;
   dim3 grid((unsigned)((n + threads - 1) / threads));
   combine_stats_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
-                                                 rows_local, logit_scale, scale_cap, diag_cos, row_lse, col_lse,
+                                                 plan.fwd1_chunks, rows_local, rows_global, row_offset, logit_scale,
+                                                 scale_cap, diag_cos, fast, pair_fast_s2_limit(), colsum, row_lse, col_lse,
                                                  diag, scale_out);
   VPA_LAUNCH_CHECK("combine_stats_kernel");
   return 0;
@@ -151,13 +212,24 @@ int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows
   VPA_CHECK_ARG(D <= 128 * kFinMaxVec, "finalize: D=%d > %d unsupported", D, 128 * kFinMaxVec);
   const int64_t n = 2 * rows_local;
   dim3 grid((unsigned)((n + kFinWarps - 1) / kFinWarps)), block(kFinWarps * 32);
-#define VPA_FIN(DT)                                                                                        \
-  finalize_bwd_kernel<DT><<<grid, block, 0, st>>>(ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, grad_out, \
-                                                  x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2,         \
-                                                  ws.dscale_part, plan.n_dscale, dlogit_scale)
-  if (in_dtype == VPA_F32) VPA_FIN(VPA_F32);
-  else if (in_dtype == VPA_BF16) VPA_FIN(VPA_BF16);
-  else VPA_FIN(VPA_F16);
+  const int nv = D <= 128 ? 1 : (D <= 256 ? 2 : (D <= 512 ? 4 : 8));
+#define VPA_FIN(DT, NV)                                                                                            \
+  finalize_bwd_kernel<DT, NV><<<grid, block, 0, st>>>(ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, grad_out, \
+                                                      x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2,             \
+                                                      ws.dscale_part, plan.n_dscale, dlogit_scale)
+#define VPA_FIN_NV(DT)                 \
+  switch (nv) {                        \
+    case 1: VPA_FIN(DT, 1); break;     \
+    case 2: VPA_FIN(DT, 2); break;     \
+    case 4: VPA_FIN(DT, 4); break;     \
+    default: VPA_FIN(DT, 8); break;    \
+  }
+  prof_begin(PROF_FINALIZE, st);
+  if (in_dtype == VPA_F32) { VPA_FIN_NV(VPA_F32) }
+  else if (in_dtype == VPA_BF16) { VPA_FIN_NV(VPA_BF16) }
+  else { VPA_FIN_NV(VPA_F16) }
+  prof_end(PROF_FINALIZE, st);
+#undef VPA_FIN_NV
 #undef VPA_FIN
   VPA_LAUNCH_CHECK("finalize_bwd_kernel");
   return 0;

@@ -70,9 +70,11 @@ normalize_cast_kernel(const void* __restrict__ x, int64_t rows, int D, int64_t l
   normalize_row<DTYPE, IN_REGS>(x, ld, row, D, already != 0, y_bf16, y_f32, inv_norm, lane, keep, inv);
 }
 
-// Both modalities + the diagonal cosine <a_i, t_i> in one launch (training path).
-template <int DTYPE>
-__global__ void __launch_bounds__(kNormWarps * 32)
+// Both modalities + the diagonal cosine <a_i, t_i> in one launch (training path).  NV = float4 chunks per lane
+// (D <= 128*NV): all 2*NV 16-byte loads of a row pair are issued before anything depends on them, and the small
+// register footprint keeps >= 32 warps per SM resident -- the kernel is pure HBM streaming.
+template <int DTYPE, int NV>
+__global__ void __launch_bounds__(kNormWarps * 32, NV <= 4 ? 4 : 2)
 normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int64_t rows, int D,
                       int64_t ld1, int64_t ld2, int already,
                       __nv_bfloat16* __restrict__ a_bf16, __nv_bfloat16* __restrict__ t_bf16,
@@ -82,27 +84,55 @@ normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, 
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float4 ka[kMaxVec], kt[kMaxVec];
-  float i1, i2;
-  normalize_row<DTYPE, true>(x1, ld1, row, D, already != 0, a_bf16, a_f32, inv1, lane, ka, i1);
-  normalize_row<DTYPE, true>(x2, ld2, row, D, already != 0, t_bf16, t_f32, inv2, lane, kt, i2);
-  if (diag_cos) {
-    const int nvec = D >> 2;
-    float dot = 0.f;
+  const int nvec = D >> 2;
+  float4 ka[NV], kt[NV];
 #pragma unroll
-    for (int v = 0; v < kMaxVec; ++v) {
-      int c = lane + 32 * v;
-      if (c < nvec) {
-        float4 p = ka[v], q = kt[v];
-        if (diag_from_bf16) {  // what the tensor cores will multiply: bf16-rounded operands
-          p.x = __bfloat162float(__float2bfloat16_rn(p.x)); p.y = __bfloat162float(__float2bfloat16_rn(p.y));
-          p.z = __bfloat162float(__float2bfloat16_rn(p.z)); p.w = __bfloat162float(__float2bfloat16_rn(p.w));
-          q.x = __bfloat162float(__float2bfloat16_rn(q.x)); q.y = __bfloat162float(__float2bfloat16_rn(q.y));
-          q.z = __bfloat162float(__float2bfloat16_rn(q.z)); q.w = __bfloat162float(__float2bfloat16_rn(q.w));
-        }
-        dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
-      }
+  for (int v = 0; v < NV; ++v) {
+    const int c = lane + 32 * v;
+    ka[v] = kt[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nvec) {
+      ka[v] = load4<DTYPE>(x1, row * ld1 + 4 * c);
+      kt[v] = load4<DTYPE>(x2, row * ld2 + 4 * c);
     }
+  }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    s1 += ka[v].x * ka[v].x + ka[v].y * ka[v].y + ka[v].z * ka[v].z + ka[v].w * ka[v].w;
+    s2 += kt[v].x * kt[v].x + kt[v].y * kt[v].y + kt[v].z * kt[v].z + kt[v].w * kt[v].w;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float n1 = already ? 1.0f : sqrtf(s1), n2 = already ? 1.0f : sqrtf(s2);
+  if (lane == 0) {
+    if (inv1) inv1[row] = 1.0f / n1;
+    if (inv2) inv2[row] = 1.0f / n2;
+  }
+  float dot = 0.f;
+  const int64_t obase = row * (int64_t)D;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = lane + 32 * v;
+    if (c < nvec) {
+      float4 p = ka[v], q = kt[v];
+      if (!already) {   // true division, as the reference does (x / norm)
+        p.x = p.x / n1; p.y = p.y / n1; p.z = p.z / n1; p.w = p.w / n1;
+        q.x = q.x / n2; q.y = q.y / n2; q.z = q.z / n2; q.w = q.w / n2;
+      }
+      if (a_f32) store4<VPA_F32>(a_f32, obase + 4 * c, p);
+      if (t_f32) store4<VPA_F32>(t_f32, obase + 4 * c, q);
+      if (a_bf16) store4<VPA_BF16>(a_bf16, obase + 4 * c, p);
+      if (t_bf16) store4<VPA_BF16>(t_bf16, obase + 4 * c, q);
+      if (diag_from_bf16) {  // what the tensor cores will multiply: bf16-rounded operands
+        p.x = __bfloat162float(__float2bfloat16_rn(p.x)); p.y = __bfloat162float(__float2bfloat16_rn(p.y));
+        p.z = __bfloat162float(__float2bfloat16_rn(p.z)); p.w = __bfloat162float(__float2bfloat16_rn(p.w));
+        q.x = __bfloat162float(__float2bfloat16_rn(q.x)); q.y = __bfloat162float(__float2bfloat16_rn(q.y));
+        q.z = __bfloat162float(__float2bfloat16_rn(q.z)); q.w = __bfloat162float(__float2bfloat16_rn(q.w));
+      }
+      dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
+    }
+  }
+  if (diag_cos) {
     dot = warp_sum(dot);
     if (lane == 0) diag_cos[row] = dot;
   }
@@ -150,13 +180,23 @@ int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t 
   dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps)), block(kNormWarps * 32);
   auto* ab = reinterpret_cast<__nv_bfloat16*>(a_bf16);
   auto* tb = reinterpret_cast<__nv_bfloat16*>(t_bf16);
+  const int nv = D <= 128 ? 1 : (D <= 256 ? 2 : (D <= 512 ? 4 : 8));
   prof_begin(PROF_NORMALIZE, st);
-  if (in_dtype == VPA_F32)
-    normalize_pair_kernel<VPA_F32><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
-  else if (in_dtype == VPA_BF16)
-    normalize_pair_kernel<VPA_BF16><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
-  else
-    normalize_pair_kernel<VPA_F16><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16);
+#define VPA_PAIR(DT, NV)                                                                                               \
+  normalize_pair_kernel<DT, NV><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, \
+                                                        inv2, diag_cos, diag_from_bf16)
+#define VPA_PAIR_NV(DT)                 \
+  switch (nv) {                         \
+    case 1: VPA_PAIR(DT, 1); break;     \
+    case 2: VPA_PAIR(DT, 2); break;     \
+    case 4: VPA_PAIR(DT, 4); break;     \
+    default: VPA_PAIR(DT, 8); break;    \
+  }
+  if (in_dtype == VPA_F32) { VPA_PAIR_NV(VPA_F32) }
+  else if (in_dtype == VPA_BF16) { VPA_PAIR_NV(VPA_BF16) }
+  else { VPA_PAIR_NV(VPA_F16) }
+#undef VPA_PAIR_NV
+#undef VPA_PAIR
   prof_end(PROF_NORMALIZE, st);
   VPA_LAUNCH_CHECK("normalize_pair_kernel");
   return 0;

@@ -94,21 +94,32 @@ class _CudaKernels:
             _ptr(inv[0]), _ptr(inv[1]), _ptr(dcos), int(tc), _stream()), "vpa_normalize_pair")
         return a, t, inv, dcos
 
-    def forward_stats(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, dcos, precision):
+    def forward_sweep(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, precision):
+        """Enqueue the forward sweeps.  Returns (col_sum, ws): col_sum (VPA_COLSUM_SPLIT, B) holds, in the single-pass
+        regime, the column sums over the LOCAL rows (to be all-reduced over the ranks); zeros otherwise."""
         lib = _cabi.lib()
         b, D = a.shape
         B = a_all.shape[0]
         dev = a.device
         ws_bytes = lib.vpa_infonce_workspace_bytes(b, B, D, precision)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        col_sum = torch.empty((lib.vpa_infonce_colsum_floats(B) // B, B), dtype=torch.float32, device=dev)
+        cap = float(scale_max) if scale_max else 0.0                     # 0 -> no clamp (`or inf`, :254)
+        _cabi.check(lib.vpa_infonce_fwd_sweep(
+            _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(logit_scale), cap,
+            _ptr(ws), ws_bytes, _ptr(col_sum), _stream()), "vpa_infonce_fwd_sweep")
+        return col_sum, ws
+
+    def forward_finish(self, b, B, D, row_offset, logit_scale, scale_max, dcos, precision, ws, col_sum):
+        lib = _cabi.lib()
+        dev = dcos.device
         stats = torch.empty((3, b), dtype=torch.float32, device=dev)     # row_lse, col_lse, diag
         scale = torch.empty((2,), dtype=torch.float32, device=dev)       # s, grad-flows flag
-        cap = float(scale_max) if scale_max else 0.0                     # 0 -> no clamp (`or inf`, :254)
-        _cabi.check(lib.vpa_infonce_fwd(
-            _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(logit_scale), cap,
-            _ptr(dcos), _ptr(ws), ws_bytes, _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(scale), _stream()),
-            "vpa_infonce_fwd")
-        return stats, scale, ws
+        cap = float(scale_max) if scale_max else 0.0
+        _cabi.check(lib.vpa_infonce_fwd_finish(
+            precision, b, B, D, row_offset, _ptr(logit_scale), cap, _ptr(dcos), _ptr(ws), ws.numel(), _ptr(col_sum),
+            _ptr(stats[0]), _ptr(stats[1]), _ptr(stats[2]), _ptr(scale), _stream()), "vpa_infonce_fwd_finish")
+        return stats, scale
 
     def loss(self, stats_all):
         B = stats_all.shape[1]
@@ -141,11 +152,12 @@ _KERNELS = _CudaKernels()
 def _sharded_forward(kern, x1, x2, logit_scale, scale_max, normalized, precision, group):
     """Row-sharded global-batch forward: rank r owns rows [r*b, (r+1)*b).
 
-    normalise locally -> all-gather the normalised features -> row logsumexp of the local x1 rows against ALL
-    x2 rows and column logsumexp of the local x2 rows against ALL x1 rows (both complete, no partial
-    statistics to reduce) -> all-gather the three (b,) statistic vectors -> identical global loss on every rank.
+    normalise locally -> all-gather the normalised features -> forward sweeps of the local rows against ALL rows
+    -> all-reduce of the (8, B) column sums (the one exchange step; only meaningful in the single-pass regime, where
+    each rank holds the sums over its own rows) -> statistics of the local rows -> all-gather of the three (b,)
+    statistic vectors -> identical global loss on every rank.
     """
-    b = x1.shape[0]
+    b, D = x1.shape
     world = dist.get_world_size(group) if group is not None else 1
     rank = dist.get_rank(group) if group is not None else 0
     a, t, inv, dcos = kern.normalize_pair(x1, x2, normalized, precision)
@@ -156,7 +168,10 @@ def _sharded_forward(kern, x1, x2, logit_scale, scale_max, normalized, precision
         dist.all_gather_into_tensor(t_all, t, group=group)
     else:
         a_all, t_all = a, t
-    stats, scale, ws = kern.forward_stats(a, t, a_all, t_all, rank * b, logit_scale, scale_max, dcos, precision)
+    col_sum, ws = kern.forward_sweep(a, t, a_all, t_all, rank * b, logit_scale, scale_max, precision)
+    if world > 1:
+        dist.all_reduce(col_sum, group=group)
+    stats, scale = kern.forward_finish(b, b * world, D, rank * b, logit_scale, scale_max, dcos, precision, ws, col_sum)
     if world > 1:
         gathered = torch.empty((world * 3, b), dtype=stats.dtype, device=stats.device)
         dist.all_gather_into_tensor(gathered, stats.contiguous(), group=group)

@@ -107,6 +107,8 @@ int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, con
  * reduced in fixed order to col_sum[VPA_COLSUM_SPLIT][rows_global].  The caller all-reduces (SUM) col_sum over the
  * ranks and calls _finish, which turns the sums into row_lse / col_lse / diag of the local rows.  For larger s (decided
  * on the device, no host sync) the exact two-sweep kernel runs instead and col_sum is zero / ignored.
+ * `parts`: 3 = everything; 1 = only the single-pass kernel, which reads a_loc and t_all (so the all-gather of a_all can
+ * still be in flight); 2 = the rest (exact kernel + column-sum reduction), which reads all four operands.  Call 1 then 2.
  * vpa_infonce_fwd == _sweep + _finish with an internal col_sum; when rows_local < rows_global it always takes the
  * exact two-sweep route (no exchange needed). */
 #define VPA_COLSUM_SPLIT 8
@@ -114,7 +116,7 @@ size_t vpa_infonce_colsum_floats(int64_t rows_global);
 int vpa_infonce_fwd_sweep(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all,
                           int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
                           const float* logit_scale, float scale_max, void* workspace, size_t workspace_bytes,
-                          float* col_sum, void* stream);
+                          float* col_sum, int parts, void* stream);
 int vpa_infonce_fwd_finish(int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
                            const float* logit_scale, float scale_max, const float* diag_cos, void* workspace,
                            size_t workspace_bytes, const float* col_sum, float* row_lse, float* col_lse,

@@ -108,7 +108,9 @@ class _CheckerKernels:
             a, t = x1 / n1[:, None], x2 / n2[:, None]
         return a, t, torch.stack([1 / n1, 1 / n2]), (a * t).sum(-1)
 
-    def forward_sweep(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, precision):
+    def forward_sweep(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, precision, before_part2=None):
+        if before_part2 is not None:
+            before_part2()
         # single-pass regime: row sums are local, column sums are partial over the ranks -> all-reduced by the caller
         s, _ = io.effective_scale(float(logit_scale), scale_max)
         S = s * a @ t_all.T

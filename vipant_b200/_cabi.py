@@ -29,7 +29,7 @@ _SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_infonce_colsum_floats": (c_size_t, [c_int64]),
     "vpa_infonce_fwd_sweep": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int64,
-                                      c_void_p, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                      c_void_p, c_float, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "vpa_infonce_fwd_finish": (c_int, [c_int, c_int64, c_int64, c_int, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_infonce_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -122,12 +122,22 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
     p.pair_bwd_iblk = (int)((rows_local + 127) / 128);
     p.n_tiles = (int)((rows_global + 255) / 256);
     pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
-    pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 1, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
+    // per-unit fixed cost (prologue, X load, pipeline fill, dX drain) measured at ~3.5 tiles of 256 columns (b=4096 sweep)
+    pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
     p.n_dscale = 2 * p.pair_bwd_iblk * p.bwd_chunks;
     p.fast_fwd = 1;
     if (const char* e = getenv("VPA_FAST_FWD")) p.fast_fwd = atoi(e) != 0;          // A/B knob
-    pick_chunks(p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2);
+    pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2);
     p.n_rowgroups = p.pair_fwd_iblk * 8;
+    auto force = [&](const char* name, int* chunks, int* tpc) {     // tuning knobs for measurements
+      if (const char* e = getenv(name)) {
+        const int c = atoi(e);
+        if (c >= 1 && c <= p.n_tiles) { *tpc = (p.n_tiles + c - 1) / c; *chunks = (p.n_tiles + *tpc - 1) / *tpc; }
+      }
+    };
+    force("VPA_FWD1_CHUNKS", &p.fwd1_chunks, &p.fwd1_tiles_per_chunk);
+    force("VPA_BWD_CHUNKS", &p.bwd_chunks, &p.bwd_tiles_per_chunk);
+    p.n_dscale = 2 * p.pair_bwd_iblk * p.bwd_chunks;
     return p;
   }
   p.fwd1_chunks = 1;
@@ -234,7 +244,7 @@ size_t vpa_infonce_colsum_floats(int64_t rows_global) { return rows_global > 0 ?
 static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
                           int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
                           float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, bool allow_fast,
-                          cudaStream_t st) {
+                          int parts, cudaStream_t st) {
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && workspace, "infonce_fwd_sweep: null pointer");
   const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
@@ -246,12 +256,19 @@ static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_al
   a.logit_scale = logit_scale;
   a.scale_cap = (scale_max > 0.f) ? scale_max : INFINITY;     // `cfg.scale_max or float("inf")`
   float* cs = col_sum ? col_sum : ws.colsum;
-  VPA_CUDA(cudaMemsetAsync(cs, 0, (size_t)kColSumSplit * rows_global * sizeof(float), st));
-  if (precision != VPA_PREC_BF16_TC) return simt_infonce_fwd(a, ws, plan, st);
-  if (plan.impl != 1) return tc_infonce_fwd(a, ws, plan, st);
-  const bool fast = plan.fast_fwd && allow_fast;
-  if (int e = pair_infonce_fwd(a, ws, plan, fast, st)) return e;
-  if (fast) return colsum_reduce_launch(ws, plan, rows_global, logit_scale, a.scale_cap, cs, st);
+  const bool fast = precision == VPA_PREC_BF16_TC && plan.impl == 1 && plan.fast_fwd && allow_fast;
+  if (parts & 1) {
+    VPA_CUDA(cudaMemsetAsync(cs, 0, (size_t)kColSumSplit * rows_global * sizeof(float), st));
+    if (fast) {
+      if (int e = pair_infonce_fwd(a, ws, plan, 1, st)) return e;
+    }
+  }
+  if (parts & 2) {
+    if (precision != VPA_PREC_BF16_TC) return simt_infonce_fwd(a, ws, plan, st);
+    if (plan.impl != 1) return tc_infonce_fwd(a, ws, plan, st);
+    if (int e = pair_infonce_fwd(a, ws, plan, fast ? 2 : 0, st)) return e;
+    if (fast) return colsum_reduce_launch(ws, plan, rows_global, logit_scale, a.scale_cap, cs, st);
+  }
   return 0;
 }
 
@@ -272,10 +289,11 @@ static int fwd_finish_impl(int precision, int64_t rows_local, int64_t rows_globa
 
 int vpa_infonce_fwd_sweep(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
                           int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
-                          float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, void* stream) {
+                          float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, int parts, void* stream) {
   VPA_CHECK_ARG(col_sum != nullptr, "infonce_fwd_sweep: null col_sum");
+  VPA_CHECK_ARG(parts >= 1 && parts <= 3, "infonce_fwd_sweep: parts must be 1, 2 or 3");
   return fwd_sweep_impl(a_loc, t_loc, a_all, t_all, precision, rows_local, rows_global, D, row_offset, logit_scale, scale_max,
-                        workspace, workspace_bytes, col_sum, true, static_cast<cudaStream_t>(stream));
+                        workspace, workspace_bytes, col_sum, true, parts, static_cast<cudaStream_t>(stream));
 }
 
 int vpa_infonce_fwd_finish(int precision, int64_t rows_local, int64_t rows_global, int D, int64_t row_offset,
@@ -295,7 +313,7 @@ int vpa_infonce_fwd(const void* a_loc, const void* t_loc, const void* a_all, con
   const bool allow_fast = rows_local == rows_global;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = fwd_sweep_impl(a_loc, t_loc, a_all, t_all, precision, rows_local, rows_global, D, row_offset, logit_scale,
-                             scale_max, workspace, workspace_bytes, nullptr, allow_fast, st)) return e;
+                             scale_max, workspace, workspace_bytes, nullptr, allow_fast, 3, st)) return e;
   return fwd_finish_impl(precision, rows_local, rows_global, D, row_offset, logit_scale, scale_max, diag_cos, workspace,
                          workspace_bytes, nullptr, allow_fast, row_lse, col_lse, diag, scale_out, st);
 }

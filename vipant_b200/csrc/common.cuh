@@ -155,7 +155,7 @@ struct SweepArgs {
 
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int tc_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
-int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, bool fast, cudaStream_t st);
+int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int which, cudaStream_t st);
 float pair_fast_s2_limit();
 int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);

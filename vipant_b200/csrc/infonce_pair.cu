@@ -635,6 +635,13 @@ static EncodeTiledFn get_encode() {
 static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(VPA_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  // The encode is a DRIVER call and needs a current context in THIS thread; a thread that has not touched the
+  // runtime yet (e.g. an autograd worker on device 0) has none -> bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)D * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBoxK, (cuuint32_t)box_rows};
@@ -707,12 +714,13 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
 
 }  // namespace pr
 
-// Forward.  With `fast` the single-pass kernel (valid while s*log2e <= 62) and the exact two-problem kernel are
-// both enqueued; each checks the DEVICE value of the temperature and returns at once when it is not its regime.
-int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, bool fast, cudaStream_t st) {
-  if (!fast) return pr::launch<pr::MODE_FWD>(a, ws, plan, 0, st);
-  if (int e = pr::launch<pr::MODE_FWD1>(a, ws, plan, 1, st)) return e;
-  return pr::launch<pr::MODE_FWD>(a, ws, plan, 2, st);
+// Forward.  In the fast configuration the single-pass kernel (valid while s*log2e <= 62) and the exact two-problem
+// kernel are both enqueued; each checks the DEVICE value of the temperature and returns at once when it is not its regime.
+// which: 0 = exact kernel unconditionally; 1 = single-pass kernel (reads x[0] = local x1 rows and y[0] = all x2 rows
+// only), gated on s*log2e <= 62; 2 = exact kernel gated on the complementary regime.
+int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int which, cudaStream_t st) {
+  if (which == 1) return pr::launch<pr::MODE_FWD1>(a, ws, plan, 1, st);
+  return pr::launch<pr::MODE_FWD>(a, ws, plan, which == 2 ? 2 : 0, st);
 }
 int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
   return pr::launch<pr::MODE_BWD>(a, ws, plan, 0, st);

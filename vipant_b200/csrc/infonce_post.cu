@@ -77,17 +77,46 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
 __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
             const float* __restrict__ diag, int64_t B, float* __restrict__ loss) {
-  __shared__ double red[1024];
+  __shared__ double red[32];
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < B; i += 1024)
-    acc += ((double)row_lse[i] - (double)diag[i]) + ((double)col_lse[i] - (double)diag[i]);
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
+  // one block, fixed order; the loads of four consecutive strides are issued together (the kernel is pure latency)
+  const bool vec = (B % 4 == 0) && ((reinterpret_cast<uintptr_t>(row_lse) | reinterpret_cast<uintptr_t>(col_lse) |
+                                     reinterpret_cast<uintptr_t>(diag)) % 16 == 0);
+  if (vec) {
+    const int64_t n4 = B / 4;
+    const float4* r4 = reinterpret_cast<const float4*>(row_lse);
+    const float4* c4 = reinterpret_cast<const float4*>(col_lse);
+    const float4* d4 = reinterpret_cast<const float4*>(diag);
+    for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 4 * 1024) {
+      float4 r[4], c[4], d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * 1024;
+        if (i < n4) { r[u] = __ldg(r4 + i); c[u] = __ldg(c4 + i); d[u] = __ldg(d4 + i); }
+        else { r[u] = c[u] = d[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc += ((double)r[u].x - (double)d[u].x) + ((double)c[u].x - (double)d[u].x);
+        acc += ((double)r[u].y - (double)d[u].y) + ((double)c[u].y - (double)d[u].y);
+        acc += ((double)r[u].z - (double)d[u].z) + ((double)c[u].z - (double)d[u].z);
+        acc += ((double)r[u].w - (double)d[u].w) + ((double)c[u].w - (double)d[u].w);
+      }
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < B; i += 1024)
+      acc += ((double)row_lse[i] - (double)diag[i]) + ((double)col_lse[i] - (double)diag[i]);
   }
-  if (threadIdx.x == 0) *loss = (float)(red[0] / (double)B);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *loss = (float)(v / (double)B);
+  }
 }
 
 // ---- backward finalisation -------------------------------------------------------------------------

@@ -551,6 +551,13 @@ static EncodeTiledFn get_encode() {
 static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_error(VPA_E_NO_DEVICE, "cuTensorMapEncodeTiled entry point unavailable");
+  // The encode is a DRIVER call and needs a current context in THIS thread; a thread that has not touched the
+  // runtime yet (e.g. an autograd worker on device 0) has none -> bind the primary context once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)D * 2};
   cuuint32_t box[2] = {(cuuint32_t)kBoxK, (cuuint32_t)box_rows};

@@ -94,9 +94,11 @@ class _CudaKernels:
             _ptr(inv[0]), _ptr(inv[1]), _ptr(dcos), int(tc), _stream()), "vpa_normalize_pair")
         return a, t, inv, dcos
 
-    def forward_sweep(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, precision):
+    def forward_sweep(self, a, t, a_all, t_all, row_offset, logit_scale, scale_max, precision, before_part2=None):
         """Enqueue the forward sweeps.  Returns (col_sum, ws): col_sum (VPA_COLSUM_SPLIT, B) holds, in the single-pass
-        regime, the column sums over the LOCAL rows (to be all-reduced over the ranks); zeros otherwise."""
+        regime, the column sums over the LOCAL rows (to be all-reduced over the ranks); zeros otherwise.
+        `before_part2()` (optional) runs between the single-pass kernel, which only reads a and t_all, and the rest,
+        which also reads a_all: the place to wait for an in-flight all-gather of a_all."""
         lib = _cabi.lib()
         b, D = a.shape
         B = a_all.shape[0]
@@ -105,9 +107,12 @@ class _CudaKernels:
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         col_sum = torch.empty((lib.vpa_infonce_colsum_floats(B) // B, B), dtype=torch.float32, device=dev)
         cap = float(scale_max) if scale_max else 0.0                     # 0 -> no clamp (`or inf`, :254)
-        _cabi.check(lib.vpa_infonce_fwd_sweep(
-            _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(logit_scale), cap,
-            _ptr(ws), ws_bytes, _ptr(col_sum), _stream()), "vpa_infonce_fwd_sweep")
+        for parts in ((1, 2) if before_part2 is not None else (3,)):
+            if parts == 2:
+                before_part2()
+            _cabi.check(lib.vpa_infonce_fwd_sweep(
+                _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(logit_scale), cap,
+                _ptr(ws), ws_bytes, _ptr(col_sum), parts, _stream()), "vpa_infonce_fwd_sweep")
         return col_sum, ws
 
     def forward_finish(self, b, B, D, row_offset, logit_scale, scale_max, dcos, precision, ws, col_sum):
@@ -161,14 +166,18 @@ def _sharded_forward(kern, x1, x2, logit_scale, scale_max, normalized, precision
     world = dist.get_world_size(group) if group is not None else 1
     rank = dist.get_rank(group) if group is not None else 0
     a, t, inv, dcos = kern.normalize_pair(x1, x2, normalized, precision)
+    wait_a = None
     if world > 1:
         a_all = torch.empty((b * world, a.shape[1]), dtype=a.dtype, device=a.device)
         t_all = torch.empty_like(a_all)
-        dist.all_gather_into_tensor(a_all, a, group=group)
-        dist.all_gather_into_tensor(t_all, t, group=group)
+        # x2 operands first: the single-pass forward needs only them; the gather of the x1 operands overlaps with it
+        work_t = dist.all_gather_into_tensor(t_all, t, group=group, async_op=True)
+        work_a = dist.all_gather_into_tensor(a_all, a, group=group, async_op=True)
+        work_t.wait()
+        wait_a = work_a.wait
     else:
         a_all, t_all = a, t
-    col_sum, ws = kern.forward_sweep(a, t, a_all, t_all, rank * b, logit_scale, scale_max, precision)
+    col_sum, ws = kern.forward_sweep(a, t, a_all, t_all, rank * b, logit_scale, scale_max, precision, before_part2=wait_a)
     if world > 1:
         dist.all_reduce(col_sum, group=group)
     stats, scale = kern.forward_finish(b, b * world, D, rank * b, logit_scale, scale_max, dcos, precision, ws, col_sum)

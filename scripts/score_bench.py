@@ -1,0 +1,77 @@
+"""Scoring-path measurements on one B200: AudioCaps-shaped retrieval (975 x 4875) and ESC50 zero-shot (2000 x 50).
+Kernel times come from the library's CUDA-event hooks; report() latency is wall clock with a final synchronize.
+CPU column: the oracle's numpy restatement (oracle/retrieval_oracle.py) on the host cores (reported, not a target)."""
+import ctypes, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import vipant_b200 as vb
+from vipant_b200 import _cabi
+from oracle import retrieval_oracle as ro
+from oracle.make_golden import retrieval_inputs_1v5, zero_shot_inputs
+from oracle.reference_loader import Cfg
+
+lib = _cabi.lib()
+out = {}
+
+def prof(kind):
+    tot, n = ctypes.c_float(), ctypes.c_int()
+    lib.vpa_profile_read(kind, ctypes.byref(tot), ctypes.byref(n))
+    return tot.value / max(n.value, 1) * 1e3, n.value          # us per launch
+
+def timed(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps): r = fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3, r
+
+# ---- C4: retrieval 975 audio x 4875 captions
+a, t = retrieval_inputs_1v5(n=975, seed=1213)
+ad, td = torch.from_numpy(a).cuda(), torch.from_numpy(t).cuda()
+an, tn = vb.l2_normalize(ad), vb.l2_normalize(td)
+gt12 = torch.arange(4875, device="cuda").view(975, 5); gt21 = torch.arange(4875, device="cuda") // 5
+lib.vpa_profile_enable(1)
+ms12, _ = timed(lambda: vb.sim_rank_topk(an, tn, gt12, topk=10))
+sim_us, _ = prof(3); rank_us, _ = prof(4)
+N, M, g, k = 975, 4875, 5, 10
+out["c4_a2t"] = {"call_ms": ms12, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us,
+                 "rank_bytes": 4 * N * M + 12 * N * k + 4 * N * g, "rank_gbs": (4 * N * M + 12 * N * k + 4 * N * g) / (rank_us * 1e-6) / 1e9,
+                 "sim_gflops": 2 * N * M * 512 / (sim_us * 1e-6) / 1e9}
+ms21, _ = timed(lambda: vb.sim_rank_topk(tn, an, gt21))
+sim_us, _ = prof(3); rank_us, _ = prof(4)
+out["c4_t2a"] = {"call_ms": ms21, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us,
+                 "rank_gbs": (4 * N * M + 4 * M) / (rank_us * 1e-6) / 1e9}
+lib.vpa_profile_enable(0)
+
+def full_report():
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None)).cuda().eval()
+    with torch.no_grad():
+        for i in range(0, 975, 64):
+            head(ad[i:i + 64], td[i * 5:(i + 64) * 5], normalized=False, names=None)
+    return head.report()
+ms_rep, rep = timed(full_report, reps=5)
+t0 = time.perf_counter(); rep_cpu, _, _ = ro.report(ro.normalize(a), ro.normalize(t)); cpu_ms = (time.perf_counter() - t0) * 1e3
+out["c4_report"] = {"gpu_ms_incl_infer_batches": ms_rep, "cpu_oracle_numpy_ms": cpu_ms, "strings_equal": rep == rep_cpu,
+                    "reference_cpu_ms_survey": 760.0}
+
+# ---- C5: zero-shot 2000 x 50
+audios, text, labels = zero_shot_inputs(c=50, seed=1213)
+au, tx = torch.from_numpy(audios).cuda(), torch.from_numpy(text).cuda()
+lib.vpa_profile_enable(1)
+ms_zs, _ = timed(lambda: vb.sim_rank_topk(au, tx, None, topk=1))
+sim_us, _ = prof(3); rank_us, _ = prof(4)
+lib.vpa_profile_enable(0)
+t0 = time.perf_counter(); ro.zero_shot_report(audios, text, labels); cpu_zs = (time.perf_counter() - t0) * 1e3
+out["c5_zero_shot"] = {"call_ms": ms_zs, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us, "cpu_oracle_numpy_ms": cpu_zs}
+
+# ---- normalise kernel alone at the training shape (HBM roofline row)
+x = torch.randn(32768, 512, device="cuda")
+lib.vpa_profile_enable(1)
+x2 = torch.randn(32768, 512, device="cuda")
+from vipant_b200 import functional as F_
+timed(lambda: F_._KERNELS.normalize_pair(x, x2, False, _cabi.PREC_BF16_TC))
+nus, _ = prof(0)
+lib.vpa_profile_enable(0)
+out["normalize_pair_32768x512"] = {"kernel_us": nus, "bytes": 2 * 32768 * 512 * 6 + 12 * 32768, "gbs": (2 * 32768 * 512 * 6 + 12 * 32768) / (nus * 1e-6) / 1e9}
+print(json.dumps(out, indent=1))

@@ -43,6 +43,7 @@ extern "C" {
 #define VPA_E_WORKSPACE (-2)   /* workspace too small */
 #define VPA_E_UNSUPPORTED (-3) /* shape/precision combination not supported by this build */
 #define VPA_E_NO_DEVICE (-4)   /* no sm_100 device / driver entry point missing */
+#define VPA_E_COMM (-5)        /* NCCL could not be loaded / a collective failed */
 
 int vpa_version(void);
 const char* vpa_last_error_string(void);
@@ -163,6 +164,40 @@ int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int 
                       int64_t ldq, int64_t ldk, const int32_t* gt_idx, int g, int k,
                       int64_t* topk_idx, float* topk_val, int32_t* ranks,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-sharded training step, orchestrated inside the library: TWO calls per step (forward, backward) instead of a
+ * dozen host-side launches and five framework collectives -- at 8 GPUs the step is ~0.6 ms of kernels, so host
+ * enqueue time decides the scaling.  One process per GPU; rank r owns rows [r*b, (r+1)*b) of the global batch
+ * (B = b * world).  Semantics == loss_head.py:271-283 on the concatenated batch (the reference's `dp` mode).
+ *
+ * Communicator: NCCL, the copy the host framework ships, bound with dlopen (vpa_comm_load(path or NULL)).  Rank 0
+ * obtains a 128-byte unique id (vpa_comm_unique_id), the host broadcasts it (e.g. torch.distributed), every rank
+ * calls vpa_comm_init.  world == 1 needs no communicator (comm = NULL): the same two calls are the single-GPU step.
+ *
+ * forward:  normalise+cast the local rows straight into the gathered operand buffers -> all-gather of the x2 operands,
+ *   then of the x1 operands on a side stream (overlapping the single-pass forward, which does not read them) ->
+ *   sweeps -> per-rank message [column sums (B) | row_lse (b) | col_lse (b) | diag (b)] -> ONE all-gather ->
+ *   statistics of all rows + the global loss (identical on every rank).  Everything the backward needs stays in `state`.
+ * backward: recompute sweeps for the local rows, d(global loss)/d(local rows) into dx1 / dx2 (dtype / ld of x1 / x2),
+ *   d logit_scale all-reduced over the ranks.
+ * ------------------------------------------------------------------------------------------ */
+int vpa_comm_load(const char* libnccl_path);
+int vpa_comm_unique_id(void* out128);
+int vpa_comm_init(const void* id128, int rank, int world, void** comm_out);
+int vpa_comm_destroy(void* comm);
+
+size_t vpa_sharded_state_bytes(int64_t rows_local, int world, int D, int precision);
+
+int vpa_infonce_fwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t rows_local, int world,
+                            int rank, int D, int64_t ld1, int64_t ld2, int already_normalized,
+                            const float* logit_scale, float scale_max, int precision, void* state,
+                            size_t state_bytes, float* loss_out, void* stream);
+
+int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t rows_local, int world,
+                            int rank, int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
+                            const float* grad_out, void* state, size_t state_bytes, void* dx1, void* dx2,
+                            float* dlogit_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (the end-to-end call timed as `e2e` in bench.py): pageable or

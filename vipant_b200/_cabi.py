@@ -36,6 +36,15 @@ _SIGNATURES = {
     "vpa_infonce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int64,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpa_comm_load": (c_int, [c_char_p]),
+    "vpa_comm_unique_id": (c_int, [c_void_p]),
+    "vpa_comm_init": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "vpa_comm_destroy": (c_int, [c_void_p]),
+    "vpa_sharded_state_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+    "vpa_infonce_fwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
+                                        c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "vpa_infonce_bwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
+                                        c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_sim_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vpa_sim_rank_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

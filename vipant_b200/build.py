@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvipant_b200.so")
-SOURCES = ["api.cu", "normalize.cu", "infonce_post.cu", "infonce_simt.cu", "infonce_tc.cu", "infonce_pair.cu", "retrieval.cu"]
+SOURCES = ["api.cu", "normalize.cu", "infonce_post.cu", "infonce_simt.cu", "infonce_tc.cu", "infonce_pair.cu", "retrieval.cu", "comm.cu"]
 HEADERS = ["common.cuh", "simt_dot.cuh", os.path.join("..", "..", "include", "vipant_b200.h")]
 
 NVCC_FLAGS = [
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-cudart", "static",
-            "-Xcompiler", "-fPIC", "-o", LIB_PATH + ".tmp"] + objs
+            "-Xcompiler", "-fPIC", "-o", LIB_PATH + ".tmp"] + objs + ["-ldl"]
     subprocess.run(link, check=True)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH

@@ -57,6 +57,10 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
                          int64_t row_offset, const float* logit_scale, float scale_cap, const float* diag_cos,
                          int fast, const float* colsum, float* row_lse, float* col_lse, float* diag, float* scale_out,
                          cudaStream_t st);
+int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
+                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg, cudaStream_t st);
+int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
+                       float* stats_all, float* scale_out, cudaStream_t st);
 int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
                 cudaStream_t st);
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
@@ -365,6 +369,142 @@ int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int 
     return set_error(VPA_E_WORKSPACE, "sim_rank_topk: workspace %zu < %zu", workspace_bytes, vpa_sim_workspace_bytes(N, M));
   return sim_rank_topk_launch(Q, K, N, M, D, ldq, ldk, gt_idx, g, k, topk_idx, topk_val, ranks,
                               static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+// ---- row-sharded step orchestrated in the library (two calls per training step) ------------------------------------
+struct ShardState {
+  void *a_all, *t_all;          // (B, D) operands: bf16 (tensor-core mode) or fp32; this rank's rows are written in place
+  float *inv1, *inv2, *dcos;    // (b,)
+  float *colsum8, *msg, *msgs;  // (8, B); (B + 3b); (R, B + 3b)
+  float *stats_all, *scale;     // (3, B); (2,)
+  void* ws;
+  size_t ws_bytes, bytes;
+};
+static ShardState carve_state(void* base, int64_t b, int world, int D, int precision) {
+  ShardState h{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t B = b * world;
+  const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
+  h.a_all = take((size_t)B * D * es);
+  h.t_all = take((size_t)B * D * es);
+  h.inv1 = (float*)take(b * 4); h.inv2 = (float*)take(b * 4); h.dcos = (float*)take(b * 4);
+  h.colsum8 = (float*)take((size_t)kColSumSplit * B * 4);
+  h.msg = (float*)take((size_t)(B + 3 * b) * 4);
+  h.msgs = world > 1 ? (float*)take((size_t)world * (B + 3 * b) * 4) : h.msg;
+  h.stats_all = (float*)take((size_t)3 * B * 4);
+  h.scale = (float*)take(16);
+  h.ws_bytes = vpa_infonce_workspace_bytes(b, B, D, precision);
+  h.ws = take(h.ws_bytes);
+  h.bytes = o;
+  return h;
+}
+
+// side stream + events: the all-gather of the x1 operands runs beside the single-pass forward, which does not read them
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, t_done = nullptr, a_done = nullptr;
+  int dev = -1;
+};
+static int side_stream(SideStream** out) {
+  static thread_local SideStream ss;
+  int dev = 0;
+  VPA_CUDA(cudaGetDevice(&dev));
+  if (!ss.s || ss.dev != dev) {
+    VPA_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+    VPA_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+    VPA_CUDA(cudaEventCreateWithFlags(&ss.t_done, cudaEventDisableTiming));
+    VPA_CUDA(cudaEventCreateWithFlags(&ss.a_done, cudaEventDisableTiming));
+    ss.dev = dev;
+  }
+  *out = &ss;
+  return 0;
+}
+
+int vpa_comm_load(const char* libnccl_path) { return comm_load(libnccl_path); }
+int vpa_comm_unique_id(void* out128) { VPA_CHECK_ARG(out128, "comm_unique_id: null"); return comm_unique_id(out128); }
+int vpa_comm_init(const void* id128, int rank, int world, void** comm_out) {
+  VPA_CHECK_ARG(id128 && comm_out && world >= 1 && rank >= 0 && rank < world, "comm_init: bad argument");
+  return comm_init(id128, rank, world, comm_out);
+}
+int vpa_comm_destroy(void* comm) { return comm_destroy(comm); }
+
+size_t vpa_sharded_state_bytes(int64_t rows_local, int world, int D, int precision) {
+  if (rows_local <= 0 || world < 1 || D <= 0) return 0;
+  return carve_state(nullptr, rows_local, world, D, precision).bytes;
+}
+
+int vpa_infonce_fwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank,
+                            int D, int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale,
+                            float scale_max, int precision, void* state, size_t state_bytes, float* loss_out,
+                            void* stream) {
+  VPA_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (world == 1 || comm), "fwd_sharded: bad world / rank / comm");
+  const int64_t B = b * world, off = (int64_t)rank * b;
+  if (int e = check_infonce_shape(b, B, D, off, precision)) return e;
+  VPA_CHECK_ARG(x1 && x2 && logit_scale && state && loss_out, "fwd_sharded: null pointer");
+  const ShardState h = carve_state(state, b, world, D, precision);
+  if (h.bytes > state_bytes) return set_error(VPA_E_WORKSPACE, "fwd_sharded: state %zu < %zu", state_bytes, h.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool tcp = precision == VPA_PREC_BF16_TC;
+  const size_t es = tcp ? 2 : 4;
+  char* a_loc = static_cast<char*>(h.a_all) + (size_t)off * D * es;
+  char* t_loc = static_cast<char*>(h.t_all) + (size_t)off * D * es;
+  if (int e = normalize_pair_launch(x1, x2, in_dtype, b, D, ld1, ld2, already_normalized, tcp ? a_loc : nullptr,
+                                    tcp ? t_loc : nullptr, tcp ? nullptr : (float*)a_loc, tcp ? nullptr : (float*)t_loc,
+                                    h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
+  SideStream* ss = nullptr;
+  if (world > 1) {
+    if (int e = side_stream(&ss)) return e;
+    const int dt = tcp ? 9 : 7;     // ncclBfloat16 / ncclFloat32
+    VPA_CUDA(cudaEventRecord(ss->fork, st));
+    VPA_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+    if (int e = comm_all_gather(comm, t_loc, h.t_all, (size_t)b * D, dt, ss->s)) return e;     // x2 operands first
+    VPA_CUDA(cudaEventRecord(ss->t_done, ss->s));
+    if (int e = comm_all_gather(comm, a_loc, h.a_all, (size_t)b * D, dt, ss->s)) return e;
+    VPA_CUDA(cudaEventRecord(ss->a_done, ss->s));
+    VPA_CUDA(cudaStreamWaitEvent(st, ss->t_done, 0));
+  }
+  // single-pass kernel (reads a_loc and t_all) ...
+  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                             h.colsum8, true, 1, st)) return e;
+  if (world > 1) VPA_CUDA(cudaStreamWaitEvent(st, ss->a_done, 0));
+  // ... then everything that also reads a_all
+  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                             h.colsum8, true, 2, st)) return e;
+  const SweepPlan plan = plan_sweep(b, B, D, precision);
+  const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
+  const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
+  const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
+  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, h.msg, st)) return e;
+  if (world > 1) {
+    if (int e = comm_all_gather(comm, h.msg, h.msgs, (size_t)(B + 3 * b), 7, st)) return e;
+  }
+  if (int e = merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, st)) return e;
+  return loss_launch(h.stats_all, h.stats_all + B, h.stats_all + 2 * B, B, loss_out, st);
+}
+
+int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank,
+                            int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
+                            const float* grad_out, void* state, size_t state_bytes, void* dx1, void* dx2,
+                            float* dlogit_scale, void* stream) {
+  VPA_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (world == 1 || comm), "bwd_sharded: bad world / rank / comm");
+  const int64_t B = b * world, off = (int64_t)rank * b;
+  VPA_CHECK_ARG(state && grad_out && dx1 && dx2 && dlogit_scale, "bwd_sharded: null pointer");
+  const ShardState h = carve_state(state, b, world, D, precision);
+  if (h.bytes > state_bytes) return set_error(VPA_E_WORKSPACE, "bwd_sharded: state %zu < %zu", state_bytes, h.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
+  const char* a_loc = static_cast<const char*>(h.a_all) + (size_t)off * D * es;
+  const char* t_loc = static_cast<const char*>(h.t_all) + (size_t)off * D * es;
+  if (int e = vpa_infonce_bwd(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B,
+                              grad_out, x1, x2, in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes,
+                              dx1, dx2, dlogit_scale, st)) return e;
+  if (world > 1) return comm_all_reduce_sum_f32(comm, dlogit_scale, dlogit_scale, 1, st);
+  return 0;
 }
 
 // ---- host-buffer end-to-end step ---------------------------------------------------------------------

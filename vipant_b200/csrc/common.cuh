@@ -106,6 +106,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- NCCL binding (comm.cu) ----------------------------------------------------------------
+struct ncclUniqueIdBlob { char internal[128]; };
+int comm_load(const char* path);
+int comm_unique_id(void* out128);
+int comm_init(const void* id128, int rank, int world, void** comm_out);
+int comm_destroy(void* comm);
+int comm_all_gather(void* comm, const void* send, void* recv, size_t count, int nccl_dtype, cudaStream_t st);
+int comm_all_reduce_sum_f32(void* comm, const void* send, void* recv, size_t count, cudaStream_t st);
+
 // ---- internal launchers (one per .cu) ----------------------------------------------------
 // Work decomposition of the two sweeps (forward statistics, backward dX).  A "unit" is one CTA's
 // work: a block of X rows swept against a contiguous chunk of 128-row Y tiles.

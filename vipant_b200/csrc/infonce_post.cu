@@ -73,6 +73,82 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
   if (p == 0 && diag) diag[row] = s * diag_cos[row];
 }
 
+// ---- row-sharded step: the per-rank message around the ONE statistics all-gather --------------------------------
+// msg = [ col_sum (B) | row_lse (b) | col_lse_local (b) | diag (b) ]:  col_sum = this rank's column sums over its own
+// rows (single-pass regime; zero otherwise), col_lse_local = column lse of the local rows (exact regime; zero otherwise).
+__global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks, int n_chunks_fast, int64_t b, int64_t B,
+                                  const float* __restrict__ logit_scale, float scale_cap,
+                                  const float* __restrict__ diag_cos, int fast, float s2_limit,
+                                  const float* __restrict__ colsum8, float* __restrict__ msg) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float s = fminf(expf(*logit_scale), scale_cap);
+  const float s2 = s * kLog2e;
+  const bool fastr = fast && s2 <= s2_limit;
+  if (idx < B) {
+    float L = 0.f;
+    if (fastr)
+      for (int g = 0; g < kColSumSplit; ++g) L += colsum8[(int64_t)g * B + idx];
+    msg[idx] = L;
+  }
+  if (idx < b) {
+    float rl, cl = 0.f;
+    if (fastr) {
+      float L = 0.f;
+      for (int c = 0; c < n_chunks_fast; ++c) {
+        const float2 h = part[(int64_t)c * b + idx];
+        L += h.x + h.y;
+      }
+      rl = (s2 + log2f(L)) * kLn2;
+    } else {
+      float lse[2];
+      for (int p = 0; p < 2; ++p) {
+        const float2* base = part + (int64_t)p * n_chunks * b + idx;
+        float M = -INFINITY;
+        for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, base[(int64_t)c * b].x);
+        float L = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          const float2 ml = base[(int64_t)c * b];
+          L += ml.y * exp2f(ml.x - M);
+        }
+        lse[p] = (M + log2f(L)) * kLn2;
+      }
+      rl = lse[0];
+      cl = lse[1];
+    }
+    msg[B + idx] = rl;
+    msg[B + b + idx] = cl;
+    msg[B + 2 * b + idx] = s * diag_cos[idx];
+  }
+}
+
+// msgs[R][B + 3b] (all-gathered) -> stats_all = [row_lse (B) | col_lse (B) | diag (B)], scale_out
+__global__ void merge_stats_kernel(const float* __restrict__ msgs, int R, int64_t b, int64_t B,
+                                   const float* __restrict__ logit_scale, float scale_cap, int fast, float s2_limit,
+                                   float* __restrict__ stats_all, float* __restrict__ scale_out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float e = expf(*logit_scale);
+  const float s = fminf(e, scale_cap);
+  if (j == 0 && scale_out) {
+    scale_out[0] = s;
+    scale_out[1] = (e <= scale_cap) ? 1.0f : 0.0f;
+  }
+  if (j >= B) return;
+  const int64_t stride = B + 3 * b;
+  const int r = (int)(j / b);
+  const int64_t i = j - (int64_t)r * b;
+  const float* own = msgs + (int64_t)r * stride;
+  stats_all[j] = own[B + i];
+  stats_all[2 * B + j] = own[B + 2 * b + i];
+  const float s2 = s * kLog2e;
+  if (fast && s2 <= s2_limit) {
+    float L = 0.f;
+    for (int q = 0; q < R; ++q) L += msgs[(int64_t)q * stride + j];      // fixed rank order
+    stats_all[B + j] = (s2 + log2f(L)) * kLn2;
+  } else {
+    stats_all[B + j] = own[B + b + i];
+  }
+}
+
 // ---- loss = mean(row_lse - diag) + mean(col_lse - diag), fixed-order fp64 reduction ---------------
 __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
@@ -224,6 +300,24 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
                                                  scale_cap, diag_cos, fast, pair_fast_s2_limit(), colsum, row_lse, col_lse,
                                                  diag, scale_out);
   VPA_LAUNCH_CHECK("combine_stats_kernel");
+  return 0;
+}
+
+int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
+                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg, cudaStream_t st) {
+  const int64_t n = B > b ? B : b;
+  pack_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
+                                                                  plan.fwd1_chunks, b, B, logit_scale, scale_cap, diag_cos, fast,
+                                                                  pair_fast_s2_limit(), colsum8, msg);
+  VPA_LAUNCH_CHECK("pack_stats_kernel");
+  return 0;
+}
+
+int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
+                       float* stats_all, float* scale_out, cudaStream_t st) {
+  merge_stats_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(msgs, R, b, B, logit_scale, scale_cap, fast,
+                                                                  pair_fast_s2_limit(), stats_all, scale_out);
+  VPA_LAUNCH_CHECK("merge_stats_kernel");
   return 0;
 }
 

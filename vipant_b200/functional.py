@@ -11,7 +11,9 @@ Reference semantics (``/root/reference/cvap/module/decoder/loss_head.py``):
 """
 from __future__ import annotations
 
+import ctypes
 import math
+import os
 from typing import Optional
 
 import torch
@@ -205,6 +207,9 @@ def _sharded_backward(kern, saved, extra, grad_out, normalized, precision, group
 
 
 class _InfoNCEFunction(torch.autograd.Function):
+    """Host-orchestrated step (a dozen C-ABI calls + torch.distributed collectives).  Kept for process groups that are
+    not NCCL and as the reference orchestration the gloo tests exercise; CUDA + NCCL / single GPU use _FusedStep."""
+
     @staticmethod
     def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
         with torch.cuda.device(x1.device):
@@ -222,6 +227,100 @@ class _InfoNCEFunction(torch.autograd.Function):
         with torch.cuda.device(ctx.saved_tensors[0].device):
             dx1, dx2, dls = _sharded_backward(_KERNELS, ctx.saved_tensors, extra, grad_out, normalized, precision, group)
         return dx1, dx2, dls, None, None, None, None
+
+
+# ---------------------------------------------------------------------------- in-library orchestration (2 calls / step)
+_COMMS = {}
+
+
+def _nccl_path():
+    try:
+        import nvidia.nccl as _n
+        for base in list(_n.__path__):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+def _get_comm(group):
+    """NCCL communicator of the library for `group` (created once): rank 0's unique id is broadcast with torch.distributed."""
+    key = id(group)
+    if key in _COMMS:
+        return _COMMS[key]
+    lib = _cabi.lib()
+    path = _nccl_path()
+    _cabi.check(lib.vpa_comm_load(path.encode() if path else None), "vpa_comm_load")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        _cabi.check(lib.vpa_comm_unique_id(buf), "vpa_comm_unique_id")
+        uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    uid = uid.to(dev)
+    dist.broadcast(uid, src=dist.get_global_rank(group, 0) if hasattr(dist, "get_global_rank") else 0, group=group)
+    raw = bytes(uid.cpu().numpy().tobytes())
+    comm = ctypes.c_void_p()
+    _cabi.check(lib.vpa_comm_init(raw, rank, world, ctypes.byref(comm)), "vpa_comm_init")
+    _COMMS[key] = (comm, rank, world)
+    return _COMMS[key]
+
+
+class _FusedStep(torch.autograd.Function):
+    """vpa_infonce_fwd_sharded / vpa_infonce_bwd_sharded: the whole step, collectives included, in two C-ABI calls."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
+        lib = _cabi.lib()
+        comm, rank, world = (None, 0, 1) if group is None else _get_comm(group)
+        b, D = x1.shape
+        dev = x1.device
+        with torch.cuda.device(dev):
+            nbytes = lib.vpa_sharded_state_bytes(b, world, D, precision)
+            state = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            cap = float(scale_max) if scale_max else 0.0
+            _cabi.check(lib.vpa_infonce_fwd_sharded(
+                comm, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0), int(normalized),
+                _ptr(logit_scale), cap, precision, _ptr(state), nbytes, _ptr(loss), _stream()), "vpa_infonce_fwd_sharded")
+        ctx.save_for_backward(x1, x2, state)
+        ctx.cfg = (comm, rank, world, normalized, precision)
+        ctx.set_materialize_grads(False)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if grad_out is None:
+            return None, None, None, None, None, None, None
+        comm, rank, world, normalized, precision = ctx.cfg
+        x1, x2, state = ctx.saved_tensors
+        lib = _cabi.lib()
+        dev = x1.device
+        b, D = x1.shape
+        with torch.cuda.device(dev):
+            g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1)
+            dx1 = torch.empty_like(x1)
+            dx2 = torch.empty_like(x2)
+            dls = torch.empty((), dtype=torch.float32, device=dev)
+            _cabi.check(lib.vpa_infonce_bwd_sharded(
+                comm, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0), int(normalized),
+                precision, _ptr(g), _ptr(state), state.numel(), _ptr(dx1), _ptr(dx2), _ptr(dls), _stream()),
+                "vpa_infonce_bwd_sharded")
+        return dx1, dx2, dls, None, None, None, None
+
+
+def _use_fused(group) -> bool:
+    if os.environ.get("VIPANT_HOST_ORCHESTRATION"):          # A/B knob: the host-orchestrated path
+        return False
+    if group is None:
+        return True
+    try:
+        return dist.get_backend(group) == "nccl"
+    except Exception:
+        return False
 
 
 def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, scale_max=None,
@@ -252,7 +351,8 @@ def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, 
     if ls.device != x1.device or ls.dtype != torch.float32:
         # `scaling=False` heads keep a plain CPU tensor (loss_head.py:252); its value is copied, no grad needed
         ls = ls.to(device=x1.device, dtype=torch.float32)
-    return _InfoNCEFunction.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group)
+    fn = _FusedStep if _use_fused(group) else _InfoNCEFunction
+    return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group)
 
 
 def sim_rank_topk(q: torch.Tensor, k: torch.Tensor, gt: Optional[torch.Tensor] = None, topk: int = 0):

@@ -200,6 +200,36 @@ int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_d
                             float* dlogit_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The same row-sharded step over NVLink PEER MEMORY instead of NCCL: the all-gather of the normalised operands is fused
+ * with the forward sweep (the kernel starts on the local block and consumes the peers' rows, pushed 256-row chunk by
+ * chunk by a side-stream kernel, as their system-scope arrival flags flip), and the statistics / d logit_scale
+ * exchanges are plain stores into the peers' segments published with epoch flags.  No collective library call on the
+ * data path; results are bitwise identical on every rank and to the NCCL transport.
+ *
+ * Setup (once per (rows_local, world, D, precision)): every rank calls vpa_p2p_create -- the library cudaMalloc's its
+ * symmetric segment (gathered operands x 2 steps, messages, flags, workspace) and returns a 64-byte CUDA IPC handle --
+ * the host exchanges the handles (e.g. torch.distributed all_gather, any backend), every rank calls vpa_p2p_connect with
+ * the world x 64 bytes in rank order.  Ranks may share a device (tests) or own one each (peer access is enabled lazily).
+ * world <= 8 (one NVSwitch node).  vpa_p2p_destroy synchronises the device and frees everything.
+ *
+ * vpa_infonce_fwd_p2p returns the step number in *epoch_out; pass it to vpa_infonce_bwd_p2p.  The segment keeps the two
+ * most recent steps: a backward for an older step returns VPA_E_INVALID.  A peer that never arrives trips a device-side
+ * timeout (8 s) and the kernel traps -- an error on the stream, not a hang.
+ * ------------------------------------------------------------------------------------------ */
+int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision, void** p2p_out,
+                   void* ipc_handle_out64);
+int vpa_p2p_connect(void* p2p, const void* all_ipc_handles /* world x 64 bytes, rank order */);
+int vpa_p2p_destroy(void* p2p);
+
+int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype, int64_t rows_local, int world, int rank,
+                        int D, int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale,
+                        float scale_max, int precision, float* loss_out, uint32_t* epoch_out, void* stream);
+
+int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x2, int in_dtype, int64_t rows_local,
+                        int world, int rank, int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
+                        const float* grad_out, void* dx1, void* dx2, float* dlogit_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (the end-to-end call timed as `e2e` in bench.py): pageable or
  * pinned HOST x1/x2 (fp32, contiguous), copies them to the device, runs normalise -> forward ->
  * loss -> backward on `stream`, copies loss / dlogit_scale (and dx1/dx2 when non-NULL) back and

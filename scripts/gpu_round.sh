@@ -9,7 +9,7 @@ cat gpurun_out/bench.json gpurun_out/bench_ref.json
 if [ -n "$NCU" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:"^pair_kernel" -s 6 -c 2 -f -o gpurun_out/prof_pair \
+  ncu --set full --clock-control none --import-source on -k regex:"pair_kernel" -s 9 -c 3 -f -o gpurun_out/prof_pair \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
   ncu --set full --clock-control none -k regex:"normalize_pair_kernel|finalize_bwd_kernel" -s 6 -c 2 -f -o gpurun_out/prof_hbm \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_hbm.log 2>&1

@@ -26,10 +26,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, B, D, precision, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+def _worker(rank, world, port, B, D, precision, transport, shared_device, steps, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VIPANT_TRANSPORT=transport)
+    dev = 0 if shared_device else rank
+    torch.cuda.set_device(dev)
+    if shared_device:      # ranks share GPU 0 (NCCL refuses that): gloo only carries the IPC-handle exchange
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
     try:
         import vipant_b200 as vb
         x1n, x2n = io.make_pair(B, D, 0.3, 21)
@@ -37,22 +41,18 @@ def _worker(rank, world, port, B, D, precision, out):
         x1 = torch.from_numpy(x1n[rank * b:(rank + 1) * b]).cuda().requires_grad_(True)
         x2 = torch.from_numpy(x2n[rank * b:(rank + 1) * b]).cuda().requires_grad_(True)
         ls = torch.tensor(math.log(1 / 0.07), device="cuda", requires_grad=True)
-        loss = vb.infonce_loss(x1, x2, ls, precision=precision, group=dist.group.WORLD)
-        (loss * 3.0).backward()
+        for _ in range(steps):       # several steps: epochs, buffer parity and flag reuse of the peer-memory transport
+            x1.grad = x2.grad = ls.grad = None
+            loss = vb.infonce_loss(x1, x2, ls, precision=precision, group=dist.group.WORLD)
+            (loss * 3.0).backward()
         torch.cuda.synchronize()
         out[rank] = (loss.item(), x1.grad.cpu().numpy(), x2.grad.cpu().numpy(), ls.grad.item())
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision,B,D", [("bf16", 1024, 512), ("bf16", 600, 256), ("fp32", 256, 128)])
-def test_sharded_matches_global_batch(precision, B, D):
-    world = 2
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs 2 GPUs")
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, out), nprocs=world, join=True)
+def _check(out, world, B, D, precision):
     x1n, x2n = io.make_pair(B, D, 0.3, 21)
     ref = io.infonce_closed_form(x1n, x2n, grad_output=3.0)
     tl, tg = (1e-3, 1e-2) if precision == "bf16" else (1e-4, 1e-3)
@@ -65,4 +65,28 @@ def test_sharded_matches_global_batch(precision, B, D):
         assert abs(loss - ref.loss) <= tl * abs(ref.loss)
         assert rel(dx1, ref.dx1[r * b:(r + 1) * b]) <= tg and rel(dx2, ref.dx2[r * b:(r + 1) * b]) <= tg
         assert abs(dls - ref.dlogit_scale) <= tg * abs(ref.dlogit_scale)
-    assert out[0][0] == out[1][0]          # identical global loss on every rank
+    for r in range(1, world):
+        assert out[0][0] == out[r][0] and out[0][3] == out[r][3]      # identical global loss / d logit_scale on every rank
+
+
+@pytest.mark.parametrize("world,precision,B,D", [(2, "bf16", 1024, 512), (2, "bf16", 600, 256), (2, "fp32", 256, 128),
+                                                 (4, "bf16", 2048, 512), (3, "bf16", 1152, 512)])
+def test_p2p_transport_ranks_sharing_one_gpu(world, precision, B, D):
+    """The peer-memory transport (CUDA IPC segments, operand push + arrival flags consumed by the forward sweep, message
+    and d logit_scale exchange by peer stores) between processes that share GPU 0: runs on a single-GPU box."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, "p2p", True, 3, out), nprocs=world, join=True)
+    _check(out, world, B, D, precision)
+
+
+@pytest.mark.parametrize("transport", ["p2p", "nccl", "host"])
+@pytest.mark.parametrize("precision,B,D", [("bf16", 1024, 512), ("bf16", 600, 256), ("fp32", 256, 128)])
+def test_sharded_matches_global_batch(precision, B, D, transport):
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, transport, False, 2, out), nprocs=world, join=True)
+    _check(out, world, B, D, precision)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 
 from . import build as _build
 
@@ -45,6 +45,13 @@ _SIGNATURES = {
                                         c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vpa_infonce_bwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
                                         c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpa_p2p_create": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p]),
+    "vpa_p2p_connect": (c_int, [c_void_p, c_void_p]),
+    "vpa_p2p_destroy": (c_int, [c_void_p]),
+    "vpa_infonce_fwd_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
+                                    c_void_p, c_float, c_int, c_void_p, POINTER(c_uint32), c_void_p]),
+    "vpa_infonce_bwd_p2p": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64,
+                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_sim_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vpa_sim_rank_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

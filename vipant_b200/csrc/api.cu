@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace vpa {
 
@@ -58,15 +59,16 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
                          int fast, const float* colsum, float* row_lse, float* col_lse, float* diag, float* scale_out,
                          cudaStream_t st);
 int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
-                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg, cudaStream_t st);
+                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg,
+                      const P2PStep* p2p, cudaStream_t st);
 int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
-                       float* stats_all, float* scale_out, cudaStream_t st);
+                       float* stats_all, float* scale_out, const P2PStep* p2p, cudaStream_t st);
 int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
                 cudaStream_t st);
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
                         const float* scale, const float* grad_out, const void* x1, const void* x2,
                         int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
-                        int already, void* dx1, void* dx2, float* dlogit_scale, cudaStream_t st);
+                        int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, cudaStream_t st);
 int sim_rank_topk_launch(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
                          const int32_t* gt_idx, int g, int k, int64_t* topk_idx, float* topk_val,
                          int32_t* ranks, float* S, cudaStream_t st);
@@ -248,7 +250,7 @@ size_t vpa_infonce_colsum_floats(int64_t rows_global) { return rows_global > 0 ?
 static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
                           int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
                           float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, bool allow_fast,
-                          int parts, cudaStream_t st) {
+                          int parts, cudaStream_t st, const P2PRowFlags* yflags = nullptr) {
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && workspace, "infonce_fwd_sweep: null pointer");
   const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
@@ -259,6 +261,7 @@ static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_al
   a.rows_local = rows_local; a.rows_global = rows_global; a.row_offset = row_offset; a.D = D;
   a.logit_scale = logit_scale;
   a.scale_cap = (scale_max > 0.f) ? scale_max : INFINITY;     // `cfg.scale_max or float("inf")`
+  if (yflags) a.yflags = *yflags;
   float* cs = col_sum ? col_sum : ws.colsum;
   const bool fast = precision == VPA_PREC_BF16_TC && plan.impl == 1 && plan.fast_fwd && allow_fast;
   if (parts & 1) {
@@ -328,12 +331,12 @@ int vpa_infonce_loss(const float* row_lse, const float* col_lse, const float* di
   return loss_launch(row_lse, col_lse, diag, rows_global, loss_out, static_cast<cudaStream_t>(stream));
 }
 
-int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+static int bwd_impl(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
                     int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* scale,
                     const float* row_lse_all, const float* col_lse_all, const float* grad_out, const void* x1,
                     const void* x2, int in_dtype, int64_t ld1, int64_t ld2, const float* inv_norm1,
                     const float* inv_norm2, int already_normalized, void* workspace, size_t workspace_bytes,
-                    void* dx1, void* dx2, float* dlogit_scale, void* stream) {
+                    void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, void* stream) {
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && scale && row_lse_all && col_lse_all && grad_out && dx1 && dx2 && workspace,
                 "infonce_bwd: null pointer");
@@ -353,7 +356,18 @@ int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, con
   if (int e = (precision == VPA_PREC_BF16_TC) ? (plan.impl == 1 ? pair_infonce_bwd(a, ws, plan, st) : tc_infonce_bwd(a, ws, plan, st))
                                               : simt_infonce_bwd(a, ws, plan, st)) return e;
   return finalize_bwd_launch(ws, plan, rows_local, D, scale, grad_out, x1, x2, in_dtype, ld1, ld2, inv_norm1, inv_norm2,
-                             already_normalized, dx1, dx2, dlogit_scale, st);
+                             already_normalized, dx1, dx2, dlogit_scale, p2p, st);
+}
+
+int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
+                    int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* scale,
+                    const float* row_lse_all, const float* col_lse_all, const float* grad_out, const void* x1,
+                    const void* x2, int in_dtype, int64_t ld1, int64_t ld2, const float* inv_norm1,
+                    const float* inv_norm2, int already_normalized, void* workspace, size_t workspace_bytes,
+                    void* dx1, void* dx2, float* dlogit_scale, void* stream) {
+  return bwd_impl(a_loc, t_loc, a_all, t_all, precision, rows_local, rows_global, D, row_offset, scale, row_lse_all,
+                  col_lse_all, grad_out, x1, x2, in_dtype, ld1, ld2, inv_norm1, inv_norm2, already_normalized, workspace,
+                  workspace_bytes, dx1, dx2, dlogit_scale, nullptr, stream);
 }
 
 size_t vpa_sim_workspace_bytes(int64_t N, int64_t M) {
@@ -479,11 +493,11 @@ int vpa_infonce_fwd_sharded(void* comm, const void* x1, const void* x2, int in_d
   const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
   const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
   const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
-  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, h.msg, st)) return e;
+  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, h.msg, nullptr, st)) return e;
   if (world > 1) {
     if (int e = comm_all_gather(comm, h.msg, h.msgs, (size_t)(B + 3 * b), 7, st)) return e;
   }
-  if (int e = merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, st)) return e;
+  if (int e = merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, nullptr, st)) return e;
   return loss_launch(h.stats_all, h.stats_all + B, h.stats_all + 2 * B, B, loss_out, st);
 }
 
@@ -505,6 +519,69 @@ int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_d
                               dx1, dx2, dlogit_scale, st)) return e;
   if (world > 1) return comm_all_reduce_sum_f32(comm, dlogit_scale, dlogit_scale, 1, st);
   return 0;
+}
+
+// ---- the same step over peer memory (p2p.cu): no NCCL call on the data path -----------------------------------------
+int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision, void** p2p_out, void* ipc_handle_out64) {
+  if (int e = check_infonce_shape(rows_local, rows_local * world, D, (int64_t)rank * rows_local, precision)) return e;
+  return p2p_create(rows_local, world, rank, D, precision, p2p_out, ipc_handle_out64);
+}
+int vpa_p2p_connect(void* p2p, const void* all_ipc_handles) { return p2p_connect(p2p, all_ipc_handles); }
+int vpa_p2p_destroy(void* p2p) { return p2p_destroy(p2p); }
+
+int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank, int D,
+                        int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale, float scale_max,
+                        int precision, float* loss_out, uint32_t* epoch_out, void* stream) {
+  const int64_t B = b * world, off = (int64_t)rank * b;
+  if (int e = check_infonce_shape(b, B, D, off, precision)) return e;
+  VPA_CHECK_ARG(x1 && x2 && logit_scale && loss_out && epoch_out, "fwd_p2p: null pointer");
+  if (int e = p2p_check(p2p, b, world, rank, D, precision)) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t epoch = p2p_next_epoch(p2p);
+  *epoch_out = epoch;
+  const P2PStep h = p2p_step(p2p, epoch);
+  const bool tcp = precision == VPA_PREC_BF16_TC;
+  const size_t es = tcp ? 2 : 4;
+  char* a_loc = static_cast<char*>(h.a_all) + (size_t)off * D * es;
+  char* t_loc = static_cast<char*>(h.t_all) + (size_t)off * D * es;
+  if (int e = p2p_join_push(p2p, st)) return e;          // an earlier push still reading this rank's block
+  if (int e = normalize_pair_launch(x1, x2, in_dtype, b, D, ld1, ld2, already_normalized, tcp ? a_loc : nullptr,
+                                    tcp ? t_loc : nullptr, tcp ? nullptr : (float*)a_loc, tcp ? nullptr : (float*)t_loc,
+                                    h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
+  if (int e = p2p_push_operands(p2p, epoch, st)) return e;      // side stream: x2 operand chunks first, then x1
+  // single-pass kernel: starts on the local block, consumes the peers' x2 rows chunk by chunk as their flags flip
+  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                             h.colsum8, true, 1, st, &h.yflags)) return e;
+  if (int e = p2p_wait_operands(p2p, epoch, st)) return e;      // everything after this may read all of a_all / t_all
+  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                             h.colsum8, true, 2, st)) return e;
+  const SweepPlan plan = plan_sweep(b, B, D, precision);
+  const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
+  const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
+  const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
+  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, nullptr, &h, st)) return e;
+  if (int e = merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, &h, st)) return e;
+  return loss_launch(h.stats_all, h.stats_all + B, h.stats_all + 2 * B, B, loss_out, st);
+}
+
+int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x2, int in_dtype, int64_t b, int world,
+                        int rank, int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
+                        const float* grad_out, void* dx1, void* dx2, float* dlogit_scale, void* stream) {
+  const int64_t B = b * world, off = (int64_t)rank * b;
+  VPA_CHECK_ARG(grad_out && dx1 && dx2 && dlogit_scale, "bwd_p2p: null pointer");
+  if (int e = p2p_check(p2p, b, world, rank, D, precision)) return e;
+  const uint32_t cur = p2p_current_epoch(p2p);
+  VPA_CHECK_ARG(epoch != 0 && cur - epoch <= 1u,
+                "bwd_p2p: the forward of step %u is no longer resident (current step %u; the segment keeps two steps)", epoch, cur);
+  const P2PStep h = p2p_step(p2p, epoch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
+  const char* a_loc = static_cast<const char*>(h.a_all) + (size_t)off * D * es;
+  const char* t_loc = static_cast<const char*>(h.t_all) + (size_t)off * D * es;
+  if (int e = bwd_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B,
+                       grad_out, x1, x2, in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes, dx1, dx2,
+                       dlogit_scale, &h, st)) return e;
+  return p2p_dls_sum(h, dlogit_scale, st);
 }
 
 // ---- host-buffer end-to-end step ---------------------------------------------------------------------

@@ -148,6 +148,13 @@ struct Workspace {
 };
 Workspace carve_workspace(void* base, int64_t rows_local, int64_t rows_global, int D, const SweepPlan& plan);
 
+// Arrival flags of gathered operand rows that are pushed by peer GPUs while the forward already runs (p2p.cuh).
+struct P2PRowFlags {
+  const uint32_t* flags;      // nullptr: no waiting (single GPU / NCCL transport)
+  int rows_per_rank, chunks_per_rank, me;
+  uint32_t epoch;
+};
+
 // Everything a sweep launch needs besides the plan.  Problem 0: X = A_loc, Y = T_all (rows of S);
 // problem 1: X = T_loc, Y = A_all (columns of S, transposed).  Both run in ONE launch.
 struct SweepArgs {
@@ -160,6 +167,7 @@ struct SweepArgs {
   const float* scale;          // backward: s as written by the forward
   const float* lse_x[2];       // backward: lse of the X rows' direction, GLOBAL vector (rows_global)
   const float* lse_y[2];       // backward: lse of the other direction, GLOBAL vector
+  P2PRowFlags yflags;          // single-pass forward over peer memory: arrival flags of y[0]'s rows (zero: none)
 };
 
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);

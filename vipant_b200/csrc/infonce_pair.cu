@@ -22,6 +22,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace vpa {
 namespace pr {
@@ -58,6 +59,7 @@ struct Params {
   float inv_B, ln_B;
   int gate;                 // 0: always run; 1: run only if s*log2e <= kFastS2Limit; 2: run only if it is larger
   float* colpart;           // FWD1: float[n_iblk*8][n_y] column sums of exp2(S*s2 - s2) per 32-row group
+  P2PRowFlags yflags;       // FWD1 over peer memory: arrival flags of the Y rows (nullptr: everything is already there)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -205,7 +207,7 @@ __host__ __device__ inline SmemLayout smem_layout(int kboxes) {
   L.x = o; o += kboxes * Cfg<MODE>::XBox;
   L.g = o; o += (MODE == MODE_BWD) ? 2 * 32768 : 0;            // two G buffers: [64 rows][256 j] bf16 each
   L.ring = o; o += kStages * kStage;
-  L.cl = o; o += 2 * 256 * 4;                                  // column lse of the current / next tile
+  L.cl = o; o += (MODE == MODE_BWD) ? 2 * 256 * 4 : 0;         // column lse of the current / next tile
   L.red = o; o += 64;
   L.bars = o; o += 32 * 8;
   L.tmem_slot = o; o += 16;
@@ -225,7 +227,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
-  if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
+  if (sbase - smem_u32(smem_raw) + L.total > (MODE == MODE_FWD1 ? L.total + 1024 : kSmemLimit)) asm volatile("trap;");     // alignment pad does not fit
   if (P.gate != 0) {       // regime gate on the DEVICE value of the temperature (no host sync): uniform over the grid
     const float gs2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
     if ((P.gate == 1) != (gs2 <= kFastS2Limit)) return;
@@ -306,6 +308,15 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     };
     for (int j = 0; j < nt; ++j) {
       const int r = (tile0 + j) * kBN + (int)crank * 128;      // this CTA's half of the tile's Y rows
+      if (MODE == MODE_FWD1 && P.yflags.flags != nullptr) {
+        // peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cu).  Poll the
+        // chunk flags (system-scope acquire), then order the TMA (async proxy) reads after the observation.
+        if (elected) {
+          p2p_wait_rows(P.yflags, r, min(r + 128, pb.n_y));
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        __syncwarp();
+      }
       for (int kb = 0; kb < P.kboxes; kb += 2) push(kb * kBoxK, (kb + 1) * kBoxK, r);
       if (MODE == MODE_BWD && j >= 1) push_dx(j - 1);
     }
@@ -680,6 +691,7 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.ln_B = logf((float)a.rows_global);
   P.gate = gate;
   P.colpart = ws.colpart;
+  if (fwd1) P.yflags = a.yflags;
   for (int p = 0; p < 2; ++p) {
     P.p[p].n_x = (int)a.rows_local;
     P.p[p].n_y = (int)a.rows_global;
@@ -696,7 +708,11 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   }
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (L.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", L.total);
-  const uint32_t dyn_smem = kSmemLimit;     // the layout plus whatever pad aligns the dynamic base to 1024 B
+  // the layout plus whatever pad aligns the dynamic base to 1024 B.  The single-pass forward asks for 2 KB less than the
+  // SM has: a CTA of the operand push kernel (p2p.cu, no shared memory of its own, 1 KB system reservation) must be able
+  // to become resident beside it, or ranks waiting for each other's rows could starve the kernels that deliver them.
+  const uint32_t dyn_smem = fwd1 ? L.total + 1024 : kSmemLimit;
+  if (fwd1 && dyn_smem > kSmemLimit - 1024) return set_error(VPA_E_UNSUPPORTED, "single-pass forward: %u bytes of shared memory leave no room for the push kernel", dyn_smem);
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[MODE]) {
     VPA_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));

@@ -1,6 +1,7 @@
 // Small memory-bound kernels around the two sweeps: merge of per-chunk (max, sum) statistics,
 // the scalar loss, and the backward finalisation (chunk sum, scale, normalisation Jacobian, cast).
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace vpa {
 
@@ -79,16 +80,23 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
 __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks, int n_chunks_fast, int64_t b, int64_t B,
                                   const float* __restrict__ logit_scale, float scale_cap,
                                   const float* __restrict__ diag_cos, int fast, float s2_limit,
-                                  const float* __restrict__ colsum8, float* __restrict__ msg) {
+                                  const float* __restrict__ colsum8, float* __restrict__ msg, const P2PView pv,
+                                  size_t off_msgs, size_t off_msg_flags, uint32_t* __restrict__ pack_counter) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float s = fminf(expf(*logit_scale), scale_cap);
   const float s2 = s * kLog2e;
   const bool fastr = fast && s2 <= s2_limit;
+  const bool p2p = pv.world > 1;          // peer-memory transport: the message goes straight into every rank's msgs[rank]
+  const int64_t slot = (int64_t)pv.rank * (B + 3 * b);
+  auto put = [&](int64_t pos, float v) {
+    if (!p2p) { msg[pos] = v; return; }
+    for (int q = 0; q < pv.world; ++q) reinterpret_cast<float*>(pv.base[q] + off_msgs)[slot + pos] = v;
+  };
   if (idx < B) {
     float L = 0.f;
     if (fastr)
       for (int g = 0; g < kColSumSplit; ++g) L += colsum8[(int64_t)g * B + idx];
-    msg[idx] = L;
+    put(idx, L);
   }
   if (idx < b) {
     float rl, cl = 0.f;
@@ -115,16 +123,38 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
       rl = lse[0];
       cl = lse[1];
     }
-    msg[B + idx] = rl;
-    msg[B + b + idx] = cl;
-    msg[B + 2 * b + idx] = s * diag_cos[idx];
+    put(B + idx, rl);
+    put(B + b + idx, cl);
+    put(B + 2 * b + idx, s * diag_cos[idx]);
+  }
+  if (p2p) {                                // last block done -> publish the message to every rank (system-scope epoch flag)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(pack_counter, 1u);
+      if ((old + 1) % gridDim.x == 0) {
+        __threadfence();
+        for (int q = 0; q < pv.world; ++q)
+          st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.base[q] + off_msg_flags) + pv.rank, pv.epoch);
+      }
+    }
   }
 }
 
 // msgs[R][B + 3b] (all-gathered) -> stats_all = [row_lse (B) | col_lse (B) | diag (B)], scale_out
-__global__ void merge_stats_kernel(const float* __restrict__ msgs, int R, int64_t b, int64_t B,
+__device__ __forceinline__ float ld_cg(const float* p) {      // L2 only: the messages may have been written by a peer GPU
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__global__ void merge_stats_kernel(const float* msgs, int R, int64_t b, int64_t B,
                                    const float* __restrict__ logit_scale, float scale_cap, int fast, float s2_limit,
-                                   float* __restrict__ stats_all, float* __restrict__ scale_out) {
+                                   float* __restrict__ stats_all, float* __restrict__ scale_out,
+                                   const uint32_t* msg_flags, uint32_t epoch) {
+  if (msg_flags) {                          // peer-memory transport: every rank's message for this step has landed
+    if ((int)threadIdx.x < R) p2p_wait_ge(msg_flags + threadIdx.x, epoch);
+    __syncthreads();
+  }
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float e = expf(*logit_scale);
   const float s = fminf(e, scale_cap);
@@ -137,15 +167,15 @@ __global__ void merge_stats_kernel(const float* __restrict__ msgs, int R, int64_
   const int r = (int)(j / b);
   const int64_t i = j - (int64_t)r * b;
   const float* own = msgs + (int64_t)r * stride;
-  stats_all[j] = own[B + i];
-  stats_all[2 * B + j] = own[B + 2 * b + i];
+  stats_all[j] = ld_cg(own + B + i);
+  stats_all[2 * B + j] = ld_cg(own + B + 2 * b + i);
   const float s2 = s * kLog2e;
   if (fast && s2 <= s2_limit) {
     float L = 0.f;
-    for (int q = 0; q < R; ++q) L += msgs[(int64_t)q * stride + j];      // fixed rank order
+    for (int q = 0; q < R; ++q) L += ld_cg(msgs + (int64_t)q * stride + j);      // fixed rank order
     stats_all[B + j] = (s2 + log2f(L)) * kLn2;
   } else {
-    stats_all[B + j] = own[B + b + i];
+    stats_all[B + j] = ld_cg(own + B + b + i);
   }
 }
 
@@ -206,7 +236,8 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
                     const void* __restrict__ x1, const void* __restrict__ x2, int64_t ld1, int64_t ld2,
                     const float* __restrict__ inv1, const float* __restrict__ inv2, int already,
                     void* __restrict__ dx1, void* __restrict__ dx2,
-                    const float* __restrict__ dscale_part, int n_dscale, float* __restrict__ dlogit_scale) {
+                    const float* __restrict__ dscale_part, int n_dscale, float* __restrict__ dlogit_scale,
+                    const P2PView pv, size_t off_dls) {
   const float s = scale[0], g = grad_out[0];
   const int lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * kFinWarps + (threadIdx.x >> 5);   // (problem, row)
@@ -275,7 +306,16 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
       if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) *dlogit_scale = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
+    if (threadIdx.x == 0) {
+      const float part_dls = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
+      if (pv.world > 1) {                   // peer-memory transport: {epoch, partial} into every rank's slot of this rank
+        const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
+        for (int q = 0; q < pv.world; ++q)
+          st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[q] + off_dls) + pv.rank, w);
+      } else {
+        *dlogit_scale = part_dls;
+      }
+    }
   }
 }
 
@@ -304,19 +344,25 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
 }
 
 int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
-                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg, cudaStream_t st) {
+                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg,
+                      const P2PStep* p2p, cudaStream_t st) {
   const int64_t n = B > b ? B : b;
+  P2PView pv{};
+  if (p2p) pv = p2p->view;
   pack_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
                                                                   plan.fwd1_chunks, b, B, logit_scale, scale_cap, diag_cos, fast,
-                                                                  pair_fast_s2_limit(), colsum8, msg);
+                                                                  pair_fast_s2_limit(), colsum8, msg, pv,
+                                                                  p2p ? p2p->off_msgs : 0, p2p ? p2p->off_msg_flags : 0,
+                                                                  p2p ? p2p->pack_counter : nullptr);
   VPA_LAUNCH_CHECK("pack_stats_kernel");
   return 0;
 }
 
 int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
-                       float* stats_all, float* scale_out, cudaStream_t st) {
+                       float* stats_all, float* scale_out, const P2PStep* p2p, cudaStream_t st) {
   merge_stats_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(msgs, R, b, B, logit_scale, scale_cap, fast,
-                                                                  pair_fast_s2_limit(), stats_all, scale_out);
+                                                                  pair_fast_s2_limit(), stats_all, scale_out,
+                                                                  p2p ? p2p->msg_flags : nullptr, p2p ? p2p->view.epoch : 0u);
   VPA_LAUNCH_CHECK("merge_stats_kernel");
   return 0;
 }
@@ -331,7 +377,10 @@ int loss_launch(const float* row_lse, const float* col_lse, const float* diag, i
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
                         const float* scale, const float* grad_out, const void* x1, const void* x2,
                         int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
-                        int already, void* dx1, void* dx2, float* dlogit_scale, cudaStream_t st) {
+                        int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, cudaStream_t st) {
+  P2PView pv{};
+  if (p2p) pv = p2p->view;
+  const size_t off_dls = p2p ? p2p->off_dls : 0;
   VPA_CHECK_ARG(D <= 128 * kFinMaxVec, "finalize: D=%d > %d unsupported", D, 128 * kFinMaxVec);
   const int64_t n = 2 * rows_local;
   dim3 grid((unsigned)((n + kFinWarps - 1) / kFinWarps)), block(kFinWarps * 32);
@@ -339,7 +388,7 @@ int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows
 #define VPA_FIN(DT, NV)                                                                                            \
   finalize_bwd_kernel<DT, NV><<<grid, block, 0, st>>>(ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, grad_out, \
                                                       x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2,             \
-                                                      ws.dscale_part, plan.n_dscale, dlogit_scale)
+                                                      ws.dscale_part, plan.n_dscale, dlogit_scale, pv, off_dls)
 #define VPA_FIN_NV(DT)                 \
   switch (nv) {                        \
     case 1: VPA_FIN(DT, 1); break;     \

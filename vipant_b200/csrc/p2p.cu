@@ -1,0 +1,327 @@
+// Peer-memory transport of the row-sharded step: the gathered operand matrices, the per-rank statistics messages and the
+// d logit_scale partials live in a SYMMETRIC segment (same layout on every rank, cudaMalloc + CUDA IPC), and every
+// exchange is a kernel storing straight into the peers' segments over NVLink, published with system-scope epoch flags:
+//   * operands: a push kernel on a side stream copies this rank's normalised rows, 256-row chunk by chunk (x2 operands
+//     first), into all peers; the single-pass forward's TMA producer polls the chunk flags, so the sweep starts on the
+//     local block and consumes remote rows as they land -- the all-gather overlaps the contraction tile by tile;
+//   * statistics: pack_stats writes its message into every peer, merge_stats waits for the R flags;
+//   * d logit_scale: finalize_bwd stores {epoch, partial} into every peer's slot, a one-warp kernel sums them in rank order
+//     (bitwise identical on every rank).
+// No NCCL call on the data path.  Buffers are double-buffered by step parity: a rank can run at most one step ahead of a
+// peer (its step k+1 push needs the peer's step k message, which the peer sends after reading step k's operands), so
+// parity k&1 is never overwritten while a peer's backward of step k-... see DESIGN.md section 4.
+#include "p2p.cuh"
+
+#include <cstring>
+#include <new>
+
+namespace vpa {
+
+struct SegLayout {
+  size_t flags[2];          // [m][world][cpr] uint32: m = 0 x2 operands (t_all), 1 x1 operands (a_all)
+  size_t msg_flags;         // [world] uint32
+  size_t dls_slots;         // [2][world] uint64 {epoch << 32 | float bits}
+  size_t counters;          // local only: [2][cpr] push arrivals, [1] pack arrivals
+  size_t mat[2][2];         // [parity][m]: (B, D) operands
+  size_t msgs[2];           // [parity]: (world, B + 3b) floats
+  size_t stats_all[2], scale[2], inv1[2], inv2[2], dcos[2];
+  size_t colsum8, ws;
+  size_t ws_bytes, total;
+  int cpr;
+};
+
+static SegLayout seg_layout(int64_t b, int world, int D, int precision) {
+  SegLayout L{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o += align_up(bytes, 256);
+    return at;
+  };
+  const int64_t B = b * world;
+  const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
+  L.cpr = (int)((b + kPushRows - 1) / kPushRows);
+  for (int m = 0; m < 2; ++m) L.flags[m] = take((size_t)world * L.cpr * 4);
+  L.msg_flags = take((size_t)world * 4);
+  L.dls_slots = take((size_t)2 * world * 8);
+  L.counters = take((size_t)(2 * L.cpr + 1) * 4);
+  for (int p = 0; p < 2; ++p) {
+    for (int m = 0; m < 2; ++m) L.mat[p][m] = take((size_t)B * D * es);
+    L.msgs[p] = take((size_t)world * (B + 3 * b) * 4);
+    L.stats_all[p] = take((size_t)3 * B * 4);
+    L.scale[p] = take(16);
+    L.inv1[p] = take(b * 4);
+    L.inv2[p] = take(b * 4);
+    L.dcos[p] = take(b * 4);
+  }
+  L.colsum8 = take((size_t)kColSumSplit * B * 4);
+  L.ws_bytes = vpa_infonce_workspace_bytes(b, B, D, precision);
+  L.ws = take(L.ws_bytes);
+  L.total = o;
+  return L;
+}
+
+struct P2PHandle {
+  int rank = 0, world = 1, D = 0, precision = 0, dev = 0;
+  int64_t b = 0;
+  char* base[kMaxPeers] = {};
+  bool opened[kMaxPeers] = {};
+  bool connected = false;
+  SegLayout L{};
+  uint32_t epoch = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool join_pending = false;
+  int push_groups = 4, push_ctas = 8;
+};
+
+// ---------------------------------------------------------------- kernels
+struct PushArgs {
+  P2PView v;
+  size_t off_mat[2];        // m = 0: t_all, 1: a_all (this step's parity)
+  size_t off_flags[2];
+  size_t off_counters;
+  int64_t b;
+  int row_bytes, cpr, groups, ctas_per_group;
+};
+
+__global__ void __launch_bounds__(256) p2p_push_kernel(const PushArgs A) {
+  const int g = blockIdx.x / A.ctas_per_group, cg = blockIdx.x - g * A.ctas_per_group;
+  const int nthreads = A.ctas_per_group * blockDim.x;
+  const int tid = cg * blockDim.x + threadIdx.x;
+  char* mine = A.v.base[A.v.rank];
+  uint32_t* counters = reinterpret_cast<uint32_t*>(mine + A.off_counters);
+  for (int item = g; item < 2 * A.cpr; item += A.groups) {
+    const int m = item / A.cpr, c = item - m * A.cpr;          // all x2-operand chunks first: the forward needs them first
+    const int64_t row0 = (int64_t)c * kPushRows;
+    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
+    const int n16 = rows * A.row_bytes / 16;
+    const size_t off = A.off_mat[m] + ((size_t)A.v.rank * A.b + row0) * A.row_bytes;
+    const uint4* src = reinterpret_cast<const uint4*>(mine + off);
+    for (int i = tid; i < n16; i += nthreads) {
+      const uint4 val = src[i];
+      for (int q = 1; q < A.v.world; ++q) {
+        const int peer = (A.v.rank + q) % A.v.world;           // rotate so that the ranks do not all hit the same target
+        reinterpret_cast<uint4*>(A.v.base[peer] + off)[i] = val;
+      }
+    }
+    __threadfence_system();                                     // this thread's peer stores are performed
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(&counters[m * A.cpr + c], 1u);
+      if ((old + 1) % (uint32_t)A.ctas_per_group == 0) {        // last CTA of the group for this chunk: publish it
+        __threadfence();
+        for (int q = 1; q < A.v.world; ++q) {
+          const int peer = (A.v.rank + q) % A.v.world;
+          uint32_t* fl = reinterpret_cast<uint32_t*>(A.v.base[peer] + A.off_flags[m]) + A.v.rank * A.cpr + c;
+          st_release_sys_u32(fl, A.v.epoch);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// every operand chunk of every peer has landed (both matrices): what all later kernels of the step rely on
+__global__ void p2p_wait_all_kernel(const uint32_t* __restrict__ flags_t, const uint32_t* __restrict__ flags_a, int world,
+                                    int cpr, int me, uint32_t epoch) {
+  const int n = world * cpr;
+  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+    const int m = i >= n, k = i - m * n;
+    if (k / cpr == me) continue;
+    p2p_wait_ge((m ? flags_a : flags_t) + k, epoch);
+  }
+}
+
+// d logit_scale = sum over ranks (rank order) of the partials the finalize kernels stored into this rank's slots
+__global__ void p2p_dls_sum_kernel(const unsigned long long* __restrict__ slots, int world, uint32_t epoch,
+                                   float* __restrict__ out) {
+  const int lane = threadIdx.x;
+  float v = 0.f;
+  if (lane < world) {
+    const unsigned long long t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (true) {
+      const unsigned long long w = ld_acquire_sys_u64(slots + lane);
+      if ((uint32_t)(w >> 32) == epoch) { v = __uint_as_float((uint32_t)w); break; }
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > kP2PTimeoutNs) p2p_timeout(slots + lane, epoch, (uint32_t)(w >> 32));
+    }
+  }
+  double acc = 0.0;
+  for (int q = 0; q < world; ++q) acc += (double)__shfl_sync(0xffffffffu, v, q);
+  if (lane == 0) *out = (float)acc;
+}
+
+// ---------------------------------------------------------------- host side
+static P2PView make_view(const P2PHandle* h, uint32_t epoch) {
+  P2PView v{};
+  for (int q = 0; q < kMaxPeers; ++q) v.base[q] = h->base[q];
+  v.rank = h->rank;
+  v.world = h->world;
+  v.epoch = epoch;
+  return v;
+}
+
+int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out, void* ipc_handle64) {
+  VPA_CHECK_ARG(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "p2p: world must be 2..%d", kMaxPeers);
+  VPA_CHECK_ARG(b > 0 && D > 0 && out && ipc_handle64, "p2p_create: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  P2PHandle* h = new (std::nothrow) P2PHandle();
+  if (!h) return set_error(VPA_E_INVALID, "p2p_create: out of host memory");
+  h->rank = rank; h->world = world; h->D = D; h->precision = precision; h->b = b;
+  h->L = seg_layout(b, world, D, precision);
+  auto fail = [&](cudaError_t e, const char* what) {
+    const int rc = set_error((int)e, "p2p_create: %s failed: %s", what, cudaGetErrorString(e));
+    if (h->base[rank]) cudaFree(h->base[rank]);
+    delete h;
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = cudaGetDevice(&h->dev)) != cudaSuccess) return fail(e, "cudaGetDevice");
+  void* p = nullptr;
+  if ((e = cudaMalloc(&p, h->L.total)) != cudaSuccess) return fail(e, "cudaMalloc");
+  h->base[rank] = static_cast<char*>(p);
+  if ((e = cudaMemset(p, 0, h->L.mat[0][0])) != cudaSuccess) return fail(e, "cudaMemset");      // flags, slots, counters
+  cudaIpcMemHandle_t ih;
+  if ((e = cudaIpcGetMemHandle(&ih, p)) != cudaSuccess) return fail(e, "cudaIpcGetMemHandle");
+  memcpy(ipc_handle64, &ih, 64);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if ((e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
+  if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
+  *out = h;
+  return 0;
+}
+
+int p2p_connect(void* handle, const void* all_handles) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  VPA_CHECK_ARG(h && all_handles, "p2p_connect: bad argument");
+  if (h->connected) return 0;
+  for (int q = 0; q < h->world; ++q) {
+    if (q == h->rank) continue;
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, static_cast<const char*>(all_handles) + (size_t)q * 64, 64);
+    void* p = nullptr;
+    VPA_CUDA(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->base[q] = static_cast<char*>(p);
+    h->opened[q] = true;
+  }
+  h->connected = true;
+  return 0;
+}
+
+int p2p_destroy(void* handle) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  if (!h) return 0;
+  cudaDeviceSynchronize();
+  for (int q = 0; q < h->world; ++q)
+    if (h->opened[q]) cudaIpcCloseMemHandle(h->base[q]);
+  if (h->base[h->rank]) cudaFree(h->base[h->rank]);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->fork) cudaEventDestroy(h->fork);
+  if (h->join) cudaEventDestroy(h->join);
+  delete h;
+  return 0;
+}
+
+// ---- accessors used by api.cu ------------------------------------------------------------------------------------
+int p2p_check(void* handle, int64_t b, int world, int rank, int D, int precision) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  VPA_CHECK_ARG(h && h->connected, "p2p: handle not connected");
+  VPA_CHECK_ARG(h->b == b && h->world == world && h->rank == rank && h->D == D && h->precision == precision,
+                "p2p: handle was created for another shape (b=%lld world=%d rank=%d D=%d precision=%d)", (long long)h->b,
+                h->world, h->rank, h->D, h->precision);
+  int dev = -1;
+  VPA_CUDA(cudaGetDevice(&dev));
+  VPA_CHECK_ARG(dev == h->dev, "p2p: handle belongs to device %d, current device is %d", h->dev, dev);
+  return 0;
+}
+
+uint32_t p2p_next_epoch(void* handle) { return ++static_cast<P2PHandle*>(handle)->epoch; }
+uint32_t p2p_current_epoch(void* handle) { return static_cast<P2PHandle*>(handle)->epoch; }
+
+P2PStep p2p_step(void* handle, uint32_t epoch) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  const SegLayout& L = h->L;
+  const int p = (int)(epoch & 1u);
+  char* base = h->base[h->rank];
+  P2PStep s{};
+  s.view = make_view(h, epoch);
+  s.t_all = base + L.mat[p][0];
+  s.a_all = base + L.mat[p][1];
+  s.inv1 = reinterpret_cast<float*>(base + L.inv1[p]);
+  s.inv2 = reinterpret_cast<float*>(base + L.inv2[p]);
+  s.dcos = reinterpret_cast<float*>(base + L.dcos[p]);
+  s.colsum8 = reinterpret_cast<float*>(base + L.colsum8);
+  s.msgs = reinterpret_cast<float*>(base + L.msgs[p]);
+  s.off_msgs = L.msgs[p];
+  s.off_msg_flags = L.msg_flags;
+  s.msg_flags = reinterpret_cast<uint32_t*>(base + L.msg_flags);
+  s.pack_counter = reinterpret_cast<uint32_t*>(base + L.counters) + 2 * L.cpr;
+  s.stats_all = reinterpret_cast<float*>(base + L.stats_all[p]);
+  s.scale = reinterpret_cast<float*>(base + L.scale[p]);
+  s.ws = base + L.ws;
+  s.ws_bytes = L.ws_bytes;
+  s.off_dls = L.dls_slots + (size_t)p * h->world * 8;
+  s.dls_slots = reinterpret_cast<unsigned long long*>(base + s.off_dls);
+  s.yflags.flags = reinterpret_cast<const uint32_t*>(base + L.flags[0]);
+  s.yflags.rows_per_rank = (int)h->b;
+  s.yflags.chunks_per_rank = L.cpr;
+  s.yflags.me = h->rank;
+  s.yflags.epoch = epoch;
+  return s;
+}
+
+// operands of this step -> all peers, on the side stream (forked after the normalise kernel on `st`)
+int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  const SegLayout& L = h->L;
+  const int p = (int)(epoch & 1u);
+  PushArgs A{};
+  A.v = make_view(h, epoch);
+  A.off_mat[0] = L.mat[p][0]; A.off_mat[1] = L.mat[p][1];
+  A.off_flags[0] = L.flags[0]; A.off_flags[1] = L.flags[1];
+  A.off_counters = L.counters;
+  A.b = h->b;
+  A.row_bytes = h->D * (h->precision == VPA_PREC_BF16_TC ? 2 : 4);
+  A.cpr = L.cpr;
+  A.groups = h->push_groups < 2 * L.cpr ? h->push_groups : 2 * L.cpr;
+  A.ctas_per_group = h->push_ctas;
+  VPA_CUDA(cudaEventRecord(h->fork, st));
+  VPA_CUDA(cudaStreamWaitEvent(h->side, h->fork, 0));
+  p2p_push_kernel<<<A.groups * A.ctas_per_group, 256, 0, h->side>>>(A);
+  VPA_LAUNCH_CHECK("p2p_push_kernel");
+  VPA_CUDA(cudaEventRecord(h->join, h->side));
+  h->join_pending = true;
+  return 0;
+}
+
+// the main stream must not overwrite this rank's operand block while an earlier push still reads it
+int p2p_join_push(void* handle, cudaStream_t st) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  if (h->join_pending) VPA_CUDA(cudaStreamWaitEvent(st, h->join, 0));
+  h->join_pending = false;
+  return 0;
+}
+
+int p2p_wait_operands(void* handle, uint32_t epoch, cudaStream_t st) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  const SegLayout& L = h->L;
+  char* base = h->base[h->rank];
+  p2p_wait_all_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(base + L.flags[0]),
+                                         reinterpret_cast<const uint32_t*>(base + L.flags[1]), h->world, L.cpr, h->rank, epoch);
+  VPA_LAUNCH_CHECK("p2p_wait_all_kernel");
+  return 0;
+}
+
+int p2p_dls_sum(const P2PStep& s, float* dlogit_scale, cudaStream_t st) {
+  p2p_dls_sum_kernel<<<1, 32, 0, st>>>(s.dls_slots, s.view.world, s.view.epoch, dlogit_scale);
+  VPA_LAUNCH_CHECK("p2p_dls_sum_kernel");
+  return 0;
+}
+
+}  // namespace vpa

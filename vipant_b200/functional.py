@@ -312,15 +312,97 @@ class _FusedStep(torch.autograd.Function):
         return dx1, dx2, dls, None, None, None, None
 
 
-def _use_fused(group) -> bool:
+# ---------------------------------------------------------------------------- peer-memory transport (no NCCL on the data path)
+_P2P = {}
+
+
+def _get_p2p(group, b, D, precision, dev):
+    """Symmetric segment of the library for (group, shape): created once; the 64-byte CUDA IPC handles are exchanged with
+    torch.distributed (any backend: object all-gather), then every rank maps its peers' segments."""
+    key = (id(group), b, D, precision, dev.index)
+    if key in _P2P:
+        return _P2P[key]
+    lib = _cabi.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handle = ctypes.c_void_p()
+    mine = ctypes.create_string_buffer(64)
+    _cabi.check(lib.vpa_p2p_create(b, world, rank, D, precision, ctypes.byref(handle), mine), "vpa_p2p_create")
+    everyone = [None] * world
+    dist.all_gather_object(everyone, bytes(mine.raw), group=group)
+    _cabi.check(lib.vpa_p2p_connect(handle, b"".join(everyone)), "vpa_p2p_connect")
+    dist.barrier(group=group)            # every rank has mapped every segment before anyone stores into a peer
+    _P2P[key] = (handle, rank, world)
+    if len(_P2P) == 1:
+        import atexit
+        atexit.register(_destroy_p2p)
+    return _P2P[key]
+
+
+def _destroy_p2p():
+    lib = _cabi.lib()
+    for handle, _, _ in _P2P.values():
+        lib.vpa_p2p_destroy(handle)
+    _P2P.clear()
+
+
+class _P2PStep(torch.autograd.Function):
+    """vpa_infonce_fwd_p2p / vpa_infonce_bwd_p2p: the row-sharded step with every exchange done by kernels storing into
+    the peers' memory (all-gather fused with the forward sweep); two C-ABI calls per step."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
+        lib = _cabi.lib()
+        b, D = x1.shape
+        dev = x1.device
+        with torch.cuda.device(dev):
+            handle, rank, world = _get_p2p(group, b, D, precision, dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            epoch = ctypes.c_uint32()
+            cap = float(scale_max) if scale_max else 0.0
+            _cabi.check(lib.vpa_infonce_fwd_p2p(
+                handle, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0), int(normalized),
+                _ptr(logit_scale), cap, precision, _ptr(loss), ctypes.byref(epoch), _stream()), "vpa_infonce_fwd_p2p")
+        ctx.save_for_backward(x1, x2)
+        ctx.cfg = (handle, epoch.value, rank, world, normalized, precision)
+        ctx.set_materialize_grads(False)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        if grad_out is None:
+            return None, None, None, None, None, None, None
+        handle, epoch, rank, world, normalized, precision = ctx.cfg
+        x1, x2 = ctx.saved_tensors
+        lib = _cabi.lib()
+        dev = x1.device
+        b, D = x1.shape
+        with torch.cuda.device(dev):
+            g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1)
+            dx1 = torch.empty_like(x1)
+            dx2 = torch.empty_like(x2)
+            dls = torch.empty((), dtype=torch.float32, device=dev)
+            _cabi.check(lib.vpa_infonce_bwd_p2p(
+                handle, epoch, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0),
+                int(normalized), precision, _ptr(g), _ptr(dx1), _ptr(dx2), _ptr(dls), _stream()), "vpa_infonce_bwd_p2p")
+        return dx1, dx2, dls, None, None, None, None
+
+
+def _transport(group) -> str:
+    """"local" (one GPU), "p2p" (peer-memory kernels, default for <= 8 ranks of one node), "nccl" (in-library NCCL
+    orchestration) or "host" (torch.distributed collectives between C-ABI calls).  VIPANT_TRANSPORT overrides."""
     if os.environ.get("VIPANT_HOST_ORCHESTRATION"):          # A/B knob: the host-orchestrated path
-        return False
-    if group is None:
-        return True
+        return "host"
+    if group is None or dist.get_world_size(group) == 1:
+        return "local"
+    forced = os.environ.get("VIPANT_TRANSPORT")
+    if forced in ("p2p", "nccl", "host"):
+        return forced
+    if dist.get_world_size(group) <= 8:
+        return "p2p"
     try:
-        return dist.get_backend(group) == "nccl"
+        return "nccl" if dist.get_backend(group) == "nccl" else "host"
     except Exception:
-        return False
+        return "host"
 
 
 def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, scale_max=None,
@@ -351,7 +433,10 @@ def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, 
     if ls.device != x1.device or ls.dtype != torch.float32:
         # `scaling=False` heads keep a plain CPU tensor (loss_head.py:252); its value is copied, no grad needed
         ls = ls.to(device=x1.device, dtype=torch.float32)
-    fn = _FusedStep if _use_fused(group) else _InfoNCEFunction
+    transport = _transport(group)
+    if transport == "local":
+        group = None
+    fn = {"local": _FusedStep, "nccl": _FusedStep, "p2p": _P2PStep, "host": _InfoNCEFunction}[transport]
     return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group)
 
 

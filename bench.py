@@ -209,6 +209,8 @@ def main():
     from vipant_b200 import _cabi
     lib = _cabi.lib()
 
+    from vipant_b200 import functional as _vf
+    transport = _vf._transport(dist.group.WORLD if world > 1 else None)
     B, D = args.batch, args.dim
     assert B % world == 0, "global batch must divide by the number of ranks"
     b = B // world
@@ -335,7 +337,8 @@ def main():
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": f"InfoNCE fwd+bwd (CELossHead), global batch {B} x {D}, {args.precision} mode, "
                                    f"rows sharded over {world} rank(s)", "global_batch": B, "dim": D, "rows_per_rank": b,
-                       "parallelism": f"row-shard x{world}" + (" + NCCL all-gather" if world > 1 else ""),
+                       "parallelism": f"row-shard x{world}" + (f" + {transport} exchange" if world > 1 else ""),
+                       "transport": transport,
                        "l2": "no explicit flush: inputs + operands + partials per step exceed the 126 MB L2",
                        "seed": SEED, "rho": RHO},
             "loss": loss_val, "host_enqueue_ms_per_step": host_ms,

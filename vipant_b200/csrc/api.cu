@@ -59,10 +59,11 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
                          int fast, const float* colsum, float* row_lse, float* col_lse, float* diag, float* scale_out,
                          cudaStream_t st);
 int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
-                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg,
+                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart, float* msg,
                       const P2PStep* p2p, cudaStream_t st);
 int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
-                       float* stats_all, float* scale_out, const P2PStep* p2p, cudaStream_t st);
+                       float* stats_all, float* scale_out, const P2PStep* p2p, double* loss_part, uint32_t* loss_counter,
+                       float* loss_out, cudaStream_t st);
 int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
                 cudaStream_t st);
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
@@ -250,7 +251,8 @@ size_t vpa_infonce_colsum_floats(int64_t rows_global) { return rows_global > 0 ?
 static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
                           int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
                           float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, bool allow_fast,
-                          int parts, cudaStream_t st, const P2PRowFlags* yflags = nullptr) {
+                          int parts, cudaStream_t st, const P2PRowFlags* yflags = nullptr, bool reduce_cols = true) {
+  // reduce_cols == false: the caller reduces the single-pass column partials itself (pack_stats); col_sum is not touched
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && workspace, "infonce_fwd_sweep: null pointer");
   const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
@@ -265,7 +267,7 @@ static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_al
   float* cs = col_sum ? col_sum : ws.colsum;
   const bool fast = precision == VPA_PREC_BF16_TC && plan.impl == 1 && plan.fast_fwd && allow_fast;
   if (parts & 1) {
-    VPA_CUDA(cudaMemsetAsync(cs, 0, (size_t)kColSumSplit * rows_global * sizeof(float), st));
+    if (reduce_cols) VPA_CUDA(cudaMemsetAsync(cs, 0, (size_t)kColSumSplit * rows_global * sizeof(float), st));
     if (fast) {
       if (int e = pair_infonce_fwd(a, ws, plan, 1, st)) return e;
     }
@@ -274,7 +276,7 @@ static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_al
     if (precision != VPA_PREC_BF16_TC) return simt_infonce_fwd(a, ws, plan, st);
     if (plan.impl != 1) return tc_infonce_fwd(a, ws, plan, st);
     if (int e = pair_infonce_fwd(a, ws, plan, fast ? 2 : 0, st)) return e;
-    if (fast) return colsum_reduce_launch(ws, plan, rows_global, logit_scale, a.scale_cap, cs, st);
+    if (fast && reduce_cols) return colsum_reduce_launch(ws, plan, rows_global, logit_scale, a.scale_cap, cs, st);
   }
   return 0;
 }
@@ -391,9 +393,15 @@ struct ShardState {
   float *inv1, *inv2, *dcos;    // (b,)
   float *colsum8, *msg, *msgs;  // (8, B); (B + 3b); (R, B + 3b)
   float *stats_all, *scale;     // (3, B); (2,)
+  double* loss_part;            // per-block partial sums of the loss (merge_stats)
+  uint32_t* loss_counter;
   void* ws;
   size_t ws_bytes, bytes;
 };
+// the single-pass column partials are few enough for pack_stats to reduce them itself (saves a launch and a pass)
+static bool pack_reduces_columns(const SweepPlan& plan, int precision) {
+  return precision == VPA_PREC_BF16_TC && plan.impl == 1 && plan.fast_fwd && plan.n_rowgroups <= 256;
+}
 static ShardState carve_state(void* base, int64_t b, int world, int D, int precision) {
   ShardState h{};
   size_t o = 0;
@@ -412,6 +420,8 @@ static ShardState carve_state(void* base, int64_t b, int world, int D, int preci
   h.msgs = world > 1 ? (float*)take((size_t)world * (B + 3 * b) * 4) : h.msg;
   h.stats_all = (float*)take((size_t)3 * B * 4);
   h.scale = (float*)take(16);
+  h.loss_part = (double*)take((size_t)((B + 255) / 256) * 8);
+  h.loss_counter = (uint32_t*)take(4);
   h.ws_bytes = vpa_infonce_workspace_bytes(b, B, D, precision);
   h.ws = take(h.ws_bytes);
   h.bytes = o;
@@ -482,23 +492,26 @@ int vpa_infonce_fwd_sharded(void* comm, const void* x1, const void* x2, int in_d
     VPA_CUDA(cudaEventRecord(ss->a_done, ss->s));
     VPA_CUDA(cudaStreamWaitEvent(st, ss->t_done, 0));
   }
+  const SweepPlan plan = plan_sweep(b, B, D, precision);
+  const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
+  const bool from_colpart = pack_reduces_columns(plan, precision);
+  VPA_CUDA(cudaMemsetAsync(h.loss_counter, 0, 4, st));
   // single-pass kernel (reads a_loc and t_all) ...
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, 1, st)) return e;
+                             h.colsum8, true, 1, st, nullptr, !from_colpart)) return e;
   if (world > 1) VPA_CUDA(cudaStreamWaitEvent(st, ss->a_done, 0));
   // ... then everything that also reads a_all
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, 2, st)) return e;
-  const SweepPlan plan = plan_sweep(b, B, D, precision);
-  const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
+                             h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
   const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
   const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
-  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, h.msg, nullptr, st)) return e;
+  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, from_colpart, h.msg, nullptr, st)) return e;
   if (world > 1) {
     if (int e = comm_all_gather(comm, h.msg, h.msgs, (size_t)(B + 3 * b), 7, st)) return e;
   }
-  if (int e = merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, nullptr, st)) return e;
-  return loss_launch(h.stats_all, h.stats_all + B, h.stats_all + 2 * B, B, loss_out, st);
+  // statistics of all rows + the global loss in one kernel
+  return merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, nullptr, h.loss_part,
+                            h.loss_counter, loss_out, st);
 }
 
 int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank,
@@ -550,18 +563,20 @@ int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype,
                                     h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
   if (int e = p2p_push_operands(p2p, epoch, st)) return e;      // side stream: x2 operand chunks first, then x1
   // single-pass kernel: starts on the local block, consumes the peers' x2 rows chunk by chunk as their flags flip
-  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, 1, st, &h.yflags)) return e;
-  if (int e = p2p_wait_operands(p2p, epoch, st)) return e;      // everything after this may read all of a_all / t_all
-  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, 2, st)) return e;
   const SweepPlan plan = plan_sweep(b, B, D, precision);
   const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
+  const bool from_colpart = pack_reduces_columns(plan, precision);
+  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                             h.colsum8, true, 1, st, &h.yflags, !from_colpart)) return e;
+  if (int e = p2p_wait_operands(p2p, epoch, st)) return e;      // everything after this may read all of a_all / t_all
+  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                             h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
   const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
   const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
-  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, nullptr, &h, st)) return e;
-  if (int e = merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, &h, st)) return e;
-  return loss_launch(h.stats_all, h.stats_all + B, h.stats_all + 2 * B, B, loss_out, st);
+  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, from_colpart, nullptr, &h, st)) return e;
+  // waits for every rank's message, then statistics of all rows + the global loss in one kernel
+  return merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, &h, h.loss_part, h.loss_counter,
+                            loss_out, st);
 }
 
 int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x2, int in_dtype, int64_t b, int world,

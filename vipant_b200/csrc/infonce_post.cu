@@ -80,7 +80,8 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
 __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks, int n_chunks_fast, int64_t b, int64_t B,
                                   const float* __restrict__ logit_scale, float scale_cap,
                                   const float* __restrict__ diag_cos, int fast, float s2_limit,
-                                  const float* __restrict__ colsum8, float* __restrict__ msg, const P2PView pv,
+                                  const float* __restrict__ colsum8, const float* __restrict__ colpart, int n_groups,
+                                  float* __restrict__ msg, const P2PView pv,
                                   size_t off_msgs, size_t off_msg_flags, uint32_t* __restrict__ pack_counter) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float s = fminf(expf(*logit_scale), scale_cap);
@@ -94,8 +95,20 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
   };
   if (idx < B) {
     float L = 0.f;
-    if (fastr)
+    if (fastr && colpart) {                 // few row groups (sharded batch): reduce the sweep's partials here, fixed order
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int g = 0;
+      for (; g + 4 <= n_groups; g += 4) {
+        a0 += __ldg(colpart + (int64_t)(g + 0) * B + idx);
+        a1 += __ldg(colpart + (int64_t)(g + 1) * B + idx);
+        a2 += __ldg(colpart + (int64_t)(g + 2) * B + idx);
+        a3 += __ldg(colpart + (int64_t)(g + 3) * B + idx);
+      }
+      for (; g < n_groups; ++g) a0 += __ldg(colpart + (int64_t)g * B + idx);
+      L = (a0 + a1) + (a2 + a3);
+    } else if (fastr) {
       for (int g = 0; g < kColSumSplit; ++g) L += colsum8[(int64_t)g * B + idx];
+    }
     put(idx, L);
   }
   if (idx < b) {
@@ -150,7 +163,8 @@ __device__ __forceinline__ float ld_cg(const float* p) {      // L2 only: the me
 __global__ void merge_stats_kernel(const float* msgs, int R, int64_t b, int64_t B,
                                    const float* __restrict__ logit_scale, float scale_cap, int fast, float s2_limit,
                                    float* __restrict__ stats_all, float* __restrict__ scale_out,
-                                   const uint32_t* msg_flags, uint32_t epoch) {
+                                   const uint32_t* msg_flags, uint32_t epoch, double* __restrict__ loss_part,
+                                   uint32_t* __restrict__ loss_counter, float* __restrict__ loss_out) {
   if (msg_flags) {                          // peer-memory transport: every rank's message for this step has landed
     if ((int)threadIdx.x < R) p2p_wait_ge(msg_flags + threadIdx.x, epoch);
     __syncthreads();
@@ -162,7 +176,8 @@ __global__ void merge_stats_kernel(const float* msgs, int R, int64_t b, int64_t 
     scale_out[0] = s;
     scale_out[1] = (e <= scale_cap) ? 1.0f : 0.0f;
   }
-  if (j >= B) return;
+  double term = 0.0;
+  if (j < B) {
   const int64_t stride = B + 3 * b;
   const int r = (int)(j / b);
   const int64_t i = j - (int64_t)r * b;
@@ -176,6 +191,33 @@ __global__ void merge_stats_kernel(const float* msgs, int R, int64_t b, int64_t 
     stats_all[B + j] = (s2 + log2f(L)) * kLn2;
   } else {
     stats_all[B + j] = ld_cg(own + B + b + i);
+  }
+  term = ((double)stats_all[j] - (double)stats_all[2 * B + j]) + ((double)stats_all[B + j] - (double)stats_all[2 * B + j]);
+  }
+  // loss = mean(row_lse - diag) + mean(col_lse - diag): per-block partials, summed in block order by the last block to
+  // finish (fixed order -> bitwise deterministic and identical on every rank)
+  if (loss_out == nullptr) return;
+  __shared__ double red[8];
+  __shared__ bool last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+    loss_part[blockIdx.x] = v;
+    __threadfence();
+    last = ((atomicAdd(loss_counter, 1u) + 1) % gridDim.x) == 0;
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) v += *reinterpret_cast<volatile double*>(loss_part + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *loss_out = (float)(v / (double)B);
   }
 }
 
@@ -344,14 +386,15 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
 }
 
 int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
-                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, float* msg,
+                      float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart, float* msg,
                       const P2PStep* p2p, cudaStream_t st) {
   const int64_t n = B > b ? B : b;
   P2PView pv{};
   if (p2p) pv = p2p->view;
   pack_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
                                                                   plan.fwd1_chunks, b, B, logit_scale, scale_cap, diag_cos, fast,
-                                                                  pair_fast_s2_limit(), colsum8, msg, pv,
+                                                                  pair_fast_s2_limit(), colsum8,
+                                                                  from_colpart ? ws.colpart : nullptr, plan.n_rowgroups, msg, pv,
                                                                   p2p ? p2p->off_msgs : 0, p2p ? p2p->off_msg_flags : 0,
                                                                   p2p ? p2p->pack_counter : nullptr);
   VPA_LAUNCH_CHECK("pack_stats_kernel");
@@ -359,10 +402,12 @@ int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int
 }
 
 int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
-                       float* stats_all, float* scale_out, const P2PStep* p2p, cudaStream_t st) {
+                       float* stats_all, float* scale_out, const P2PStep* p2p, double* loss_part, uint32_t* loss_counter,
+                       float* loss_out, cudaStream_t st) {
   merge_stats_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(msgs, R, b, B, logit_scale, scale_cap, fast,
                                                                   pair_fast_s2_limit(), stats_all, scale_out,
-                                                                  p2p ? p2p->msg_flags : nullptr, p2p ? p2p->view.epoch : 0u);
+                                                                  p2p ? p2p->msg_flags : nullptr, p2p ? p2p->view.epoch : 0u,
+                                                                  loss_part, loss_counter, loss_out);
   VPA_LAUNCH_CHECK("merge_stats_kernel");
   return 0;
 }

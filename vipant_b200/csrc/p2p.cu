@@ -21,7 +21,8 @@ struct SegLayout {
   size_t flags[2];          // [m][world][cpr] uint32: m = 0 x2 operands (t_all), 1 x1 operands (a_all)
   size_t msg_flags;         // [world] uint32
   size_t dls_slots;         // [2][world] uint64 {epoch << 32 | float bits}
-  size_t counters;          // local only: [2][cpr] push arrivals, [1] pack arrivals
+  size_t counters;          // local only: [2][cpr] push arrivals, [1] pack arrivals, [1] loss arrivals
+  size_t loss_part;         // local only: per-block loss partials (doubles)
   size_t mat[2][2];         // [parity][m]: (B, D) operands
   size_t msgs[2];           // [parity]: (world, B + 3b) floats
   size_t stats_all[2], scale[2], inv1[2], inv2[2], dcos[2];
@@ -44,7 +45,8 @@ static SegLayout seg_layout(int64_t b, int world, int D, int precision) {
   for (int m = 0; m < 2; ++m) L.flags[m] = take((size_t)world * L.cpr * 4);
   L.msg_flags = take((size_t)world * 4);
   L.dls_slots = take((size_t)2 * world * 8);
-  L.counters = take((size_t)(2 * L.cpr + 1) * 4);
+  L.counters = take((size_t)(2 * L.cpr + 2) * 4);
+  L.loss_part = take((size_t)((B + 255) / 256) * 8);
   for (int p = 0; p < 2; ++p) {
     for (int m = 0; m < 2; ++m) L.mat[p][m] = take((size_t)B * D * es);
     L.msgs[p] = take((size_t)world * (B + 3 * b) * 4);
@@ -72,7 +74,7 @@ struct P2PHandle {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   bool join_pending = false;
-  int push_groups = 4, push_ctas = 8;
+  int push_groups = 8, push_ctas = 4, push_rounds = 8;
 };
 
 // ---------------------------------------------------------------- kernels
@@ -82,8 +84,10 @@ struct PushArgs {
   size_t off_flags[2];
   size_t off_counters;
   int64_t b;
-  int row_bytes, cpr, groups, ctas_per_group;
+  int row_bytes, cpr, groups, ctas_per_group, batch;
 };
+
+constexpr int kPushUnroll = 8;      // 16-byte loads in flight per thread: the copy is bound by L2 load latency otherwise
 
 __global__ void __launch_bounds__(256) p2p_push_kernel(const PushArgs A) {
   const int g = blockIdx.x / A.ctas_per_group, cg = blockIdx.x - g * A.ctas_per_group;
@@ -91,30 +95,42 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(const PushArgs A) {
   const int tid = cg * blockDim.x + threadIdx.x;
   char* mine = A.v.base[A.v.rank];
   uint32_t* counters = reinterpret_cast<uint32_t*>(mine + A.off_counters);
-  for (int item = g; item < 2 * A.cpr; item += A.groups) {
-    const int m = item / A.cpr, c = item - m * A.cpr;          // all x2-operand chunks first: the forward needs them first
-    const int64_t row0 = (int64_t)c * kPushRows;
-    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
-    const int n16 = rows * A.row_bytes / 16;
+  const int nbatch = (A.cpr + A.batch - 1) / A.batch;         // batches of `batch` chunks per matrix: one fence each
+  for (int item = g; item < 2 * nbatch; item += A.groups) {
+    const int m = item / nbatch, k = item - m * nbatch;        // all x2-operand batches first: the forward needs them first
+    const int c0 = k * A.batch, c1 = min(A.cpr, c0 + A.batch);
+    const int64_t row0 = (int64_t)c0 * kPushRows;
+    const int rows = (int)min((int64_t)(c1 - c0) * kPushRows, A.b - row0);
+    const int n16 = rows * (A.row_bytes / 16);
     const size_t off = A.off_mat[m] + ((size_t)A.v.rank * A.b + row0) * A.row_bytes;
     const uint4* src = reinterpret_cast<const uint4*>(mine + off);
-    for (int i = tid; i < n16; i += nthreads) {
-      const uint4 val = src[i];
+    for (int i = tid; i < n16; i += nthreads * kPushUnroll) {
+      uint4 val[kPushUnroll];
+#pragma unroll
+      for (int u = 0; u < kPushUnroll; ++u) {
+        const int idx = i + u * nthreads;
+        if (idx < n16) val[u] = __ldg(src + idx);
+      }
       for (int q = 1; q < A.v.world; ++q) {
         const int peer = (A.v.rank + q) % A.v.world;           // rotate so that the ranks do not all hit the same target
-        reinterpret_cast<uint4*>(A.v.base[peer] + off)[i] = val;
+        uint4* dst = reinterpret_cast<uint4*>(A.v.base[peer] + off);
+#pragma unroll
+        for (int u = 0; u < kPushUnroll; ++u) {
+          const int idx = i + u * nthreads;
+          if (idx < n16) dst[idx] = val[u];
+        }
       }
     }
     __threadfence_system();                                     // this thread's peer stores are performed
     __syncthreads();
     if (threadIdx.x == 0) {
-      const uint32_t old = atomicAdd(&counters[m * A.cpr + c], 1u);
-      if ((old + 1) % (uint32_t)A.ctas_per_group == 0) {        // last CTA of the group for this chunk: publish it
+      const uint32_t old = atomicAdd(&counters[m * A.cpr + c0], 1u);
+      if ((old + 1) % (uint32_t)A.ctas_per_group == 0) {        // last CTA of the group for this batch: publish its chunks
         __threadfence();
         for (int q = 1; q < A.v.world; ++q) {
           const int peer = (A.v.rank + q) % A.v.world;
-          uint32_t* fl = reinterpret_cast<uint32_t*>(A.v.base[peer] + A.off_flags[m]) + A.v.rank * A.cpr + c;
-          st_release_sys_u32(fl, A.v.epoch);
+          uint32_t* fl = reinterpret_cast<uint32_t*>(A.v.base[peer] + A.off_flags[m]) + A.v.rank * A.cpr;
+          for (int c = c0; c < c1; ++c) st_release_sys_u32(fl + c, A.v.epoch);
         }
       }
     }
@@ -192,6 +208,7 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
+  if (const char* s = getenv("VPA_P2P_PUSH_ROUNDS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->push_rounds = v; }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
   *out = h;
   return 0;
@@ -262,6 +279,8 @@ P2PStep p2p_step(void* handle, uint32_t epoch) {
   s.off_msg_flags = L.msg_flags;
   s.msg_flags = reinterpret_cast<uint32_t*>(base + L.msg_flags);
   s.pack_counter = reinterpret_cast<uint32_t*>(base + L.counters) + 2 * L.cpr;
+  s.loss_counter = s.pack_counter + 1;
+  s.loss_part = reinterpret_cast<double*>(base + L.loss_part);
   s.stats_all = reinterpret_cast<float*>(base + L.stats_all[p]);
   s.scale = reinterpret_cast<float*>(base + L.scale[p]);
   s.ws = base + L.ws;
@@ -289,8 +308,12 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
   A.b = h->b;
   A.row_bytes = h->D * (h->precision == VPA_PREC_BF16_TC ? 2 : 4);
   A.cpr = L.cpr;
-  A.groups = h->push_groups < 2 * L.cpr ? h->push_groups : 2 * L.cpr;
   A.ctas_per_group = h->push_ctas;
+  // fences (one NVLink round trip each) per group and matrix are bounded by push_rounds: large blocks go in multi-chunk batches
+  A.batch = (L.cpr + h->push_groups * h->push_rounds - 1) / (h->push_groups * h->push_rounds);
+  if (A.batch < 1) A.batch = 1;
+  const int nbatch = (L.cpr + A.batch - 1) / A.batch;
+  A.groups = h->push_groups < 2 * nbatch ? h->push_groups : 2 * nbatch;
   VPA_CUDA(cudaEventRecord(h->fork, st));
   VPA_CUDA(cudaStreamWaitEvent(h->side, h->fork, 0));
   p2p_push_kernel<<<A.groups * A.ctas_per_group, 256, 0, h->side>>>(A);

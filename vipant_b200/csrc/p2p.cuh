@@ -84,6 +84,8 @@ struct P2PStep {
   size_t off_msgs, off_msg_flags, off_dls;
   uint32_t *msg_flags, *pack_counter;
   unsigned long long* dls_slots;
+  double* loss_part;
+  uint32_t* loss_counter;
   void* ws;
   size_t ws_bytes;
   P2PRowFlags yflags;       // chunk flags of the x2 operands (the Y stream of the single-pass forward)

@@ -251,7 +251,7 @@ def main():
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     prof = {}
-    for kind, name in ((0, "normalize"), (1, "fwd_sweep"), (2, "bwd_sweep"), (5, "fwd_general_gated"), (6, "finalize")):
+    for kind, name in ((0, "normalize"), (1, "fwd_sweep"), (2, "bwd_sweep"), (5, "fwd_general_gated"), (6, "finalize"), (7, "push")):
         tot, n = ctypes.c_float(), ctypes.c_int()
         lib.vpa_profile_read(kind, ctypes.byref(tot), ctypes.byref(n))
         prof[name] = (tot.value, n.value)
@@ -347,7 +347,8 @@ def main():
             "kernel_ms": {"normalize_pair": nrm_ms / max(nrm_n, 1), "fwd_sweep": fwd_ms / max(fwd_n, 1),
                           "bwd_sweep": bwd_ms / max(bwd_n, 1),
                           "fwd_general_gated_off": prof["fwd_general_gated"][0] / max(prof["fwd_general_gated"][1], 1),
-                          "finalize_bwd": prof["finalize"][0] / max(prof["finalize"][1], 1)},
+                          "finalize_bwd": prof["finalize"][0] / max(prof["finalize"][1], 1),
+                          "p2p_push_side_stream": prof["push"][0] / max(prof["push"][1], 1)},
             "finalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 4 + 4)) / (prof["finalize"][0] / max(prof["finalize"][1], 1) * 1e-3) / 1e9
                              if prof["finalize"][1] else None, "peak_gbs": pk["hbm"]},
             "normalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 2) + 12 * b) / (nrm_ms / max(nrm_n, 1) * 1e-3) / 1e9 if nrm_n else None,

@@ -58,6 +58,7 @@ const char* vpa_last_error_string(void);
 #define VPA_PROF_RANK 4
 #define VPA_PROF_FWD_GENERAL 5 /* the exact two-sweep forward when the single-pass one is also enqueued */
 #define VPA_PROF_FINALIZE 6
+#define VPA_PROF_PUSH 7 /* peer-memory transport: the operand push kernel (side stream) */
 int vpa_profile_enable(int on);
 int vpa_profile_read(int kind, float* total_ms, int* launches);
 

@@ -26,8 +26,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, B, D, precision, transport, shared_device, steps, out):
+def _worker(rank, world, port, B, D, precision, transport, shared_device, steps, out, env=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VIPANT_TRANSPORT=transport)
+    os.environ.update(env or {})
     dev = 0 if shared_device else rank
     torch.cuda.set_device(dev)
     if shared_device:      # ranks share GPU 0 (NCCL refuses that): gloo only carries the IPC-handle exchange
@@ -69,14 +70,18 @@ def _check(out, world, B, D, precision):
         assert out[0][0] == out[r][0] and out[0][3] == out[r][3]      # identical global loss / d logit_scale on every rank
 
 
-@pytest.mark.parametrize("world,precision,B,D", [(2, "bf16", 1024, 512), (2, "bf16", 600, 256), (2, "fp32", 256, 128),
-                                                 (4, "bf16", 2048, 512), (3, "bf16", 1152, 512)])
-def test_p2p_transport_ranks_sharing_one_gpu(world, precision, B, D):
-    """The peer-memory transport (CUDA IPC segments, operand push + arrival flags consumed by the forward sweep, message
-    and d logit_scale exchange by peer stores) between processes that share GPU 0: runs on a single-GPU box."""
+# env: VPA_FWD1_CHUNKS=1 makes one CTA pair sweep ALL rank blocks (the chunk-major tile order over several peer blocks);
+# VPA_P2P_MODE=push selects the store-based operand transport instead of the default pull
+@pytest.mark.parametrize("world,precision,B,D,env", [
+    (2, "bf16", 1024, 512, None), (2, "bf16", 600, 256, None), (2, "fp32", 256, 128, None),
+    (4, "bf16", 2048, 512, {"VPA_FWD1_CHUNKS": "1"}), (3, "bf16", 1152, 512, None),
+    (4, "bf16", 4096, 256, {"VPA_FWD1_CHUNKS": "2", "VPA_P2P_MODE": "push"})])
+def test_p2p_transport_ranks_sharing_one_gpu(world, precision, B, D, env):
+    """The peer-memory transport (CUDA IPC segments, operand transfer + arrival flags consumed by the forward sweep,
+    message and d logit_scale exchange by peer stores) between processes that share GPU 0: runs on a single-GPU box."""
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, "p2p", True, 3, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, "p2p", True, 3, out, env), nprocs=world, join=True)
     _check(out, world, B, D, precision)
 
 

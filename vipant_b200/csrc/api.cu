@@ -568,7 +568,11 @@ int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype,
   const bool from_colpart = pack_reduces_columns(plan, precision);
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
                              h.colsum8, true, 1, st, &h.yflags, !from_colpart)) return e;
-  if (int e = p2p_wait_operands(p2p, epoch, st)) return e;      // everything after this may read all of a_all / t_all
+  // The exact two-sweep kernel (other regime) also reads the peers' x1 operands: wait for everything, but only then.  In
+  // the single-pass regime nothing of the forward needs them -- their transfer keeps overlapping the statistics exchange
+  // and the backward waits for it.
+  const bool single_pass = tcp && plan.impl == 1 && plan.fast_fwd;
+  if (int e = p2p_wait_operands(p2p, epoch, single_pass ? logit_scale : nullptr, (scale_max > 0.f) ? scale_max : INFINITY, st)) return e;
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
                              h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
   const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
@@ -593,6 +597,9 @@ int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x
   const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
   const char* a_loc = static_cast<const char*>(h.a_all) + (size_t)off * D * es;
   const char* t_loc = static_cast<const char*>(h.t_all) + (size_t)off * D * es;
+  if (cur == epoch) {       // (a later forward has already waited for this step's transfer: stream order)
+    if (int e = p2p_wait_operands(p2p, epoch, nullptr, INFINITY, st)) return e;      // all operands of the peers have landed
+  }
   if (int e = bwd_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B,
                        grad_out, x1, x2, in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes, dx1, dx2,
                        dlogit_scale, &h, st)) return e;

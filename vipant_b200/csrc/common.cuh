@@ -35,7 +35,7 @@ int set_error(int code, const char* fmt, ...);
 // ---- opt-in launch timing (vpa_profile_*): CUDA events recorded on the launch stream around the
 // dominant kernels; used by bench.py for the roofline numbers, off by default (no cost, no state).
 enum { PROF_NORMALIZE = 0, PROF_FWD_SWEEP = 1, PROF_BWD_SWEEP = 2, PROF_SIM = 3, PROF_RANK = 4, PROF_FWD_GENERAL = 5,
-       PROF_FINALIZE = 6, PROF_KINDS = 7 };
+       PROF_FINALIZE = 6, PROF_PUSH = 7, PROF_KINDS = 8 };
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);
 

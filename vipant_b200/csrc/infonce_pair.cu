@@ -247,6 +247,20 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const int tile0 = chunk * P.tiles_per_chunk;
   const int nt = min(P.tiles_per_chunk, P.n_tiles - tile0);
   const int row0 = iblk * C::RP + (int)crank * C::RC;   // first local X row of this CTA
+  // Order in which this CTA visits its tiles.  Over peer memory (single-pass forward) the rows of every peer block
+  // arrive chunk by chunk, all blocks at the same pace: a CTA whose range spans several whole rank blocks visits them
+  // chunk-major (chunk 0 of each block, chunk 1 of each block, ...) instead of one block after the other, so it never
+  // needs the LAST chunk of one peer before the first of the next.
+  int ilv_nb = 1, ilv_cpr = 1;
+  if (MODE == MODE_FWD1 && P.yflags.flags != nullptr && P.yflags.rows_per_rank % kBN == 0) {
+    const int cpr = P.yflags.chunks_per_rank;
+    if (tile0 % cpr == 0 && nt % cpr == 0 && nt / cpr > 1) { ilv_nb = nt / cpr; ilv_cpr = cpr; }
+  }
+  auto tile_at = [&](int j) {
+    if (ilv_nb == 1) return tile0 + j;
+    const int c = j / ilv_nb;
+    return tile0 + (j - c * ilv_nb) * ilv_cpr + c;
+  };
 
   const uint32_t bar0 = sbase + L.bars;
   auto bar = [&](int i) { return bar0 + 8u * i; };
@@ -307,7 +321,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
         }
     };
     for (int j = 0; j < nt; ++j) {
-      const int r = (tile0 + j) * kBN + (int)crank * 128;      // this CTA's half of the tile's Y rows
+      const int r = tile_at(j) * kBN + (int)crank * 128;       // this CTA's half of the tile's Y rows
       if (MODE == MODE_FWD1 && P.yflags.flags != nullptr) {
         // peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cu).  Poll the
         // chunk flags (system-scope acquire), then order the TMA (async proxy) reads after the observation.
@@ -454,7 +468,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
         const int b = j & 1;
         mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
         tc_fence_after();
-        const int col0 = (tile0 + j) * kBN;
+        const int col0 = tile_at(j) * kBN;
         const bool full = rows_full && (col0 + kBN <= pb.n_y);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {

@@ -141,16 +141,16 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
     put(B + 2 * b + idx, s * diag_cos[idx]);
   }
   if (p2p) {                                // last block done -> publish the message to every rank (system-scope epoch flag)
+    __shared__ bool last;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-      const uint32_t old = atomicAdd(pack_counter, 1u);
-      if ((old + 1) % gridDim.x == 0) {
-        __threadfence();
-        for (int q = 0; q < pv.world; ++q)
-          st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.base[q] + off_msg_flags) + pv.rank, pv.epoch);
-      }
+      last = ((atomicAdd(pack_counter, 1u) + 1) % gridDim.x) == 0;
+      __threadfence();
     }
+    __syncthreads();
+    if (last && (int)threadIdx.x < pv.world)      // one thread per destination: the release stores travel in parallel
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.base[threadIdx.x] + off_msg_flags) + pv.rank, pv.epoch);
   }
 }
 
@@ -348,15 +348,14 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
       if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      const float part_dls = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
-      if (pv.world > 1) {                   // peer-memory transport: {epoch, partial} into every rank's slot of this rank
+    const float part_dls = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
+    if (pv.world > 1) {                     // peer-memory transport: {epoch, partial} into every rank's slot of this rank,
+      if ((int)threadIdx.x < pv.world) {    // one thread per destination
         const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
-        for (int q = 0; q < pv.world; ++q)
-          st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[q] + off_dls) + pv.rank, w);
-      } else {
-        *dlogit_scale = part_dls;
+        st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[threadIdx.x] + off_dls) + pv.rank, w);
       }
+    } else if (threadIdx.x == 0) {
+      *dlogit_scale = part_dls;
     }
   }
 }

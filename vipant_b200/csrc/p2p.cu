@@ -20,6 +20,7 @@ namespace vpa {
 struct SegLayout {
   size_t flags[2];          // [m][world][cpr] uint32: m = 0 x2 operands (t_all), 1 x1 operands (a_all)
   size_t msg_flags;         // [world] uint32
+  size_t ready;             // [world] uint32: rank q's operands of epoch e are complete in ITS segment (pull mode)
   size_t dls_slots;         // [2][world] uint64 {epoch << 32 | float bits}
   size_t counters;          // local only: [2][cpr] push arrivals, [1] pack arrivals, [1] loss arrivals
   size_t loss_part;         // local only: per-block loss partials (doubles)
@@ -44,6 +45,7 @@ static SegLayout seg_layout(int64_t b, int world, int D, int precision) {
   L.cpr = (int)((b + kPushRows - 1) / kPushRows);
   for (int m = 0; m < 2; ++m) L.flags[m] = take((size_t)world * L.cpr * 4);
   L.msg_flags = take((size_t)world * 4);
+  L.ready = take((size_t)world * 4);
   L.dls_slots = take((size_t)2 * world * 8);
   L.counters = take((size_t)(2 * L.cpr + 2) * 4);
   L.loss_part = take((size_t)((B + 255) / 256) * 8);
@@ -75,6 +77,7 @@ struct P2PHandle {
   cudaEvent_t fork = nullptr, join = nullptr;
   bool join_pending = false;
   int push_groups = 8, push_ctas = 4, push_rounds = 8;
+  int pull = 1, pull_ctas = 64;
 };
 
 // ---------------------------------------------------------------- kernels
@@ -138,9 +141,73 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(const PushArgs A) {
   }
 }
 
+// ---- operands, consumer driven: every rank PULLS its peers' rows (loads over NVLink, stores to local memory) ------------
+// No system-scope fence per chunk (the puller knows when its own loads have returned) and the only remote store is one
+// "my rows are complete" flag per peer and step; a chunk's arrival flag is a local store.  Items are ordered x2 operands
+// first, chunk-major over the peers, so the forward sweep finds the early tiles of every peer block first.
+struct PullArgs {
+  P2PView v;
+  size_t off_mat[2], off_flags[2], off_ready;
+  int64_t b;
+  int row_bytes, cpr;
+};
+constexpr int kPullUnroll = 8;
+
+__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {      // L1 must not serve a line cached two steps ago
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
+  const int me = A.v.rank, world = A.v.world;
+  char* mine = A.v.base[me];
+  if (blockIdx.x == 0 && (int)threadIdx.x < world && (int)threadIdx.x != me) {
+    // the normalise kernel that wrote this rank's rows finished before this kernel started (stream order)
+    __threadfence_system();
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[threadIdx.x] + A.off_ready) + me, A.v.epoch);
+  }
+  const uint32_t* ready = reinterpret_cast<const uint32_t*>(mine + A.off_ready);
+  const int per_m = (world - 1) * A.cpr, total = 2 * per_m;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int m = item / per_m, r = item - m * per_m;
+    const int c = r / (world - 1), q = r - c * (world - 1) + 1;
+    const int src = (me + q) % world;
+    if (threadIdx.x == 0) p2p_wait_ge(ready + src, A.v.epoch);
+    __syncthreads();
+    const int64_t row0 = (int64_t)c * kPushRows;
+    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
+    const int n16 = rows * (A.row_bytes / 16);
+    const size_t off = A.off_mat[m] + ((size_t)src * A.b + row0) * A.row_bytes;
+    const uint4* from = reinterpret_cast<const uint4*>(A.v.base[src] + off);
+    uint4* to = reinterpret_cast<uint4*>(mine + off);
+    for (int i = threadIdx.x; i < n16; i += 256 * kPullUnroll) {
+      uint4 val[kPullUnroll];
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * 256;
+        if (idx < n16) val[u] = ld_peer_v4(from + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * 256;
+        if (idx < n16) to[idx] = val[u];
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(mine + A.off_flags[m]) + src * A.cpr + c, A.v.epoch);
+  }
+}
+
 // every operand chunk of every peer has landed (both matrices): what all later kernels of the step rely on
+// gate_scale != nullptr: only in the exact two-sweep regime (s * log2e > limit, decided on the device like the sweeps do);
+// the single-pass forward has consumed every x2-operand chunk itself and reads no x1 operands of the peers.
 __global__ void p2p_wait_all_kernel(const uint32_t* __restrict__ flags_t, const uint32_t* __restrict__ flags_a, int world,
-                                    int cpr, int me, uint32_t epoch) {
+                                    int cpr, int me, uint32_t epoch, const float* __restrict__ gate_scale, float scale_cap,
+                                    float s2_limit) {
+  if (gate_scale != nullptr && fminf(expf(*gate_scale), scale_cap) * kLog2e <= s2_limit) return;
   const int n = world * cpr;
   for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
     const int m = i >= n, k = i - m * n;
@@ -208,6 +275,8 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
+  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") != 0;
+  if (const char* s = getenv("VPA_P2P_PULL_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_ROUNDS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->push_rounds = v; }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
   *out = h;
@@ -316,8 +385,21 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
   A.groups = h->push_groups < 2 * nbatch ? h->push_groups : 2 * nbatch;
   VPA_CUDA(cudaEventRecord(h->fork, st));
   VPA_CUDA(cudaStreamWaitEvent(h->side, h->fork, 0));
-  p2p_push_kernel<<<A.groups * A.ctas_per_group, 256, 0, h->side>>>(A);
-  VPA_LAUNCH_CHECK("p2p_push_kernel");
+  prof_begin(PROF_PUSH, h->side);
+  if (h->pull) {
+    PullArgs G{};
+    G.v = A.v;
+    G.off_mat[0] = A.off_mat[0]; G.off_mat[1] = A.off_mat[1];
+    G.off_flags[0] = A.off_flags[0]; G.off_flags[1] = A.off_flags[1];
+    G.off_ready = L.ready;
+    G.b = h->b; G.row_bytes = A.row_bytes; G.cpr = L.cpr;
+    const int items = 2 * (h->world - 1) * L.cpr;
+    p2p_pull_kernel<<<items < h->pull_ctas ? items : h->pull_ctas, 256, 0, h->side>>>(G);
+  } else {
+    p2p_push_kernel<<<A.groups * A.ctas_per_group, 256, 0, h->side>>>(A);
+  }
+  prof_end(PROF_PUSH, h->side);
+  VPA_LAUNCH_CHECK("p2p_push / p2p_pull kernel");
   VPA_CUDA(cudaEventRecord(h->join, h->side));
   h->join_pending = true;
   return 0;
@@ -331,12 +413,13 @@ int p2p_join_push(void* handle, cudaStream_t st) {
   return 0;
 }
 
-int p2p_wait_operands(void* handle, uint32_t epoch, cudaStream_t st) {
+int p2p_wait_operands(void* handle, uint32_t epoch, const float* gate_scale, float scale_cap, cudaStream_t st) {
   P2PHandle* h = static_cast<P2PHandle*>(handle);
   const SegLayout& L = h->L;
   char* base = h->base[h->rank];
   p2p_wait_all_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(base + L.flags[0]),
-                                         reinterpret_cast<const uint32_t*>(base + L.flags[1]), h->world, L.cpr, h->rank, epoch);
+                                         reinterpret_cast<const uint32_t*>(base + L.flags[1]), h->world, L.cpr, h->rank, epoch,
+                                         gate_scale, scale_cap, pair_fast_s2_limit());
   VPA_LAUNCH_CHECK("p2p_wait_all_kernel");
   return 0;
 }

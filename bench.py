@@ -353,7 +353,10 @@ def main():
                              if prof["finalize"][1] else None, "peak_gbs": pk["hbm"]},
             "normalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 2) + 12 * b) / (nrm_ms / max(nrm_n, 1) * 1e-3) / 1e9 if nrm_n else None,
                               "peak_gbs": pk["hbm"]},
-            "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": 10 * args.steps,
+            "roofline": roofline, "clocks": clocks, "e2e": e2e,
+            # kernels of libvipant_b200.so per step: normalise, single-pass fwd, exact fwd (device-gated), column reduce / pack,
+            # merge+loss, bwd sweep, finalize (+ operand pull, 2 flag waits, d logit_scale sum on the peer-memory transport)
+            "gpu_launches": {"local": 8, "p2p": 11, "nccl": 8, "host": 9}[transport] * args.steps,
         }
         if not args.no_cpu_baseline and world == 1:
             cx1, cx2, cls_, cb, cores = cpu_block_sample(B, D)

@@ -208,6 +208,34 @@ def test_host_buffer_entry_point():
         assert abs(dls.value - ref.dlogit_scale) <= tol["grad"] * abs(ref.dlogit_scale)
 
 
+@pytest.mark.parametrize("B,shards,ls,rho", [(2048, 4, math.log(1 / 0.07), 0.3), (1536, 3, math.log(1 / 0.07), 0.3),
+                                             (1024, 2, math.log(100.0), 0.1)])
+def test_host_buffer_entry_point_pipelined(B, shards, ls, rho, monkeypatch):
+    """The pipelined host step: V row shards, copy-in / sweeps / copy-out overlapped on three streams (the default for
+    batches >= 8192; forced here at a size the oracle handles).  ls = log(100) exercises the exact two-sweep regime."""
+    from vipant_b200 import _cabi
+    lib = _cabi.lib()
+    D = 512
+    monkeypatch.setenv("VPA_HOST_SHARDS", str(shards))
+    x1n, x2n = io.make_pair(B, D, rho, 77)       # rho = 0.1 at s = 100: a loss that is not vanishingly small
+    ref = io.infonce_closed_form(x1n, x2n, float(np.float32(ls)), None, False, 2.0)
+    prec, tol = _cabi.PREC_BF16_TC, TOL["bf16"]
+    nbytes = lib.vpa_infonce_host_scratch_bytes(B, D, prec)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    x1p, x2p = torch.from_numpy(x1n).pin_memory(), torch.from_numpy(x2n).pin_memory()
+    dx1, dx2 = torch.empty_like(x1p).pin_memory(), torch.empty_like(x2p).pin_memory()
+    for _ in range(2):            # twice: events / streams are reused across calls
+        dx1.zero_(); dx2.zero_()
+        loss, dls = ctypes.c_float(), ctypes.c_float()
+        rc = lib.vpa_infonce_step_host(x1p.data_ptr(), x2p.data_ptr(), B, D, ls, 0.0, 2.0, prec, scratch.data_ptr(), nbytes,
+                                       ctypes.addressof(loss), ctypes.addressof(dls), dx1.data_ptr(), dx2.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.vpa_last_error_string()
+        assert abs(loss.value - ref.loss) <= tol["loss"] * abs(ref.loss)
+        assert rel(dx1.numpy(), ref.dx1) <= tol["grad"] and rel(dx2.numpy(), ref.dx2) <= tol["grad"]
+        assert abs(dls.value - ref.dlogit_scale) <= tol["grad"] * abs(ref.dlogit_scale)
+
+
 def test_loss_head_module_train_step_with_amp():
     """The monitors' step: autocast + GradScaler (cvap/monitor/cvap.py:189-193) through the drop-in module."""
     import vipant_b200 as vb

@@ -37,11 +37,12 @@ def _worker(rank, world, port, B, D, precision, transport, shared_device, steps,
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
     try:
         import vipant_b200 as vb
-        x1n, x2n = io.make_pair(B, D, 0.3, 21)
+        lsv, rho = _case(env)
+        x1n, x2n = io.make_pair(B, D, rho, 21)
         b = B // world
         x1 = torch.from_numpy(x1n[rank * b:(rank + 1) * b]).cuda().requires_grad_(True)
         x2 = torch.from_numpy(x2n[rank * b:(rank + 1) * b]).cuda().requires_grad_(True)
-        ls = torch.tensor(math.log(1 / 0.07), device="cuda", requires_grad=True)
+        ls = torch.tensor(lsv, device="cuda", requires_grad=True)
         for _ in range(steps):       # several steps: epochs, buffer parity and flag reuse of the peer-memory transport
             x1.grad = x2.grad = ls.grad = None
             loss = vb.infonce_loss(x1, x2, ls, precision=precision, group=dist.group.WORLD)
@@ -53,9 +54,17 @@ def _worker(rank, world, port, B, D, precision, transport, shared_device, steps,
         dist.destroy_process_group()
 
 
-def _check(out, world, B, D, precision):
-    x1n, x2n = io.make_pair(B, D, 0.3, 21)
-    ref = io.infonce_closed_form(x1n, x2n, grad_output=3.0)
+def _case(env):
+    """(logit_scale, rho): TEST_SCALE100 selects the exact two-sweep regime (s = 100 > 43) on data whose loss is not tiny."""
+    if env and env.get("TEST_SCALE100"):
+        return math.log(100.0), 0.1
+    return math.log(1 / 0.07), 0.3
+
+
+def _check(out, world, B, D, precision, env=None):
+    lsv, rho = _case(env)
+    x1n, x2n = io.make_pair(B, D, rho, 21)
+    ref = io.infonce_closed_form(x1n, x2n, float(np.float32(lsv)), grad_output=3.0)
     tl, tg = (1e-3, 1e-2) if precision == "bf16" else (1e-4, 1e-3)
     b = B // world
 
@@ -75,14 +84,15 @@ def _check(out, world, B, D, precision):
 @pytest.mark.parametrize("world,precision,B,D,env", [
     (2, "bf16", 1024, 512, None), (2, "bf16", 600, 256, None), (2, "fp32", 256, 128, None),
     (4, "bf16", 2048, 512, {"VPA_FWD1_CHUNKS": "1"}), (3, "bf16", 1152, 512, None),
-    (4, "bf16", 4096, 256, {"VPA_FWD1_CHUNKS": "2", "VPA_P2P_MODE": "push"})])
+    (4, "bf16", 4096, 256, {"VPA_FWD1_CHUNKS": "2", "VPA_P2P_MODE": "push"}),
+    (2, "bf16", 1024, 512, {"TEST_SCALE100": "1"})])
 def test_p2p_transport_ranks_sharing_one_gpu(world, precision, B, D, env):
     """The peer-memory transport (CUDA IPC segments, operand transfer + arrival flags consumed by the forward sweep,
     message and d logit_scale exchange by peer stores) between processes that share GPU 0: runs on a single-GPU box."""
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), B, D, precision, "p2p", True, 3, out, env), nprocs=world, join=True)
-    _check(out, world, B, D, precision)
+    _check(out, world, B, D, precision, env)
 
 
 @pytest.mark.parametrize("transport", ["p2p", "nccl", "host"])

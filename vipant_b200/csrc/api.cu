@@ -70,6 +70,7 @@ int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows
                         const float* scale, const float* grad_out, const void* x1, const void* x2,
                         int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
                         int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, cudaStream_t st);
+int diag_cos_bf16_launch(const void* a_bf16, const void* t_bf16, int64_t rows, int D, float* diag_cos, cudaStream_t st);
 int sim_rank_topk_launch(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
                          const int32_t* gt_idx, int g, int k, int64_t* topk_idx, float* topk_val,
                          int32_t* ranks, float* S, cudaStream_t st);
@@ -607,11 +608,28 @@ int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x
 }
 
 // ---- host-buffer end-to-end step ---------------------------------------------------------------------
+// Pipelined over V row shards of the batch (the same row-sharded sweeps the multi-GPU path runs, all on one device):
+//   copy-in stream:  x2 (whole) | x1 shard 0 | x1 shard 1 | ...
+//   compute stream:  normalise x2 | per shard, as it lands: normalise x1 shard, <a_i,t_i>, single-pass forward sweep of the
+//                    shard's rows against ALL x2 rows | statistics merge + loss | per shard: backward sweeps + finalize
+//   copy-out stream: dx1 / dx2 of shard k while shard k+1 computes
+// so the PCIe transfers hide behind the sweeps except the first matrix in and the last shard out.
 struct HostScratch {
-  float *x1, *x2, *af, *tf, *inv1, *inv2, *dcos, *rl, *cl, *dg, *sc, *loss, *dls, *gout, *lsc, *dx1, *dx2;
-  void *ab, *tb, *ws;
+  float *x1, *x2, *af, *tf, *inv1, *inv2, *dcos, *msgs, *stats_all, *sc, *loss, *dls, *gout, *lsc, *dx1, *dx2, *colsum8;
+  double* loss_part;
+  uint32_t* loss_counter;
+  void *ab, *tb;
+  void* ws[16];
   size_t ws_bytes, bytes;
+  int shards;
 };
+static int host_shards(int64_t rows, int D, int precision) {
+  if (precision != VPA_PREC_BF16_TC || !(D == 256 || D == 512)) return 1;      // the pipeline is built on the CTA-pair sweeps
+  int v = rows >= 32768 ? 8 : (rows >= 8192 ? 4 : 1);      // measured at 32768 x 512: 8.64 ms unpipelined, 6.79 (4 shards), 6.42 (8)
+  if (const char* e = getenv("VPA_HOST_SHARDS")) { const int q = atoi(e); if (q >= 1 && q <= 16) v = q; }
+  while (v > 1 && (rows % ((int64_t)v * 256) != 0)) --v;      // equal shards on 256-row tile boundaries
+  return v;
+}
 static HostScratch carve_host(void* base, int64_t rows, int D, int precision) {
   HostScratch h{};
   size_t o = 0;
@@ -621,16 +639,22 @@ static HostScratch carve_host(void* base, int64_t rows, int D, int precision) {
     return p;
   };
   const size_t mat = (size_t)rows * D;
+  h.shards = host_shards(rows, D, precision);
+  const int64_t b = rows / h.shards;
   h.x1 = (float*)take(mat * 4); h.x2 = (float*)take(mat * 4);
   h.dx1 = (float*)take(mat * 4); h.dx2 = (float*)take(mat * 4);
   h.ab = take(mat * 2); h.tb = take(mat * 2);
   if (precision == VPA_PREC_FP32_SIMT) { h.af = (float*)take(mat * 4); h.tf = (float*)take(mat * 4); }
   h.inv1 = (float*)take(rows * 4); h.inv2 = (float*)take(rows * 4); h.dcos = (float*)take(rows * 4);
-  h.rl = (float*)take(rows * 4); h.cl = (float*)take(rows * 4); h.dg = (float*)take(rows * 4);
-  h.sc = (float*)take(16); h.loss = (float*)take(16); h.dls = (float*)take(16);
+  h.msgs = (float*)take((size_t)h.shards * (rows + 3 * b) * 4);
+  h.stats_all = (float*)take((size_t)3 * rows * 4);
+  h.colsum8 = (float*)take((size_t)kColSumSplit * rows * 4);
+  h.loss_part = (double*)take((size_t)((rows + 255) / 256) * 8);
+  h.loss_counter = (uint32_t*)take(4);
+  h.sc = (float*)take(16); h.loss = (float*)take(16); h.dls = (float*)take(16 * 4);
   h.gout = (float*)take(16); h.lsc = (float*)take(16);
-  h.ws_bytes = vpa_infonce_workspace_bytes(rows, rows, D, precision);
-  h.ws = take(h.ws_bytes);
+  h.ws_bytes = vpa_infonce_workspace_bytes(b, rows, D, precision);
+  for (int k = 0; k < h.shards; ++k) h.ws[k] = take(h.ws_bytes);
   h.bytes = o;
   return h;
 }
@@ -638,6 +662,31 @@ static HostScratch carve_host(void* base, int64_t rows, int D, int precision) {
 size_t vpa_infonce_host_scratch_bytes(int64_t rows, int D, int precision) {
   if (rows <= 0 || D <= 0) return 0;
   return carve_host(nullptr, rows, D, precision).bytes;
+}
+
+struct HostPipe {       // copy streams + events of the pipelined host step (one set per thread and device)
+  cudaStream_t cin = nullptr, cout = nullptr;
+  cudaEvent_t start = nullptr, x2_in = nullptr, x1_in[16] = {}, bwd_done[16] = {}, out_done = nullptr;
+  int dev = -1;
+};
+static int host_pipe(HostPipe** out) {
+  static thread_local HostPipe hp;
+  int dev = 0;
+  VPA_CUDA(cudaGetDevice(&dev));
+  if (!hp.cin || hp.dev != dev) {
+    VPA_CUDA(cudaStreamCreateWithFlags(&hp.cin, cudaStreamNonBlocking));
+    VPA_CUDA(cudaStreamCreateWithFlags(&hp.cout, cudaStreamNonBlocking));
+    VPA_CUDA(cudaEventCreateWithFlags(&hp.start, cudaEventDisableTiming));
+    VPA_CUDA(cudaEventCreateWithFlags(&hp.x2_in, cudaEventDisableTiming));
+    VPA_CUDA(cudaEventCreateWithFlags(&hp.out_done, cudaEventDisableTiming));
+    for (int k = 0; k < 16; ++k) {
+      VPA_CUDA(cudaEventCreateWithFlags(&hp.x1_in[k], cudaEventDisableTiming));
+      VPA_CUDA(cudaEventCreateWithFlags(&hp.bwd_done[k], cudaEventDisableTiming));
+    }
+    hp.dev = dev;
+  }
+  *out = &hp;
+  return 0;
 }
 
 int vpa_infonce_step_host(const float* x1_host, const float* x2_host, int64_t rows, int D, float logit_scale,
@@ -650,25 +699,97 @@ int vpa_infonce_step_host(const float* x1_host, const float* x2_host, int64_t ro
   if (h.bytes > dev_scratch_bytes) return set_error(VPA_E_WORKSPACE, "infonce_step_host: scratch %zu < %zu", dev_scratch_bytes, h.bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t mat = (size_t)rows * D * sizeof(float);
-  VPA_CUDA(cudaMemcpyAsync(h.x1, x1_host, mat, cudaMemcpyHostToDevice, st));
-  VPA_CUDA(cudaMemcpyAsync(h.x2, x2_host, mat, cudaMemcpyHostToDevice, st));
+  const bool tcp = precision == VPA_PREC_BF16_TC;
+  if (h.shards == 1) {        // small batches / fp32 mode: one shot
+    VPA_CUDA(cudaMemcpyAsync(h.x1, x1_host, mat, cudaMemcpyHostToDevice, st));
+    VPA_CUDA(cudaMemcpyAsync(h.x2, x2_host, mat, cudaMemcpyHostToDevice, st));
+    VPA_CUDA(cudaMemcpyAsync(h.lsc, &logit_scale, sizeof(float), cudaMemcpyHostToDevice, st));
+    VPA_CUDA(cudaMemcpyAsync(h.gout, &grad_out, sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int e = vpa_normalize_pair(h.x1, h.x2, VPA_F32, rows, D, D, D, 0, tcp ? h.ab : nullptr, tcp ? h.tb : nullptr,
+                                   h.af, h.tf, h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
+    const void* a = tcp ? h.ab : (const void*)h.af;
+    const void* t = tcp ? h.tb : (const void*)h.tf;
+    float* rl = h.stats_all, *cl = h.stats_all + rows, *dg = h.stats_all + 2 * rows;
+    if (int e = vpa_infonce_fwd(a, t, a, t, precision, rows, rows, D, 0, h.lsc, scale_max, h.dcos, h.ws[0], h.ws_bytes,
+                                rl, cl, dg, h.sc, st)) return e;
+    if (int e = vpa_infonce_loss(rl, cl, dg, rows, h.loss, st)) return e;
+    if (int e = vpa_infonce_bwd(a, t, a, t, precision, rows, rows, D, 0, h.sc, rl, cl, h.gout, h.x1, h.x2, VPA_F32,
+                                D, D, h.inv1, h.inv2, 0, h.ws[0], h.ws_bytes, h.dx1, h.dx2, h.dls, st)) return e;
+    VPA_CUDA(cudaMemcpyAsync(loss_host, h.loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (dlogit_scale_host) VPA_CUDA(cudaMemcpyAsync(dlogit_scale_host, h.dls, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (dx1_host) VPA_CUDA(cudaMemcpyAsync(dx1_host, h.dx1, mat, cudaMemcpyDeviceToHost, st));
+    if (dx2_host) VPA_CUDA(cudaMemcpyAsync(dx2_host, h.dx2, mat, cudaMemcpyDeviceToHost, st));
+    VPA_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+
+  HostPipe* hp = nullptr;
+  if (int e = host_pipe(&hp)) return e;
+  const int V = h.shards;
+  const int64_t b = rows / V;
+  const size_t shard_elems = (size_t)b * D, shard_bytes = shard_elems * sizeof(float);
+  const SweepPlan plan = plan_sweep(b, rows, D, precision);
+  const bool from_colpart = pack_reduces_columns(plan, precision);
+  const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
+  char* ab = static_cast<char*>(h.ab);
+  char* tb = static_cast<char*>(h.tb);
+  // ---- copy-in: x2 first (every forward shard sweeps all of it), then x1 shard by shard
+  VPA_CUDA(cudaEventRecord(hp->start, st));
+  VPA_CUDA(cudaStreamWaitEvent(hp->cin, hp->start, 0));
+  VPA_CUDA(cudaMemcpyAsync(h.x2, x2_host, mat, cudaMemcpyHostToDevice, hp->cin));
+  VPA_CUDA(cudaEventRecord(hp->x2_in, hp->cin));
+  for (int k = 0; k < V; ++k) {
+    VPA_CUDA(cudaMemcpyAsync(h.x1 + k * shard_elems, x1_host + k * shard_elems, shard_bytes, cudaMemcpyHostToDevice, hp->cin));
+    VPA_CUDA(cudaEventRecord(hp->x1_in[k], hp->cin));
+  }
   VPA_CUDA(cudaMemcpyAsync(h.lsc, &logit_scale, sizeof(float), cudaMemcpyHostToDevice, st));
   VPA_CUDA(cudaMemcpyAsync(h.gout, &grad_out, sizeof(float), cudaMemcpyHostToDevice, st));
-  const bool tcp = precision == VPA_PREC_BF16_TC;
-  if (int e = vpa_normalize_pair(h.x1, h.x2, VPA_F32, rows, D, D, D, 0, tcp ? h.ab : nullptr, tcp ? h.tb : nullptr,
-                                 h.af, h.tf, h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
-  const void* a = tcp ? h.ab : (const void*)h.af;
-  const void* t = tcp ? h.tb : (const void*)h.tf;
-  if (int e = vpa_infonce_fwd(a, t, a, t, precision, rows, rows, D, 0, h.lsc, scale_max, h.dcos, h.ws, h.ws_bytes,
-                              h.rl, h.cl, h.dg, h.sc, st)) return e;
-  if (int e = vpa_infonce_loss(h.rl, h.cl, h.dg, rows, h.loss, st)) return e;
-  if (int e = vpa_infonce_bwd(a, t, a, t, precision, rows, rows, D, 0, h.sc, h.rl, h.cl, h.gout, h.x1, h.x2, VPA_F32,
-                              D, D, h.inv1, h.inv2, 0, h.ws, h.ws_bytes, h.dx1, h.dx2, h.dls, st)) return e;
+  VPA_CUDA(cudaMemsetAsync(h.loss_counter, 0, 4, st));
+  // ---- forward
+  VPA_CUDA(cudaStreamWaitEvent(st, hp->x2_in, 0));
+  if (int e = normalize_cast_launch(h.x2, VPA_F32, rows, D, D, 0, h.tb, nullptr, h.inv2, st)) return e;
+  for (int k = 0; k < V; ++k) {
+    const int64_t off = (int64_t)k * b;
+    VPA_CUDA(cudaStreamWaitEvent(st, hp->x1_in[k], 0));
+    if (int e = normalize_cast_launch(h.x1 + k * shard_elems, VPA_F32, b, D, D, 0, ab + off * D * 2, nullptr, h.inv1 + off, st)) return e;
+    if (int e = diag_cos_bf16_launch(ab + off * D * 2, tb + off * D * 2, b, D, h.dcos + off, st)) return e;
+    // single-pass sweep of this shard's x1 rows against all x2 rows (reads nothing of the x1 shards still in flight)
+    if (int e = fwd_sweep_impl(ab + off * D * 2, tb + off * D * 2, h.ab, h.tb, precision, b, rows, D, off, h.lsc, scale_max,
+                               h.ws[k], h.ws_bytes, h.colsum8, true, 1, st, nullptr, !from_colpart)) return e;
+  }
+  for (int k = 0; k < V; ++k) {        // the exact-regime kernel (device-gated) needs all x1 operands; then the shard's message
+    const int64_t off = (int64_t)k * b;
+    if (int e = fwd_sweep_impl(ab + off * D * 2, tb + off * D * 2, h.ab, h.tb, precision, b, rows, D, off, h.lsc, scale_max,
+                               h.ws[k], h.ws_bytes, h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
+    const Workspace ws = carve_workspace(h.ws[k], b, rows, D, plan);
+    if (int e = pack_stats_launch(ws, plan, b, rows, h.lsc, cap, h.dcos + off, 1, h.colsum8, from_colpart,
+                                  h.msgs + (size_t)k * (rows + 3 * b), nullptr, st)) return e;
+  }
+  if (int e = merge_stats_launch(h.msgs, V, b, rows, h.lsc, cap, 1, h.stats_all, h.sc, nullptr, h.loss_part, h.loss_counter,
+                                 h.loss, st)) return e;
+  // ---- backward, shard by shard; gradients leave on the copy-out stream while the next shard computes
+  for (int k = 0; k < V; ++k) {
+    const int64_t off = (int64_t)k * b;
+    if (int e = bwd_impl(ab + off * D * 2, tb + off * D * 2, h.ab, h.tb, precision, b, rows, D, off, h.sc, h.stats_all,
+                         h.stats_all + rows, h.gout, h.x1 + k * shard_elems, h.x2 + k * shard_elems, VPA_F32, D, D,
+                         h.inv1 + off, h.inv2 + off, 0, h.ws[k], h.ws_bytes, h.dx1 + k * shard_elems, h.dx2 + k * shard_elems,
+                         h.dls + k, nullptr, st)) return e;
+    VPA_CUDA(cudaEventRecord(hp->bwd_done[k], st));
+    VPA_CUDA(cudaStreamWaitEvent(hp->cout, hp->bwd_done[k], 0));
+    if (dx1_host) VPA_CUDA(cudaMemcpyAsync(dx1_host + k * shard_elems, h.dx1 + k * shard_elems, shard_bytes, cudaMemcpyDeviceToHost, hp->cout));
+    if (dx2_host) VPA_CUDA(cudaMemcpyAsync(dx2_host + k * shard_elems, h.dx2 + k * shard_elems, shard_bytes, cudaMemcpyDeviceToHost, hp->cout));
+  }
+  float dls_parts[16] = {};
+  VPA_CUDA(cudaMemcpyAsync(dls_parts, h.dls, sizeof(float) * V, cudaMemcpyDeviceToHost, hp->cout));
+  VPA_CUDA(cudaEventRecord(hp->out_done, hp->cout));
+  VPA_CUDA(cudaStreamWaitEvent(st, hp->out_done, 0));        // the caller's stream observes the whole step
   VPA_CUDA(cudaMemcpyAsync(loss_host, h.loss, sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (dlogit_scale_host) VPA_CUDA(cudaMemcpyAsync(dlogit_scale_host, h.dls, sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (dx1_host) VPA_CUDA(cudaMemcpyAsync(dx1_host, h.dx1, mat, cudaMemcpyDeviceToHost, st));
-  if (dx2_host) VPA_CUDA(cudaMemcpyAsync(dx2_host, h.dx2, mat, cudaMemcpyDeviceToHost, st));
   VPA_CUDA(cudaStreamSynchronize(st));
+  if (dlogit_scale_host) {
+    double acc = 0.0;
+    for (int k = 0; k < V; ++k) acc += (double)dls_parts[k];   // shard order: deterministic
+    *dlogit_scale_host = (float)acc;
+  }
   return 0;
 }
 

@@ -138,6 +138,23 @@ normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, 
   }
 }
 
+// diag_cos[i] = <a_i, t_i> of already normalised bf16 rows (exactly the operands the tensor cores multiply): used when the
+// two modalities were normalised by separate launches (pipelined host step).  One warp per row.
+__global__ void __launch_bounds__(kNormWarps * 32)
+diag_cos_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ t, int64_t rows, int D,
+                     float* __restrict__ diag_cos) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int c = lane; c < (D >> 2); c += 32) {
+    const float4 p = load4<VPA_BF16>(a, row * D + 4 * c), q = load4<VPA_BF16>(t, row * D + 4 * c);
+    dot += p.x * q.x + p.y * q.y + p.z * q.z + p.w * q.w;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) diag_cos[row] = dot;
+}
+
 static int check_rows(const void* x, int64_t rows, int D, int64_t ld, int in_dtype) {
   VPA_CHECK_ARG(x != nullptr, "normalize: null input");
   VPA_CHECK_ARG(rows >= 0 && D > 0 && (D % 4) == 0, "normalize: need rows >= 0, D %% 4 == 0 (D=%d)", D);
@@ -163,6 +180,15 @@ int normalize_cast_launch(const void* x, int in_dtype, int64_t rows, int D, int6
   else { VPA_NORM(VPA_F16) }
 #undef VPA_NORM
   VPA_LAUNCH_CHECK("normalize_cast_kernel");
+  return 0;
+}
+
+int diag_cos_bf16_launch(const void* a_bf16, const void* t_bf16, int64_t rows, int D, float* diag_cos, cudaStream_t st) {
+  if (rows == 0) return 0;
+  dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps)), block(kNormWarps * 32);
+  diag_cos_bf16_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16),
+                                               reinterpret_cast<const __nv_bfloat16*>(t_bf16), rows, D, diag_cos);
+  VPA_LAUNCH_CHECK("diag_cos_bf16_kernel");
   return 0;
 }
 

@@ -60,6 +60,10 @@ const char* vpa_last_error_string(void);
 #define VPA_PROF_FINALIZE 6
 #define VPA_PROF_PUSH 7 /* peer-memory transport: the operand push kernel (side stream) */
 int vpa_profile_enable(int on);
+/* Work decomposition chosen for a shape (diagnostics / tests; host only, no device needed): out10 = n_tiles, single-pass
+ * forward {chunks, tiles per equal chunk, tiles of the short tail chunk}, backward {same three}, forward row blocks,
+ * backward row blocks, impl (1 = CTA-pair kernels). */
+int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision, int* out10);
 int vpa_profile_read(int kind, float* total_ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------

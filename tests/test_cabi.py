@@ -83,3 +83,21 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.VipantB200Error, match="no CPU or PyTorch fallback"):
         _cabi.lib()
+
+
+@pytest.mark.parametrize("b,B", [(32768, 32768), (16384, 32768), (8192, 32768), (4096, 32768), (512, 512), (640, 640),
+                                 (384, 1152), (64, 64), (1000, 1000), (4096, 4096), (2048, 16384), (300, 2400)])
+def test_sweep_plan_covers_every_tile(b, B):
+    """vpa_plan_query (host only): every row block's tiles are covered exactly once by n_big equal chunks + one short tail."""
+    import ctypes
+    from vipant_b200 import _cabi
+    lib = _cabi.lib()
+    out = (ctypes.c_int * 10)()
+    assert lib.vpa_plan_query(b, B, 512, _cabi.PREC_BF16_TC, out) == 0
+    n_tiles, f_chunks, f_tpc, f_small, b_chunks, b_tpc, b_small, f_iblk, b_iblk, impl = list(out)
+    assert impl == 1 and n_tiles == -(-B // 256) and f_iblk == -(-b // 256) and b_iblk == -(-b // 128)
+    for chunks, tpc, small in ((f_chunks, f_tpc, f_small), (b_chunks, b_tpc, b_small)):
+        n_big = chunks - (1 if small else 0)
+        big_tiles = n_tiles - small
+        assert n_big >= 1 and 0 <= small < max(tpc, 1) + (small == 0)
+        assert (n_big - 1) * tpc < big_tiles <= n_big * tpc          # no empty chunk, nothing left over

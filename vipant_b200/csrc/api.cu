@@ -3,6 +3,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
 
 #include "common.cuh"
 #include "p2p.cuh"
@@ -107,7 +113,61 @@ static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int
   *chunks = (n_tiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
 }
 
+// Pair kernels: split every row block's n_tiles into k equal chunks (+ optionally one short tail) so that the makespan on the
+// SM pairs is minimal.  The grid lists all big units first, then the tails, and the hardware hands the next unit to the
+// first free slot: simulated here exactly (in-order list scheduling).  `fixed` = per-unit cost in tile equivalents.
+// Equal chunking alone wastes up to a whole wave when units do not divide the slots (64 backward units on 74 slots).
+static void pick_split(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int* small_tiles) {
+  const int slots = sm_count() / 2;
+  long best = -1;
+  int best_k = 1, best_small = 0;
+  const int kmax = n_tiles < 16 ? n_tiles : 16;
+  std::vector<long> heap;
+  for (int k = 1; k <= kmax; ++k) {
+    for (int small = 0; small < n_tiles && small <= 48; ++small) {
+      const int big_tiles = n_tiles - small;
+      const int tpc = (big_tiles + k - 1) / k;
+      if ((long)(k - 1) * tpc >= big_tiles) continue;                 // an empty chunk
+      if (small > 0 && small >= tpc) break;                             // the tail must be the short one
+      heap.assign(slots, 0);                                            // min-heap of the slots' free times
+      long makespan = 0;
+      auto place = [&](long cost) {
+        std::pop_heap(heap.begin(), heap.end(), std::greater<long>());
+        heap.back() += cost;
+        if (heap.back() > makespan) makespan = heap.back();
+        std::push_heap(heap.begin(), heap.end(), std::greater<long>());
+      };
+      const int last = big_tiles - (k - 1) * tpc;                       // the last big chunk may be shorter
+      for (int c = 0; c < k; ++c)
+        for (int u = 0; u < base_units; ++u) place((c == k - 1 ? last : tpc) + fixed);
+      if (small > 0)
+        for (int u = 0; u < base_units; ++u) place(small + fixed);
+      if (best < 0 || makespan < best) { best = makespan; best_k = k; best_small = small; }
+    }
+  }
+  const int big_tiles = n_tiles - best_small;
+  *tiles_per_chunk = (big_tiles + best_k - 1) / best_k;
+  *chunks = best_k + (best_small > 0 ? 1 : 0);
+  *small_tiles = best_small;
+}
+
+static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, int D, int precision);
+
+// The split search costs milliseconds: plans are computed once per shape.
 SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision) {
+  static std::mutex mu;
+  static std::map<std::tuple<int64_t, int64_t, int, int>, SweepPlan> cache;
+  const auto key = std::make_tuple(rows_local, rows_global, D, precision);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const SweepPlan p = plan_sweep_uncached(rows_local, rows_global, D, precision);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, p);
+  return p;
+}
+
+static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, int D, int precision) {
   SweepPlan p{};
   if (precision == VPA_PREC_FP32_SIMT) {
     p.rows_per_blk = 8;
@@ -131,20 +191,22 @@ SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precisi
     p.n_tiles = (int)((rows_global + 255) / 256);
     pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
     // per-unit fixed cost (prologue, X load, pipeline fill, dX drain) measured at ~3.5 tiles of 256 columns (b=4096 sweep)
-    pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
-    p.n_dscale = 2 * p.pair_bwd_iblk * p.bwd_chunks;
+    const bool uneven = !getenv("VPA_EVEN_CHUNKS");                                 // A/B knob: equal chunks only
+    if (uneven) pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small);
+    else pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
     p.fast_fwd = 1;
     if (const char* e = getenv("VPA_FAST_FWD")) p.fast_fwd = atoi(e) != 0;          // A/B knob
-    pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2);
+    if (uneven) pick_split(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, &p.fwd1_small);
+    else pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2);
     p.n_rowgroups = p.pair_fwd_iblk * 8;
-    auto force = [&](const char* name, int* chunks, int* tpc) {     // tuning knobs for measurements
+    auto force = [&](const char* name, int* chunks, int* tpc, int* small) {     // tuning knobs for measurements
       if (const char* e = getenv(name)) {
         const int c = atoi(e);
-        if (c >= 1 && c <= p.n_tiles) { *tpc = (p.n_tiles + c - 1) / c; *chunks = (p.n_tiles + *tpc - 1) / *tpc; }
+        if (c >= 1 && c <= p.n_tiles) { *tpc = (p.n_tiles + c - 1) / c; *chunks = (p.n_tiles + *tpc - 1) / *tpc; *small = 0; }
       }
     };
-    force("VPA_FWD1_CHUNKS", &p.fwd1_chunks, &p.fwd1_tiles_per_chunk);
-    force("VPA_BWD_CHUNKS", &p.bwd_chunks, &p.bwd_tiles_per_chunk);
+    force("VPA_FWD1_CHUNKS", &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, &p.fwd1_small);
+    force("VPA_BWD_CHUNKS", &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small);
     p.n_dscale = 2 * p.pair_bwd_iblk * p.bwd_chunks;
     return p;
   }
@@ -206,6 +268,17 @@ extern "C" {
 int vpa_version(void) { return VPA_VERSION; }
 
 const char* vpa_last_error_string(void) { return g_err; }
+
+// Work decomposition of the sweeps for a shape (diagnostics / tests): out[0..9] = n_tiles, fwd1 chunks, fwd1 tiles per big
+// chunk, fwd1 tail tiles, bwd chunks, bwd tiles per big chunk, bwd tail tiles, fwd1 row blocks, bwd row blocks, impl.
+int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision, int* out10) {
+  VPA_CHECK_ARG(out10 && rows_local > 0 && rows_global >= rows_local && D > 0, "plan_query: bad argument");
+  const SweepPlan p = plan_sweep(rows_local, rows_global, D, precision);
+  const int v[10] = {p.n_tiles, p.fwd1_chunks, p.fwd1_tiles_per_chunk, p.fwd1_small, p.bwd_chunks, p.bwd_tiles_per_chunk,
+                     p.bwd_small, p.pair_fwd_iblk, p.pair_bwd_iblk, p.impl};
+  for (int i = 0; i < 10; ++i) out10[i] = v[i];
+  return 0;
+}
 
 int vpa_profile_enable(int on) {
   g_prof.on = on != 0;

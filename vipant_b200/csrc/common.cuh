@@ -132,6 +132,7 @@ struct SweepPlan {
   int pair_bwd_iblk;
   int fast_fwd;             // pair kernels: the single-pass forward (one S sweep, both statistics) is available
   int fwd1_chunks, fwd1_tiles_per_chunk;
+  int bwd_small, fwd1_small;   // pair kernels: tiles of the short tail chunk of every row block (0: equal chunks only)
   int n_rowgroups;          // single-pass forward: 32-row groups of column partial sums (8 per 256-row block)
 };
 constexpr int kColSumSplit = 8;   // column sums are reduced to [kColSumSplit][rows_global] (fixed order) before any all-reduce

@@ -52,6 +52,10 @@ struct Params {
   Problem p[2];
   int pairs_per_problem;    // n_iblk * n_chunks
   int n_iblk, n_chunks, tiles_per_chunk, n_tiles;
+  // Every X row block is swept by n_big equal chunks of tiles_per_chunk tiles plus (small_tiles > 0) one short tail chunk.
+  // All big units come first in the grid (both problems), the tails last: CTAs are dispatched in blockIdx order to the
+  // first free SM pair, so the tails fill the slots a single wave of big units leaves idle (LPT scheduling; api.cu).
+  int n_big, small_tiles, n_prob;
   int D, kboxes, nblk;      // kboxes = D / 64; nblk = D / 256 accumulator blocks (BWD)
   const float* logit_scale;
   float scale_cap;
@@ -237,31 +241,60 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const bool is_leader = crank == 0;
 
   int u = blockIdx.x >> 1;                             // pair index
-  const int prob = u >= P.pairs_per_problem;
-  u -= prob * P.pairs_per_problem;
-  const int chunk = u / P.n_iblk;
-  const int iblk = u - chunk * P.n_iblk;
+  int prob_, chunk_, iblk_, tile0_, nt_;
+  {
+    const int per = P.n_iblk * P.n_big, big_units = P.n_prob * per;
+    if (u < big_units) {
+      prob_ = u >= per;
+      u -= prob_ * per;
+      chunk_ = u / P.n_iblk;
+      iblk_ = u - chunk_ * P.n_iblk;
+      tile0_ = chunk_ * P.tiles_per_chunk;
+      nt_ = min(P.tiles_per_chunk, (P.n_tiles - P.small_tiles) - tile0_);
+    } else {
+      u -= big_units;
+      prob_ = u >= P.n_iblk;
+      iblk_ = u - prob_ * P.n_iblk;
+      chunk_ = P.n_big;
+      tile0_ = P.n_tiles - P.small_tiles;
+      nt_ = P.small_tiles;
+    }
+  }
+  const int prob = prob_, chunk = chunk_, iblk = iblk_, tile0 = tile0_, nt = nt_;
   const Problem& pb = P.p[prob];
   const CUtensorMap* mapx = prob ? &mx1 : &mx0;
   const CUtensorMap* mapy = prob ? &my1 : &my0;
-  const int tile0 = chunk * P.tiles_per_chunk;
-  const int nt = min(P.tiles_per_chunk, P.n_tiles - tile0);
   const int row0 = iblk * C::RP + (int)crank * C::RC;   // first local X row of this CTA
   // Order in which this CTA visits its tiles.  Over peer memory (single-pass forward) the rows of every peer block
-  // arrive chunk by chunk, all blocks at the same pace: a CTA whose range spans several whole rank blocks visits them
+  // arrive chunk by chunk, all blocks at the same pace: a CTA whose range touches several rank blocks visits it
   // chunk-major (chunk 0 of each block, chunk 1 of each block, ...) instead of one block after the other, so it never
-  // needs the LAST chunk of one peer before the first of the next.
-  int ilv_nb = 1, ilv_cpr = 1;
-  if (MODE == MODE_FWD1 && P.yflags.flags != nullptr && P.yflags.rows_per_rank % kBN == 0) {
-    const int cpr = P.yflags.chunks_per_rank;
-    if (tile0 % cpr == 0 && nt % cpr == 0 && nt / cpr > 1) { ilv_nb = nt / cpr; ilv_cpr = cpr; }
-  }
-  auto tile_at = [&](int j) {
-    if (ilv_nb == 1) return tile0 + j;
-    const int c = j / ilv_nb;
-    return tile0 + (j - c * ilv_nb) * ilv_cpr + c;
+  // needs the LAST chunk of one peer before the first of the next.  Producer and epilogue run the same iterator.
+  struct TileOrder {
+    int cpr, blk0, blk1, lo, hi, c, blk, lin;      // cpr == 0: ascending
+    __device__ int first() {
+      if (cpr == 0) return lin;
+      c = 0; blk = blk0 - 1;
+      return next();
+    }
+    __device__ int next() {
+      if (cpr == 0) return ++lin;
+      while (true) {
+        if (++blk > blk1) { blk = blk0; ++c; }
+        const int t = blk * cpr + c;
+        if (t >= lo && t < hi) return t;
+      }
+    }
   };
-
+  auto make_order = [&]() {
+    TileOrder o{};
+    o.cpr = 0; o.lin = tile0; o.lo = tile0; o.hi = tile0 + nt;
+    if (MODE == MODE_FWD1 && P.yflags.flags != nullptr && P.yflags.rows_per_rank % kBN == 0) {
+      const int cpr = P.yflags.chunks_per_rank;
+      const int b0 = tile0 / cpr, b1 = (tile0 + nt - 1) / cpr;
+      if (b1 > b0) { o.cpr = cpr; o.blk0 = b0; o.blk1 = b1; }
+    }
+    return o;
+  };
   const uint32_t bar0 = sbase + L.bars;
   auto bar = [&](int i) { return bar0 + 8u * i; };
   auto lbar = [&](int i) { return mapa(bar0 + 8u * i, 0); };      // the leader's copy (cluster address)
@@ -320,8 +353,10 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
           push(d0, d0 + 64, (tile0 + t) * kBN + jh * 128);
         }
     };
-    for (int j = 0; j < nt; ++j) {
-      const int r = tile_at(j) * kBN + (int)crank * 128;       // this CTA's half of the tile's Y rows
+    TileOrder order = make_order();
+    int tcur = order.first();
+    for (int j = 0; j < nt; ++j, tcur = (j < nt) ? order.next() : tcur) {
+      const int r = tcur * kBN + (int)crank * 128;             // this CTA's half of the tile's Y rows
       if (MODE == MODE_FWD1 && P.yflags.flags != nullptr) {
         // peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cu).  Poll the
         // chunk flags (system-scope acquire), then order the TMA (async proxy) reads after the observation.
@@ -464,11 +499,13 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       const float s2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
       float* cp = P.colpart + (int64_t)(iblk * 8 + (int)crank * 4 + sub) * pb.n_y;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      for (int j = 0; j < nt; ++j) {
+      TileOrder order = make_order();
+      int tcur = order.first();
+      for (int j = 0; j < nt; ++j, tcur = (j < nt) ? order.next() : tcur) {
         const int b = j & 1;
         mbar_wait(bar(B_TFULL0 + b), (j >> 1) & 1);
         tc_fence_after();
-        const int col0 = tile_at(j) * kBN;
+        const int col0 = tcur * kBN;
         const bool full = rows_full && (col0 + kBN <= pb.n_y);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
@@ -628,7 +665,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
         if (lane == 0) red[warp - 2] = v;
         epi_bar_sync<256>();
         if (etb == 0)
-          pb.dscale[blockIdx.x - prob * 2 * P.pairs_per_problem] =
+          pb.dscale[(chunk * P.n_iblk + iblk) * 2 + (int)crank] =
               ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
       }
     }
@@ -695,6 +732,9 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.tiles_per_chunk = bwd ? plan.bwd_tiles_per_chunk : (fwd1 ? plan.fwd1_tiles_per_chunk : plan.fwd_tiles_per_chunk);
   P.n_tiles = plan.n_tiles;
   P.pairs_per_problem = P.n_iblk * P.n_chunks;
+  P.small_tiles = bwd ? plan.bwd_small : (fwd1 ? plan.fwd1_small : 0);
+  P.n_big = P.n_chunks - (P.small_tiles > 0 ? 1 : 0);
+  P.n_prob = fwd1 ? 1 : 2;
   P.D = a.D;
   P.kboxes = a.D / 64;
   P.nblk = a.D / 256;

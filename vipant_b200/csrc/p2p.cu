@@ -77,7 +77,11 @@ struct P2PHandle {
   cudaEvent_t fork = nullptr, join = nullptr;
   bool join_pending = false;
   int push_groups = 8, push_ctas = 4, push_rounds = 8;
-  int pull = 1, pull_ctas = 64;
+  int pull = 1, pull_ctas = 64;      // pull: 0 = push kernel, 1 = pull kernel, 2 = copy engines
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ready_ev = nullptr, join2 = nullptr;
+  int ce_streams = 2;
+  size_t ce_bytes = 4u << 20;
 };
 
 // ---------------------------------------------------------------- kernels
@@ -201,6 +205,23 @@ __global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
   }
 }
 
+// ---- operands by the COPY ENGINES: no SM, no issue slots and no L2->SM bandwidth taken from the sweep that runs meanwhile --
+// signal "my rows are complete" to every peer / wait for every peer's signal / publish the chunks a finished copy delivered
+__global__ void p2p_signal_ready_kernel(const P2PView v, size_t off_ready) {
+  const int q = threadIdx.x;
+  if (q < v.world && q != v.rank) {
+    __threadfence_system();
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(v.base[q] + off_ready) + v.rank, v.epoch);
+  }
+}
+__global__ void p2p_wait_ready_kernel(const uint32_t* __restrict__ ready, int world, int me, uint32_t epoch) {
+  const int q = threadIdx.x;
+  if (q < world && q != me) p2p_wait_ge(ready + q, epoch);
+}
+__global__ void p2p_set_flags_kernel(uint32_t* flags, int n, uint32_t epoch) {
+  if ((int)threadIdx.x < n) st_release_sys_u32(flags + threadIdx.x, epoch);
+}
+
 // every operand chunk of every peer has landed (both matrices): what all later kernels of the step rely on
 // gate_scale != nullptr: only in the exact two-sweep regime (s * log2e > limit, decided on the device like the sweeps do);
 // the single-pass forward has consumed every x2-operand chunk itself and reads no x1 operands of the peers.
@@ -275,7 +296,12 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
-  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") != 0;
+  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : 1);
+  if (const char* s = getenv("VPA_P2P_CE_STREAMS")) { const int v = atoi(s); if (v == 1 || v == 2) h->ce_streams = v; }
+  if (const char* s = getenv("VPA_P2P_CE_KB")) { const int v = atoi(s); if (v >= 256) h->ce_bytes = (size_t)v << 10; }
+  if ((e = cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreateWithFlags(&h->ready_ev, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreateWithFlags(&h->join2, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_PULL_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_ROUNDS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->push_rounds = v; }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
@@ -308,6 +334,9 @@ int p2p_destroy(void* handle) {
     if (h->opened[q]) cudaIpcCloseMemHandle(h->base[q]);
   if (h->base[h->rank]) cudaFree(h->base[h->rank]);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->ready_ev) cudaEventDestroy(h->ready_ev);
+  if (h->join2) cudaEventDestroy(h->join2);
   if (h->fork) cudaEventDestroy(h->fork);
   if (h->join) cudaEventDestroy(h->join);
   delete h;
@@ -385,6 +414,43 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
   A.groups = h->push_groups < 2 * nbatch ? h->push_groups : 2 * nbatch;
   VPA_CUDA(cudaEventRecord(h->fork, st));
   VPA_CUDA(cudaStreamWaitEvent(h->side, h->fork, 0));
+  if (h->pull == 2) {
+    // copy engines: signal / wait readiness once, then one peer-to-local copy per (matrix, peer, <= ce_bytes piece), each
+    // followed by a one-warp kernel that flips the arrival flags of the chunks it delivered.  x2 operands first.
+    char* mine = h->base[h->rank];
+    p2p_signal_ready_kernel<<<1, 32, 0, h->side>>>(A.v, L.ready);
+    p2p_wait_ready_kernel<<<1, 32, 0, h->side>>>(reinterpret_cast<const uint32_t*>(mine + L.ready), h->world, h->rank, epoch);
+    VPA_LAUNCH_CHECK("p2p ready kernels");
+    cudaStream_t ss[2] = {h->side, h->ce_streams == 2 ? h->side2 : h->side};
+    if (h->ce_streams == 2) {
+      VPA_CUDA(cudaEventRecord(h->ready_ev, h->side));
+      VPA_CUDA(cudaStreamWaitEvent(h->side2, h->ready_ev, 0));
+    }
+    prof_begin(PROF_PUSH, h->side);
+    const size_t chunk_bytes = (size_t)kPushRows * A.row_bytes;
+    int per = (int)(h->ce_bytes / chunk_bytes);
+    if (per < 1) per = 1;
+    if (per > 32) per = 32;
+    int n = 0;
+    for (int m = 0; m < 2; ++m)
+      for (int c0 = 0; c0 < L.cpr; c0 += per)
+        for (int q = 1; q < h->world; ++q, ++n) {
+          const int src = (h->rank + q) % h->world;
+          const int c1 = c0 + per < L.cpr ? c0 + per : L.cpr;
+          const int64_t row0 = (int64_t)c0 * kPushRows;
+          const int64_t rows = ((int64_t)c1 * kPushRows < h->b ? (int64_t)c1 * kPushRows : h->b) - row0;
+          const size_t off = A.off_mat[m] + ((size_t)src * h->b + row0) * A.row_bytes;
+          cudaStream_t cs = ss[n & 1];
+          VPA_CUDA(cudaMemcpyAsync(mine + off, h->base[src] + off, (size_t)rows * A.row_bytes, cudaMemcpyDeviceToDevice, cs));
+          p2p_set_flags_kernel<<<1, 32, 0, cs>>>(reinterpret_cast<uint32_t*>(mine + L.flags[m]) + src * L.cpr + c0, c1 - c0, epoch);
+        }
+    VPA_LAUNCH_CHECK("p2p_set_flags_kernel");
+    if (h->ce_streams == 2) {
+      VPA_CUDA(cudaEventRecord(h->join2, h->side2));
+      VPA_CUDA(cudaStreamWaitEvent(h->side, h->join2, 0));
+    }
+    prof_end(PROF_PUSH, h->side);
+  } else {
   prof_begin(PROF_PUSH, h->side);
   if (h->pull) {
     PullArgs G{};
@@ -400,6 +466,7 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
   }
   prof_end(PROF_PUSH, h->side);
   VPA_LAUNCH_CHECK("p2p_push / p2p_pull kernel");
+  }
   VPA_CUDA(cudaEventRecord(h->join, h->side));
   h->join_pending = true;
   return 0;

@@ -189,6 +189,59 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- small-batch latency (configs[1])
+def c2_latency(lib, dev, iters=300):
+    """BASELINE.json configs[1]: per-GPU batch 512 x 512, bf16 mode.  1 GFLOP -- launch-latency bound, so it is reported in
+    microseconds per fwd+bwd step, eager (two C-ABI calls = 9 kernels) and replayed from a CUDA graph of the same calls."""
+    from vipant_b200 import _cabi
+    B, D, prec = 512, 512, _cabi.PREC_BF16_TC
+    x1h, x2h = make_inputs(B, D, 0, B)
+    x1, x2 = x1h.to(dev), x2h.to(dev)
+    ls = torch.tensor(math.log(1 / 0.07), device=dev)
+    g = torch.tensor(1.0, device=dev)
+    nbytes = lib.vpa_sharded_state_bytes(B, 1, D, prec)
+    state = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    loss, dls = torch.empty((), device=dev), torch.empty((), device=dev)
+    dx1, dx2 = torch.empty_like(x1), torch.empty_like(x2)
+
+    def enqueue():
+        st = torch.cuda.current_stream().cuda_stream
+        _cabi.check(lib.vpa_infonce_fwd_sharded(None, x1.data_ptr(), x2.data_ptr(), _cabi.F32, B, 1, 0, D, D, D, 0, ls.data_ptr(),
+                                                0.0, prec, state.data_ptr(), nbytes, loss.data_ptr(), st), "fwd")
+        _cabi.check(lib.vpa_infonce_bwd_sharded(None, x1.data_ptr(), x2.data_ptr(), _cabi.F32, B, 1, 0, D, D, D, 0, prec,
+                                                g.data_ptr(), state.data_ptr(), nbytes, dx1.data_ptr(), dx2.data_ptr(),
+                                                dls.data_ptr(), st), "bwd")
+
+    def timed(fn):
+        for _ in range(20):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    out = {"batch": B, "dim": D, "eager_us_per_step": timed(enqueue), "loss": float(loss.item())}
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            enqueue()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            enqueue()
+        out["cuda_graph_us_per_step"] = timed(graph.replay)
+        out["graph_loss"] = float(loss.item())
+    except Exception as exc:          # reported, never fatal for the headline line
+        out["cuda_graph_us_per_step"] = None
+        out["cuda_graph_error"] = str(exc)[:200]
+    return out
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -358,6 +411,11 @@ def main():
             # merge+loss, bwd sweep, finalize (+ operand pull, 2 flag waits, d logit_scale sum on the peer-memory transport)
             "gpu_launches": {"local": 8, "p2p": 11, "nccl": 8, "host": 9}[transport] * args.steps,
         }
+        if world == 1 and not args.no_e2e:
+            try:
+                line["c2_batch512_latency"] = c2_latency(lib, dev)
+            except Exception as exc:
+                line["c2_batch512_latency"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline and world == 1:
             cx1, cx2, cls_, cb, cores = cpu_block_sample(B, D)
             times = run_cpu_steps(cx1, cx2, cls_, cb, 2)

@@ -15,3 +15,4 @@ if [ -n "$NCU" ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_hbm.log 2>&1
 fi
 tail -5 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log
+python scripts/score_bench.py > gpurun_out/scoring.json 2> gpurun_out/scoring.err; echo "score_bench exit $?"

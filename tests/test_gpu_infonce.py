@@ -149,6 +149,29 @@ def test_full_size_against_eager_formula():
     assert abs(dls - ls.grad.item()) <= 1e-2 * max(abs(ls.grad.item()), 1e-3)
 
 
+def test_full_size_invariants():
+    """B = 32768 x 512 (BASELINE.json's size) through size-independent properties of the symmetric InfoNCE:
+    swapping the modalities keeps the loss and swaps the gradients; permuting the pairs jointly permutes the gradients;
+    every gradient row is orthogonal to its input row (normalisation Jacobian); rescaling a modality leaves the loss
+    unchanged and divides its gradient."""
+    B, D = 32768, 512
+    x1n, x2n = io.make_pair(B, D, 0.3, 99)
+    loss, dx1, dx2, dls = run(x1n, x2n, "bf16")
+    loss_s, dx1_s, dx2_s, dls_s = run(x2n, x1n, "bf16")
+    assert abs(loss - loss_s) <= 1e-5 * abs(loss) and abs(dls - dls_s) <= 1e-3 * abs(dls)
+    assert rel(dx1_s, dx2) <= 1e-3 and rel(dx2_s, dx1) <= 1e-3
+    perm = np.random.default_rng(5).permutation(B)
+    loss_p, dx1_p, dx2_p, dls_p = run(np.ascontiguousarray(x1n[perm]), np.ascontiguousarray(x2n[perm]), "bf16")
+    assert abs(loss - loss_p) <= 1e-5 * abs(loss) and abs(dls - dls_p) <= 1e-3 * abs(dls)
+    assert rel(dx1_p, dx1[perm]) <= 1e-3 and rel(dx2_p, dx2[perm]) <= 1e-3
+    for dx, x in ((dx1, x1n), (dx2, x2n)):
+        dots = np.abs(np.einsum("ij,ij->i", dx.astype(np.float64), x.astype(np.float64)))
+        bound = np.linalg.norm(dx, axis=1).astype(np.float64) * np.linalg.norm(x, axis=1)
+        assert np.all(dots <= 1e-4 * bound + 1e-12)
+    loss_c, dx1_c, _, _ = run(np.ascontiguousarray(4.0 * x1n), x2n, "bf16")      # power of two: the bf16 operands are identical
+    assert abs(loss - loss_c) <= 1e-6 * abs(loss) and rel(4.0 * dx1_c, dx1) <= 1e-5
+
+
 def test_row_shard_offsets_single_gpu():
     """The multi-GPU decomposition on one device: four row shards against the gathered matrices reproduce the
     single-shot statistics and gradients (C-ABI row_offset / rows_local / rows_global contract)."""

@@ -318,7 +318,8 @@ _P2P = {}
 
 def _get_p2p(group, b, D, precision, dev):
     """Symmetric segment of the library for (group, shape): created once; the 64-byte CUDA IPC handles are exchanged with
-    torch.distributed (any backend: object all-gather), then every rank maps its peers' segments."""
+    torch.distributed (any backend: object all-gather), then every rank maps its peers' segments.  Returns None when some
+    rank cannot set it up (no peer access / IPC): the ranks agree on that and the caller uses the NCCL transport."""
     key = (id(group), b, D, precision, dev.index)
     if key in _P2P:
         return _P2P[key]
@@ -326,22 +327,39 @@ def _get_p2p(group, b, D, precision, dev):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     handle = ctypes.c_void_p()
     mine = ctypes.create_string_buffer(64)
-    _cabi.check(lib.vpa_p2p_create(b, world, rank, D, precision, ctypes.byref(handle), mine), "vpa_p2p_create")
+    rc = lib.vpa_p2p_create(b, world, rank, D, precision, ctypes.byref(handle), mine)
+    err = "" if rc == 0 else (lib.vpa_last_error_string() or b"").decode()
     everyone = [None] * world
-    dist.all_gather_object(everyone, bytes(mine.raw), group=group)
-    _cabi.check(lib.vpa_p2p_connect(handle, b"".join(everyone)), "vpa_p2p_connect")
-    dist.barrier(group=group)            # every rank has mapped every segment before anyone stores into a peer
+    dist.all_gather_object(everyone, (rc, bytes(mine.raw)), group=group)
+    ok = all(r == 0 for r, _ in everyone)
+    if ok:
+        rc = lib.vpa_p2p_connect(handle, b"".join(h for _, h in everyone))
+        err = "" if rc == 0 else (lib.vpa_last_error_string() or b"").decode()
+    status = [None] * world
+    dist.all_gather_object(status, rc if ok else 1, group=group)    # also: nobody stores into a peer before all have mapped
+    if not all(r == 0 for r in status):
+        if handle:
+            lib.vpa_p2p_destroy(handle)
+        import warnings
+        warnings.warn(f"vipant_b200: peer-memory transport unavailable on rank {rank} ({err or 'a peer failed'}); using NCCL")
+        _P2P[key] = None
+        return None
     _P2P[key] = (handle, rank, world)
-    if len(_P2P) == 1:
+    if not _P2P_ATEXIT:
         import atexit
         atexit.register(_destroy_p2p)
+        _P2P_ATEXIT.append(True)
     return _P2P[key]
+
+
+_P2P_ATEXIT = []
 
 
 def _destroy_p2p():
     lib = _cabi.lib()
-    for handle, _, _ in _P2P.values():
-        lib.vpa_p2p_destroy(handle)
+    for entry in _P2P.values():
+        if entry is not None:
+            lib.vpa_p2p_destroy(entry[0])
     _P2P.clear()
 
 
@@ -436,6 +454,10 @@ def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, 
     transport = _transport(group)
     if transport == "local":
         group = None
+    if transport == "p2p":
+        with torch.cuda.device(x1.device):
+            if _get_p2p(group, x1.shape[0], x1.shape[1], prec, x1.device) is None:
+                transport = "nccl" if dist.get_backend(group) == "nccl" else "host"
     fn = {"local": _FusedStep, "nccl": _FusedStep, "p2p": _P2PStep, "host": _InfoNCEFunction}[transport]
     return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group)
 

@@ -43,8 +43,14 @@ def _worker(rank, world, port, B, D, precision, transport, shared_device, steps,
         x1 = torch.from_numpy(x1n[rank * b:(rank + 1) * b]).cuda().requires_grad_(True)
         x2 = torch.from_numpy(x2n[rank * b:(rank + 1) * b]).cuda().requires_grad_(True)
         ls = torch.tensor(lsv, device="cuda", requires_grad=True)
-        for _ in range(steps):       # several steps: epochs, buffer parity and flag reuse of the peer-memory transport
+        gen = torch.Generator(device="cuda").manual_seed(100 + rank)
+        for i in range(steps):       # several steps: epochs, buffer parity and flag reuse of the peer-memory transport
             x1.grad = x2.grad = ls.grad = None
+            if i < steps - 1:        # different data on the earlier steps: a stale operand / message buffer would show
+                y1 = (x1.detach() + torch.randn(x1.shape, device="cuda", generator=gen)).requires_grad_(True)
+                y2 = (x2.detach() + torch.randn(x2.shape, device="cuda", generator=gen)).requires_grad_(True)
+                vb.infonce_loss(y1, y2, ls, precision=precision, group=dist.group.WORLD).backward()
+                continue
             loss = vb.infonce_loss(x1, x2, ls, precision=precision, group=dist.group.WORLD)
             (loss * 3.0).backward()
         torch.cuda.synchronize()
@@ -103,5 +109,5 @@ def test_sharded_matches_global_batch(precision, B, D, transport):
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, transport, False, 2, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), B, D, precision, transport, False, 4, out), nprocs=world, join=True)
     _check(out, world, B, D, precision)

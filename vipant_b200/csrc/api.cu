@@ -642,6 +642,7 @@ int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype,
   const bool from_colpart = pack_reduces_columns(plan, precision);
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
                              h.colsum8, true, 1, st, &h.yflags, !from_colpart)) return e;
+  if (int e = p2p_pull_rest(p2p, epoch, st)) return e;          // (serial plan only: x1 operands after the forward sweep)
   // The exact two-sweep kernel (other regime) also reads the peers' x1 operands: wait for everything, but only then.  In
   // the single-pass regime nothing of the forward needs them -- their transfer keeps overlapping the statistics exchange
   // and the backward waits for it.

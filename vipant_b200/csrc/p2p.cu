@@ -81,6 +81,9 @@ struct P2PHandle {
   cudaStream_t side2 = nullptr;
   cudaEvent_t ready_ev = nullptr, join2 = nullptr;
   int ce_streams = 2;
+  int strong_ld = 1;        // system-scope relaxed loads of peer rows (VPA_P2P_PULL_LD=weak: L1::no_allocate weak loads, same speed at N=2)
+  int serial = 0, pull_ctas_alone = 148;    // serial plan: x2 operands alone before the forward, x1 operands after it
+  cudaEvent_t t_done = nullptr, fwd_done = nullptr;
   size_t ce_bytes = 4u << 20;
 };
 
@@ -154,27 +157,37 @@ struct PullArgs {
   size_t off_mat[2], off_flags[2], off_ready;
   int64_t b;
   int row_bytes, cpr;
+  int m0, m1;               // matrices [m0, m1) of {0: x2 operands, 1: x1 operands}; the ready signal goes out with m0 == 0
 };
 constexpr int kPullUnroll = 8;
 
-__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {      // L1 must not serve a line cached two steps ago
+// Loads of peer rows.  Peer addresses bypass the local L2 and are cached by the local L1 only (B300_MICROARCH.md).
+// STRONG = 1 (default): system-scope relaxed loads, never served by L1 -- a line cached two steps ago (same buffer parity)
+// cannot come back.  STRONG = 0: weak loads that do not allocate in L1 (every address is read once per kernel and L1 is
+// invalidated at kernel boundaries); measured equally fast at N = 2 (72 vs 76 us for 32 MiB), kept for A/B.
+template <int STRONG>
+__device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {
   uint4 v;
-  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  if (STRONG)
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  else
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 
+template <int STRONG>
 __global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
   const int me = A.v.rank, world = A.v.world;
   char* mine = A.v.base[me];
-  if (blockIdx.x == 0 && (int)threadIdx.x < world && (int)threadIdx.x != me) {
+  if (A.m0 == 0 && blockIdx.x == 0 && (int)threadIdx.x < world && (int)threadIdx.x != me) {
     // the normalise kernel that wrote this rank's rows finished before this kernel started (stream order)
     __threadfence_system();
     st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[threadIdx.x] + A.off_ready) + me, A.v.epoch);
   }
   const uint32_t* ready = reinterpret_cast<const uint32_t*>(mine + A.off_ready);
-  const int per_m = (world - 1) * A.cpr, total = 2 * per_m;
+  const int per_m = (world - 1) * A.cpr, total = (A.m1 - A.m0) * per_m;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int m = item / per_m, r = item - m * per_m;
+    const int m = A.m0 + item / per_m, r = item % per_m;
     const int c = r / (world - 1), q = r - c * (world - 1) + 1;
     const int src = (me + q) % world;
     if (threadIdx.x == 0) p2p_wait_ge(ready + src, A.v.epoch);
@@ -185,18 +198,26 @@ __global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
     const size_t off = A.off_mat[m] + ((size_t)src * A.b + row0) * A.row_bytes;
     const uint4* from = reinterpret_cast<const uint4*>(A.v.base[src] + off);
     uint4* to = reinterpret_cast<uint4*>(mine + off);
-    for (int i = threadIdx.x; i < n16; i += 256 * kPullUnroll) {
-      uint4 val[kPullUnroll];
+    // software pipeline: the loads of batch k+1 are in flight while batch k is stored (2 x 8 x 16 B per thread outstanding)
+    constexpr int kStride = 256 * kPullUnroll;
+    uint4 cur[kPullUnroll], nxt[kPullUnroll];
+    auto load = [&](uint4 (&v)[kPullUnroll], int i0) {
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i0 + u * 256;
+        if (idx < n16) v[u] = ld_peer_v4<STRONG>(from + idx);
+      }
+    };
+    load(cur, threadIdx.x);
+    for (int i = threadIdx.x; i < n16; i += kStride) {
+      if (i + kStride < n16) load(nxt, i + kStride);
 #pragma unroll
       for (int u = 0; u < kPullUnroll; ++u) {
         const int idx = i + u * 256;
-        if (idx < n16) val[u] = ld_peer_v4(from + idx);
+        if (idx < n16) to[idx] = cur[u];
       }
 #pragma unroll
-      for (int u = 0; u < kPullUnroll; ++u) {
-        const int idx = i + u * 256;
-        if (idx < n16) to[idx] = val[u];
-      }
+      for (int u = 0; u < kPullUnroll; ++u) cur[u] = nxt[u];
     }
     __threadfence();
     __syncthreads();
@@ -297,6 +318,11 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
   if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : 1);
+  if (const char* s = getenv("VPA_P2P_PULL_LD")) h->strong_ld = strcmp(s, "weak") != 0;
+  if (const char* s = getenv("VPA_P2P_PLAN")) h->serial = strcmp(s, "serial") == 0;
+  if (const char* s = getenv("VPA_P2P_PULL_CTAS_ALONE")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas_alone = v; }
+  if ((e = cudaEventCreateWithFlags(&h->t_done, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreateWithFlags(&h->fwd_done, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_CE_STREAMS")) { const int v = atoi(s); if (v == 1 || v == 2) h->ce_streams = v; }
   if (const char* s = getenv("VPA_P2P_CE_KB")) { const int v = atoi(s); if (v >= 256) h->ce_bytes = (size_t)v << 10; }
   if ((e = cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
@@ -336,6 +362,8 @@ int p2p_destroy(void* handle) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
   if (h->ready_ev) cudaEventDestroy(h->ready_ev);
+  if (h->t_done) cudaEventDestroy(h->t_done);
+  if (h->fwd_done) cudaEventDestroy(h->fwd_done);
   if (h->join2) cudaEventDestroy(h->join2);
   if (h->fork) cudaEventDestroy(h->fork);
   if (h->join) cudaEventDestroy(h->join);
@@ -459,14 +487,46 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
     G.off_flags[0] = A.off_flags[0]; G.off_flags[1] = A.off_flags[1];
     G.off_ready = L.ready;
     G.b = h->b; G.row_bytes = A.row_bytes; G.cpr = L.cpr;
-    const int items = 2 * (h->world - 1) * L.cpr;
-    p2p_pull_kernel<<<items < h->pull_ctas ? items : h->pull_ctas, 256, 0, h->side>>>(G);
+    const bool serial = h->serial && h->pull == 1;
+    G.m0 = 0; G.m1 = serial ? 1 : 2;
+    const int items = (G.m1 - G.m0) * (h->world - 1) * L.cpr;
+    const int ctas = serial ? h->pull_ctas_alone : h->pull_ctas;
+    if (h->strong_ld) p2p_pull_kernel<1><<<items < ctas ? items : ctas, 256, 0, h->side>>>(G);
+    else p2p_pull_kernel<0><<<items < ctas ? items : ctas, 256, 0, h->side>>>(G);
+    if (serial) {      // the forward starts when all x2 operands are here: the transfer has the fabric and the L2s to itself
+      VPA_CUDA(cudaEventRecord(h->t_done, h->side));
+      VPA_CUDA(cudaStreamWaitEvent(st, h->t_done, 0));
+    }
   } else {
     p2p_push_kernel<<<A.groups * A.ctas_per_group, 256, 0, h->side>>>(A);
   }
   prof_end(PROF_PUSH, h->side);
   VPA_LAUNCH_CHECK("p2p_push / p2p_pull kernel");
   }
+  VPA_CUDA(cudaEventRecord(h->join, h->side));
+  h->join_pending = true;
+  return 0;
+}
+
+// serial plan: the x1 operands (read by the backward only) move once the forward sweep on `st` has finished
+int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  if (!(h->serial && h->pull == 1)) return 0;
+  const SegLayout& L = h->L;
+  const int p = (int)(epoch & 1u);
+  PullArgs G{};
+  G.v = make_view(h, epoch);
+  G.off_mat[0] = L.mat[p][0]; G.off_mat[1] = L.mat[p][1];
+  G.off_flags[0] = L.flags[0]; G.off_flags[1] = L.flags[1];
+  G.off_ready = L.ready;
+  G.b = h->b; G.row_bytes = h->D * (h->precision == VPA_PREC_BF16_TC ? 2 : 4); G.cpr = L.cpr;
+  G.m0 = 1; G.m1 = 2;
+  VPA_CUDA(cudaEventRecord(h->fwd_done, st));
+  VPA_CUDA(cudaStreamWaitEvent(h->side, h->fwd_done, 0));
+  const int items = (h->world - 1) * L.cpr;
+  if (h->strong_ld) p2p_pull_kernel<1><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, 256, 0, h->side>>>(G);
+  else p2p_pull_kernel<0><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, 256, 0, h->side>>>(G);
+  VPA_LAUNCH_CHECK("p2p_pull_kernel");
   VPA_CUDA(cudaEventRecord(h->join, h->side));
   h->join_pending = true;
   return 0;

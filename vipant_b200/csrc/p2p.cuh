@@ -99,6 +99,7 @@ uint32_t p2p_next_epoch(void* handle);
 uint32_t p2p_current_epoch(void* handle);
 P2PStep p2p_step(void* handle, uint32_t epoch);
 int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st);
+int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st);
 int p2p_join_push(void* handle, cudaStream_t st);
 int p2p_wait_operands(void* handle, uint32_t epoch, const float* gate_scale, float scale_cap, cudaStream_t st);
 int p2p_dls_sum(const P2PStep& s, float* dlogit_scale, cudaStream_t st);

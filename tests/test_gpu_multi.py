@@ -86,12 +86,15 @@ def _check(out, world, B, D, precision, env=None):
 
 
 # env: VPA_FWD1_CHUNKS=1 makes one CTA pair sweep ALL rank blocks (the chunk-major tile order over several peer blocks);
-# VPA_P2P_MODE=push selects the store-based operand transport instead of the default pull
+# VPA_P2P_MODE=push / stream select the store-based operand transports instead of the default pull; VPA_P2P_PLAN=serial moves
+# the x2 operands before and the x1 operands after the forward sweep instead of overlapping them with it
 @pytest.mark.parametrize("world,precision,B,D,env", [
     (2, "bf16", 1024, 512, None), (2, "bf16", 600, 256, None), (2, "fp32", 256, 128, None),
     (4, "bf16", 2048, 512, {"VPA_FWD1_CHUNKS": "1"}), (3, "bf16", 1152, 512, None),
     (4, "bf16", 4096, 256, {"VPA_FWD1_CHUNKS": "2", "VPA_P2P_MODE": "push"}),
-    (2, "bf16", 1024, 512, {"TEST_SCALE100": "1"})])
+    (2, "bf16", 1024, 512, {"TEST_SCALE100": "1"}),
+    (4, "bf16", 2048, 512, {"VPA_P2P_MODE": "stream", "VPA_FWD1_CHUNKS": "1"}),
+    (2, "bf16", 1024, 512, {"VPA_P2P_PLAN": "serial"})])
 def test_p2p_transport_ranks_sharing_one_gpu(world, precision, B, D, env):
     """The peer-memory transport (CUDA IPC segments, operand transfer + arrival flags consumed by the forward sweep,
     message and d logit_scale exchange by peer stores) between processes that share GPU 0: runs on a single-GPU box."""

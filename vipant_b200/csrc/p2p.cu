@@ -77,7 +77,8 @@ struct P2PHandle {
   cudaEvent_t fork = nullptr, join = nullptr;
   bool join_pending = false;
   int push_groups = 8, push_ctas = 4, push_rounds = 8;
-  int pull = 1, pull_ctas = 64;      // pull: 0 = push kernel, 1 = pull kernel, 2 = copy engines
+  int pull = 1, pull_ctas = 64;      // pull: 0 = push kernel, 1 = pull kernel, 2 = copy engines, 3 = streaming push kernel
+  int stream_ctas = 96;
   cudaStream_t side2 = nullptr;
   cudaEvent_t ready_ev = nullptr, join2 = nullptr;
   int ce_streams = 2;
@@ -226,6 +227,45 @@ __global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
   }
 }
 
+// ---- operands, producer driven, streaming variant (VPA_P2P_MODE=stream): posted stores are not bound by the number of
+// outstanding read requests an SM can hold.  One item = one 256-row chunk to ONE peer, handled by one CTA start to finish:
+// no cross-CTA counters, one system fence per item, then the chunk's arrival flag in that peer.  Items are ordered
+// x2 operands first, chunk-major, peers rotating; CTAs take them round-robin.
+__global__ void __launch_bounds__(128) p2p_stream_push_kernel(const PullArgs A) {
+  const int me = A.v.rank, world = A.v.world;
+  char* mine = A.v.base[me];
+  const int per_m = (world - 1) * A.cpr, total = (A.m1 - A.m0) * per_m;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int m = A.m0 + item / per_m, r = item % per_m;
+    const int c = r / (world - 1), q = r - c * (world - 1) + 1;
+    const int dst = (me + q) % world;
+    const int64_t row0 = (int64_t)c * kPushRows;
+    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
+    const int n16 = rows * (A.row_bytes / 16);
+    const size_t off = A.off_mat[m] + ((size_t)me * A.b + row0) * A.row_bytes;
+    const uint4* from = reinterpret_cast<const uint4*>(mine + off);
+    uint4* to = reinterpret_cast<uint4*>(A.v.base[dst] + off);
+    constexpr int kStride = 128 * kPullUnroll;
+    for (int i = threadIdx.x; i < n16; i += kStride) {
+      uint4 val[kPullUnroll];
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * 128;
+        if (idx < n16) val[u] = __ldg(from + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * 128;
+        if (idx < n16) to[idx] = val[u];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[dst] + A.off_flags[m]) + me * A.cpr + c, A.v.epoch);
+  }
+}
+
 // ---- operands by the COPY ENGINES: no SM, no issue slots and no L2->SM bandwidth taken from the sweep that runs meanwhile --
 // signal "my rows are complete" to every peer / wait for every peer's signal / publish the chunks a finished copy delivered
 __global__ void p2p_signal_ready_kernel(const P2PView v, size_t off_ready) {
@@ -317,7 +357,8 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
-  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : 1);
+  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : (strcmp(s, "stream") == 0 ? 3 : 1));
+  if (const char* s = getenv("VPA_P2P_STREAM_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->stream_ctas = v; }
   if (const char* s = getenv("VPA_P2P_PULL_LD")) h->strong_ld = strcmp(s, "weak") != 0;
   if (const char* s = getenv("VPA_P2P_PLAN")) h->serial = strcmp(s, "serial") == 0;
   if (const char* s = getenv("VPA_P2P_PULL_CTAS_ALONE")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas_alone = v; }
@@ -480,7 +521,17 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
     prof_end(PROF_PUSH, h->side);
   } else {
   prof_begin(PROF_PUSH, h->side);
-  if (h->pull) {
+  if (h->pull == 3) {
+    PullArgs G{};
+    G.v = A.v;
+    G.off_mat[0] = A.off_mat[0]; G.off_mat[1] = A.off_mat[1];
+    G.off_flags[0] = A.off_flags[0]; G.off_flags[1] = A.off_flags[1];
+    G.off_ready = L.ready;
+    G.b = h->b; G.row_bytes = A.row_bytes; G.cpr = L.cpr;
+    G.m0 = 0; G.m1 = 2;
+    const int items = 2 * (h->world - 1) * L.cpr;
+    p2p_stream_push_kernel<<<items < h->stream_ctas ? items : h->stream_ctas, 128, 0, h->side>>>(G);
+  } else if (h->pull) {
     PullArgs G{};
     G.v = A.v;
     G.off_mat[0] = A.off_mat[0]; G.off_mat[1] = A.off_mat[1];

@@ -442,7 +442,6 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     // =========================== epilogue warps (128 threads per CTA) ===========================
     const int sub = warp & 3;                         // TMEM sub-partition (lanes 32*sub .. +32) this warp may access
     const uint32_t t_lane = tmem_base + ((uint32_t)(sub * 32) << 16);
-    const int et = threadIdx.x - 64;                  // 0..127
     if (MODE == MODE_FWD) {
       const int row = row0 + sub * 32 + lane;         // lane = row (128 rows per CTA)
       const bool row_ok = row < pb.n_x;

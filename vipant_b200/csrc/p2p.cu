@@ -1,15 +1,24 @@
 // Peer-memory transport of the row-sharded step: the gathered operand matrices, the per-rank statistics messages and the
 // d logit_scale partials live in a SYMMETRIC segment (same layout on every rank, cudaMalloc + CUDA IPC), and every
-// exchange is a kernel storing straight into the peers' segments over NVLink, published with system-scope epoch flags:
-//   * operands: a push kernel on a side stream copies this rank's normalised rows, 256-row chunk by chunk (x2 operands
-//     first), into all peers; the single-pass forward's TMA producer polls the chunk flags, so the sweep starts on the
-//     local block and consumes remote rows as they land -- the all-gather overlaps the contraction tile by tile;
+// exchange is done by kernels reading / writing the peers' segments over NVLink, published with system-scope epoch flags:
+//   * operands (default: pull): a kernel on a high-priority side stream loads the peers' normalised rows (x2 operands
+//     first, 256-row chunks, chunk-major over the peers) and stores them locally; one local arrival flag per chunk.  The
+//     single-pass forward's TMA producer polls the flag of every tile before loading it, so the sweep starts on the local
+//     block and consumes remote rows as they land -- the all-gather overlaps the contraction tile by tile.  The only remote
+//     store of the pull is one "my rows are complete" flag per peer and step.  Alternatives kept for A/B (VPA_P2P_MODE):
+//     push (stores to all peers + fence.sys per batch), stream (one chunk to one peer per CTA), ce (copy engines);
+//     VPA_P2P_PLAN=serial moves the x2 operands before and the x1 operands after the forward instead of beside it.
 //   * statistics: pack_stats writes its message into every peer, merge_stats waits for the R flags;
 //   * d logit_scale: finalize_bwd stores {epoch, partial} into every peer's slot, a one-warp kernel sums them in rank order
 //     (bitwise identical on every rank).
-// No NCCL call on the data path.  Buffers are double-buffered by step parity: a rank can run at most one step ahead of a
-// peer (its step k+1 push needs the peer's step k message, which the peer sends after reading step k's operands), so
-// parity k&1 is never overwritten while a peer's backward of step k-... see DESIGN.md section 4.
+// No NCCL call on the data path.
+//
+// Buffer reuse.  Flags carry the step number (monotonic); operands, messages and slots are double-buffered by step parity.
+// A rank's step k+1 transfer starts after its merge_stats(k), which waited for every peer's message(k), which a peer sends
+// after its forward sweep(k) and after everything it enqueued before that -- in particular its backward(k-1).  Hence when
+// parity (k+1)&1 is overwritten (it last held step k-1), no peer can still be reading step k-1, and nobody can be more
+// than one step ahead of anybody else.  The segment therefore keeps exactly two steps; vpa_infonce_bwd_p2p refuses older
+// ones.  Every spin is bounded (8 s of %globaltimer) and traps: a missing peer is an error on the stream, not a hang.
 #include "p2p.cuh"
 
 #include <cstring>

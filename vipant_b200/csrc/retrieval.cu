@@ -10,7 +10,6 @@
 
 namespace vpa {
 
-constexpr int kSimRB = 8;
 constexpr int kSimThreads = 256;
 constexpr int kMaxGt = 8;
 

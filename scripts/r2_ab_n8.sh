@@ -1,0 +1,8 @@
+#!/bin/bash
+# Round-2 first visit (8 GPUs): A/B of the operand transfer variants at N = 8, B = 32768 x 512.
+#   gpurun --gpus 8 --timeout 600 -- 'bash scripts/r2_ab_n8.sh'
+N=8 CONFIGS="VIPANT_TRANSPORT=p2p
+VIPANT_TRANSPORT=p2p VPA_P2P_MODE=stream VPA_P2P_STREAM_CTAS=64
+VIPANT_TRANSPORT=p2p VPA_P2P_MODE=stream VPA_P2P_STREAM_CTAS=128
+VIPANT_TRANSPORT=p2p VPA_P2P_PULL_CTAS=148 VPA_P2P_PULL_THREADS=128
+VIPANT_TRANSPORT=p2p VPA_P2P_PLAN=serial" bash scripts/gpu_p2p8.sh

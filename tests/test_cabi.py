@@ -101,3 +101,52 @@ def test_sweep_plan_covers_every_tile(b, B):
         big_tiles = n_tiles - small
         assert n_big >= 1 and 0 <= small < max(tpc, 1) + (small == 0)
         assert (n_big - 1) * tpc < big_tiles <= n_big * tpc          # no empty chunk, nothing left over
+
+
+def test_peer_memory_entry_points_reject_bad_arguments(lib):
+    """The vpa_p2p_* surface validates before it touches the device: world range, null handles, stale steps."""
+    handle = ctypes.c_void_p()
+    ipc = ctypes.create_string_buffer(64)
+    assert lib.vpa_p2p_create(512, 1, 0, 512, 0, ctypes.byref(handle), ipc) == -1        # needs >= 2 ranks
+    assert b"world" in lib.vpa_last_error_string()
+    assert lib.vpa_p2p_create(512, 9, 0, 512, 0, ctypes.byref(handle), ipc) == -1        # one NVSwitch node: <= 8
+    assert lib.vpa_p2p_create(512, 4, 4, 512, 0, ctypes.byref(handle), ipc) == -1        # rank out of range
+    assert lib.vpa_p2p_create(512, 2, 0, 96, 0, ctypes.byref(handle), ipc) == -3         # D not covered by the tensor-core tiling
+    assert lib.vpa_p2p_connect(None, ipc) == -1
+    assert lib.vpa_p2p_destroy(None) == 0
+    one = ctypes.c_float(0.0)
+    p = ctypes.addressof(one)
+    epoch = ctypes.c_uint32()
+    assert lib.vpa_infonce_fwd_p2p(None, p, p, 0, 512, 2, 0, 512, 512, 512, 0, p, 0.0, 0, p, ctypes.byref(epoch), None) == -1
+    assert lib.vpa_infonce_bwd_p2p(None, 1, p, p, 0, 512, 2, 0, 512, 512, 512, 0, 0, p, p, p, p, None) == -1
+
+
+def test_transport_selection(monkeypatch):
+    """functional._transport: one GPU -> local; a process group of <= 8 ranks -> peer memory unless overridden."""
+    from vipant_b200 import functional as F_
+
+    class FakeDist:
+        def __init__(self, world, backend):
+            self.world, self.backend = world, backend
+
+        def get_world_size(self, group=None):
+            return self.world
+
+        def get_backend(self, group=None):
+            return self.backend
+    monkeypatch.delenv("VIPANT_TRANSPORT", raising=False)
+    monkeypatch.delenv("VIPANT_HOST_ORCHESTRATION", raising=False)
+    assert F_._transport(None) == "local"
+    monkeypatch.setattr(F_, "dist", FakeDist(1, "nccl"))
+    assert F_._transport(object()) == "local"
+    monkeypatch.setattr(F_, "dist", FakeDist(8, "nccl"))
+    assert F_._transport(object()) == "p2p"
+    monkeypatch.setattr(F_, "dist", FakeDist(16, "nccl"))
+    assert F_._transport(object()) == "nccl"
+    monkeypatch.setattr(F_, "dist", FakeDist(16, "gloo"))
+    assert F_._transport(object()) == "host"
+    monkeypatch.setattr(F_, "dist", FakeDist(4, "nccl"))
+    monkeypatch.setenv("VIPANT_TRANSPORT", "nccl")
+    assert F_._transport(object()) == "nccl"
+    monkeypatch.setenv("VIPANT_HOST_ORCHESTRATION", "1")
+    assert F_._transport(object()) == "host"

@@ -91,6 +91,7 @@ struct P2PHandle {
   cudaStream_t side2 = nullptr;
   cudaEvent_t ready_ev = nullptr, join2 = nullptr;
   int ce_streams = 2;
+  int pull_threads = 256;   // threads per pull CTA (VPA_P2P_PULL_THREADS: lighter CTAs when many SMs pull)
   int strong_ld = 1;        // system-scope relaxed loads of peer rows (VPA_P2P_PULL_LD=weak: L1::no_allocate weak loads, same speed at N=2)
   int serial = 0, pull_ctas_alone = 148;    // serial plan: x2 operands alone before the forward, x1 operands after it
   cudaEvent_t t_done = nullptr, fwd_done = nullptr;
@@ -209,21 +210,21 @@ __global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
     const uint4* from = reinterpret_cast<const uint4*>(A.v.base[src] + off);
     uint4* to = reinterpret_cast<uint4*>(mine + off);
     // software pipeline: the loads of batch k+1 are in flight while batch k is stored (2 x 8 x 16 B per thread outstanding)
-    constexpr int kStride = 256 * kPullUnroll;
+    const int nthr = blockDim.x, stride = nthr * kPullUnroll;
     uint4 cur[kPullUnroll], nxt[kPullUnroll];
     auto load = [&](uint4 (&v)[kPullUnroll], int i0) {
 #pragma unroll
       for (int u = 0; u < kPullUnroll; ++u) {
-        const int idx = i0 + u * 256;
+        const int idx = i0 + u * nthr;
         if (idx < n16) v[u] = ld_peer_v4<STRONG>(from + idx);
       }
     };
     load(cur, threadIdx.x);
-    for (int i = threadIdx.x; i < n16; i += kStride) {
-      if (i + kStride < n16) load(nxt, i + kStride);
+    for (int i = threadIdx.x; i < n16; i += stride) {
+      if (i + stride < n16) load(nxt, i + stride);
 #pragma unroll
       for (int u = 0; u < kPullUnroll; ++u) {
-        const int idx = i + u * 256;
+        const int idx = i + u * nthr;
         if (idx < n16) to[idx] = cur[u];
       }
 #pragma unroll
@@ -368,6 +369,7 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
   if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : (strcmp(s, "stream") == 0 ? 3 : 1));
   if (const char* s = getenv("VPA_P2P_STREAM_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->stream_ctas = v; }
+  if (const char* s = getenv("VPA_P2P_PULL_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= 256 && v % 32 == 0) h->pull_threads = v; }
   if (const char* s = getenv("VPA_P2P_PULL_LD")) h->strong_ld = strcmp(s, "weak") != 0;
   if (const char* s = getenv("VPA_P2P_PLAN")) h->serial = strcmp(s, "serial") == 0;
   if (const char* s = getenv("VPA_P2P_PULL_CTAS_ALONE")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas_alone = v; }
@@ -551,8 +553,8 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
     G.m0 = 0; G.m1 = serial ? 1 : 2;
     const int items = (G.m1 - G.m0) * (h->world - 1) * L.cpr;
     const int ctas = serial ? h->pull_ctas_alone : h->pull_ctas;
-    if (h->strong_ld) p2p_pull_kernel<1><<<items < ctas ? items : ctas, 256, 0, h->side>>>(G);
-    else p2p_pull_kernel<0><<<items < ctas ? items : ctas, 256, 0, h->side>>>(G);
+    if (h->strong_ld) p2p_pull_kernel<1><<<items < ctas ? items : ctas, h->pull_threads, 0, h->side>>>(G);
+    else p2p_pull_kernel<0><<<items < ctas ? items : ctas, h->pull_threads, 0, h->side>>>(G);
     if (serial) {      // the forward starts when all x2 operands are here: the transfer has the fabric and the L2s to itself
       VPA_CUDA(cudaEventRecord(h->t_done, h->side));
       VPA_CUDA(cudaStreamWaitEvent(st, h->t_done, 0));
@@ -584,8 +586,8 @@ int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st) {
   VPA_CUDA(cudaEventRecord(h->fwd_done, st));
   VPA_CUDA(cudaStreamWaitEvent(h->side, h->fwd_done, 0));
   const int items = (h->world - 1) * L.cpr;
-  if (h->strong_ld) p2p_pull_kernel<1><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, 256, 0, h->side>>>(G);
-  else p2p_pull_kernel<0><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, 256, 0, h->side>>>(G);
+  if (h->strong_ld) p2p_pull_kernel<1><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, h->pull_threads, 0, h->side>>>(G);
+  else p2p_pull_kernel<0><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, h->pull_threads, 0, h->side>>>(G);
   VPA_LAUNCH_CHECK("p2p_pull_kernel");
   VPA_CUDA(cudaEventRecord(h->join, h->side));
   h->join_pending = true;

@@ -796,4 +796,14 @@ int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& p
 }
 float pair_fast_s2_limit() { return pr::kFastS2Limit; }
 
+// registers one resident CTA of the single-pass forward takes (allocation granularity: 8 per thread); 0 if unknown
+int pair_fwd1_regs_per_cta() {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, pr::pair_kernel<pr::MODE_FWD1>) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (fa.numRegs + 7) / 8 * 8 * pr::kThreadsBwd;
+}
+
 }  // namespace vpa

@@ -186,8 +186,11 @@ __device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {
   return v;
 }
 
-template <int STRONG>
-__global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
+// Register budget: a pull CTA must fit beside a resident single-pass forward CTA (320 threads x 104 registers = 33280 of
+// the SM's 65536), or ranks polling for rows could starve the kernels that deliver them: <= 126 registers at 256 threads.
+// __maxnreg__(112) pins that (ptxas -v: 112 registers, no spills).
+template <int STRONG, int THREADS>
+__global__ void __maxnreg__(112) p2p_pull_kernel(const PullArgs A) {
   const int me = A.v.rank, world = A.v.world;
   char* mine = A.v.base[me];
   if (A.m0 == 0 && blockIdx.x == 0 && (int)threadIdx.x < world && (int)threadIdx.x != me) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(256) p2p_pull_kernel(const PullArgs A) {
     const uint4* from = reinterpret_cast<const uint4*>(A.v.base[src] + off);
     uint4* to = reinterpret_cast<uint4*>(mine + off);
     // software pipeline: the loads of batch k+1 are in flight while batch k is stored (2 x 8 x 16 B per thread outstanding)
-    const int nthr = blockDim.x, stride = nthr * kPullUnroll;
+    constexpr int nthr = THREADS, stride = nthr * kPullUnroll;
     uint4 cur[kPullUnroll], nxt[kPullUnroll];
     auto load = [&](uint4 (&v)[kPullUnroll], int i0) {
 #pragma unroll
@@ -337,6 +340,16 @@ static P2PView make_view(const P2PHandle* h, uint32_t epoch) {
   return v;
 }
 
+static void launch_pull(const P2PHandle* h, const PullArgs& G, int ctas) {
+  if (h->pull_threads == 128) {
+    if (h->strong_ld) p2p_pull_kernel<1, 128><<<ctas, 128, 0, h->side>>>(G);
+    else p2p_pull_kernel<0, 128><<<ctas, 128, 0, h->side>>>(G);
+  } else {
+    if (h->strong_ld) p2p_pull_kernel<1, 256><<<ctas, 256, 0, h->side>>>(G);
+    else p2p_pull_kernel<0, 256><<<ctas, 256, 0, h->side>>>(G);
+  }
+}
+
 int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out, void* ipc_handle64) {
   VPA_CHECK_ARG(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "p2p: world must be 2..%d", kMaxPeers);
   VPA_CHECK_ARG(b > 0 && D > 0 && out && ipc_handle64, "p2p_create: bad argument");
@@ -369,7 +382,7 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
   if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : (strcmp(s, "stream") == 0 ? 3 : 1));
   if (const char* s = getenv("VPA_P2P_STREAM_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->stream_ctas = v; }
-  if (const char* s = getenv("VPA_P2P_PULL_THREADS")) { const int v = atoi(s); if (v >= 32 && v <= 256 && v % 32 == 0) h->pull_threads = v; }
+  if (const char* s = getenv("VPA_P2P_PULL_THREADS")) { const int v = atoi(s); if (v == 128 || v == 256) h->pull_threads = v; }
   if (const char* s = getenv("VPA_P2P_PULL_LD")) h->strong_ld = strcmp(s, "weak") != 0;
   if (const char* s = getenv("VPA_P2P_PLAN")) h->serial = strcmp(s, "serial") == 0;
   if (const char* s = getenv("VPA_P2P_PULL_CTAS_ALONE")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas_alone = v; }
@@ -383,6 +396,24 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if (const char* s = getenv("VPA_P2P_PULL_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->pull_ctas = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_ROUNDS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->push_rounds = v; }
   if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail(e, "cudaDeviceSynchronize");
+  {
+    // The pull CTAs must be able to become resident beside the single-pass forward (see p2p_pull_kernel): check the
+    // register budget of THIS build instead of trusting a comment.
+    cudaFuncAttributes fa;
+    const int fwd_regs = pair_fwd1_regs_per_cta();
+    if (fwd_regs > 0 && cudaFuncGetAttributes(&fa, p2p_pull_kernel<1, 256>) == cudaSuccess) {
+      const int pull_regs = (fa.numRegs + 7) / 8 * 8 * 256;
+      if (fwd_regs + pull_regs > 65536) {
+        const int rc = set_error(VPA_E_UNSUPPORTED, "p2p: pull kernel (%d regs/CTA) cannot co-reside with the forward sweep (%d regs/CTA)",
+                                 pull_regs, fwd_regs);
+        cudaFree(h->base[rank]);
+        delete h;
+        return rc;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
   *out = h;
   return 0;
 }
@@ -553,8 +584,7 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
     G.m0 = 0; G.m1 = serial ? 1 : 2;
     const int items = (G.m1 - G.m0) * (h->world - 1) * L.cpr;
     const int ctas = serial ? h->pull_ctas_alone : h->pull_ctas;
-    if (h->strong_ld) p2p_pull_kernel<1><<<items < ctas ? items : ctas, h->pull_threads, 0, h->side>>>(G);
-    else p2p_pull_kernel<0><<<items < ctas ? items : ctas, h->pull_threads, 0, h->side>>>(G);
+    launch_pull(h, G, items < ctas ? items : ctas);
     if (serial) {      // the forward starts when all x2 operands are here: the transfer has the fabric and the L2s to itself
       VPA_CUDA(cudaEventRecord(h->t_done, h->side));
       VPA_CUDA(cudaStreamWaitEvent(st, h->t_done, 0));
@@ -586,8 +616,7 @@ int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st) {
   VPA_CUDA(cudaEventRecord(h->fwd_done, st));
   VPA_CUDA(cudaStreamWaitEvent(h->side, h->fwd_done, 0));
   const int items = (h->world - 1) * L.cpr;
-  if (h->strong_ld) p2p_pull_kernel<1><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, h->pull_threads, 0, h->side>>>(G);
-  else p2p_pull_kernel<0><<<items < h->pull_ctas_alone ? items : h->pull_ctas_alone, h->pull_threads, 0, h->side>>>(G);
+  launch_pull(h, G, items < h->pull_ctas_alone ? items : h->pull_ctas_alone);
   VPA_LAUNCH_CHECK("p2p_pull_kernel");
   VPA_CUDA(cudaEventRecord(h->join, h->side));
   h->join_pending = true;

@@ -6,15 +6,19 @@
         bench.py --gpus N --steps K --warmup W
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
-  normalise+cast both modalities -> [all-gather] -> forward statistics -> loss -> backward (dx1, dx2, dlogit_scale).
+  normalise+cast both modalities -> [operand exchange] -> single-pass forward statistics -> loss -> backward (dx1, dx2,
+  dlogit_scale).
 metric  pairs/s = GLOBAL batch / step time   (strong scaling: the global batch is fixed at 32768, rows are
-        sharded over the N ranks, BASELINE.json configs[2])
+        sharded over the N ranks, BASELINE.json configs[2]); at N > 1 the exchange runs over NVLink peer memory
+        (config.transport = "p2p"; VIPANT_TRANSPORT=nccl|host selects the other transports)
 value   inputs already resident in HBM, CUDA-event timed, max over ranks
-e2e     the same step through the host-buffer entry (C-ABI vpa_infonce_step_host at N=1, the Python public
-        API with pinned host tensors at N>1): H2D of the embeddings and D2H of loss + gradients inside the
-        timed region
-roofline  the backward sweep kernel (tcgen05), algorithmic 6*b*B*D flops per launch / its CUDA-event time
+e2e     the same step through the host-buffer entry (C-ABI vpa_infonce_step_host at N=1 -- pipelined over row shards on
+        three streams --, the Python public API with pinned host tensors at N>1): H2D of the embeddings and D2H of
+        loss + gradients inside the timed region
+roofline  the backward sweep kernel (tcgen05), algorithmic 6*b*B*D flops per launch / its CUDA-event time; traffic = DRAM
+        bytes per launch from the committed ncu capture (profiles/traffic.json)
 cpu_baseline  the oracle's torch-CPU port of the reference arithmetic on a bounded row-block sample
+c2_batch512_latency  BASELINE.json configs[1] (per-GPU batch 512 x 512): microseconds per step, eager and CUDA-graph replay
 --impl reference   times that CPU port as the main line (the reference itself cannot travel to the GPU box)
 """
 from __future__ import annotations

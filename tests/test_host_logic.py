@@ -171,7 +171,7 @@ def _worker(rank, world, port, B, D, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 3])
 def test_row_sharded_plumbing_gloo(world):
     B, D = 48, 32
     mgr = mp.Manager()

@@ -1,8 +1,10 @@
 """vipant_b200 -- B200-native InfoNCE / retrieval-scoring hot path of VIP-ANT (zhaoyanpeng/vipant).
 
 Host side: Python mirror of the reference's loss-head API (``loss_head``), tensor-level functions
-(``functional``) and the ctypes binding (``_cabi``) of the C-ABI CUDA library built from ``csrc/``.
+(``functional``) and the ctypes binding (``_cabi``) of the C-ABI CUDA library built from ``csrc/``;
+``embed_cache``: packed shards of pre-computed embeddings (the on-disk format either side of the path).
 """
+from . import embed_cache  # noqa: F401
 from .functional import infonce_loss, l2_normalize, sim_rank_topk, tensor_core_supported  # noqa: F401
 from .loss_head import (  # noqa: F401
     LOSS_HEADS_REGISTRY,

@@ -226,6 +226,17 @@ int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles /* world x 64 bytes, rank order */);
 int vpa_p2p_destroy(void* p2p);
 
+/* EXPERIMENTAL (VPA_P2P_MODE=nvls at vpa_p2p_create time; compiled, not yet exercised on hardware): the segment is backed by
+ * VMM memory bound into one NVSwitch multicast object, and every exchange is a multimem.st (one store, all ranks).
+ * vpa_p2p_mode: 0 push, 1 pull (default), 2 copy engines, 3 streaming push, 4 NVLS.  Setup in mode 4 replaces the IPC handle
+ * exchange: rank 0 calls vpa_p2p_nvls_export and passes the POSIX file descriptor to the other ranks' processes (SCM_RIGHTS);
+ * every rank calls vpa_p2p_nvls_attach (fd < 0 on rank 0); after a host barrier every rank calls vpa_p2p_nvls_bind, then
+ * vpa_p2p_connect(p2p, NULL-able). */
+int vpa_p2p_mode(void* p2p);
+int vpa_p2p_nvls_export(void* p2p, int* fd_out);
+int vpa_p2p_nvls_attach(void* p2p, int fd);
+int vpa_p2p_nvls_bind(void* p2p);
+
 int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype, int64_t rows_local, int world, int rank,
                         int D, int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale,
                         float scale_max, int precision, float* loss_out, uint32_t* epoch_out, void* stream);

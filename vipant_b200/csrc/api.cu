@@ -615,6 +615,10 @@ int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision
 }
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles) { return p2p_connect(p2p, all_ipc_handles); }
 int vpa_p2p_destroy(void* p2p) { return p2p_destroy(p2p); }
+int vpa_p2p_mode(void* p2p) { return p2p_mode(p2p); }
+int vpa_p2p_nvls_export(void* p2p, int* fd_out) { return p2p_nvls_export(p2p, fd_out); }
+int vpa_p2p_nvls_attach(void* p2p, int fd) { return p2p_nvls_attach(p2p, fd); }
+int vpa_p2p_nvls_bind(void* p2p) { return p2p_nvls_bind(p2p); }
 
 int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank, int D,
                         int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale, float scale_max,

@@ -91,6 +91,7 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
   const int64_t slot = (int64_t)pv.rank * (B + 3 * b);
   auto put = [&](int64_t pos, float v) {
     if (!p2p) { msg[pos] = v; return; }
+    if (pv.mc) { mc_st_f32(reinterpret_cast<float*>(pv.mc + off_msgs) + slot + pos, v); return; }      // NVLS: one store, all ranks
     for (int q = 0; q < pv.world; ++q) reinterpret_cast<float*>(pv.base[q] + off_msgs)[slot + pos] = v;
   };
   if (idx < B) {
@@ -149,8 +150,11 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
       __threadfence();
     }
     __syncthreads();
-    if (last && (int)threadIdx.x < pv.world)      // one thread per destination: the release stores travel in parallel
+    if (last && pv.mc) {
+      if (threadIdx.x == 0) mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.mc + off_msg_flags) + pv.rank, pv.epoch);
+    } else if (last && (int)threadIdx.x < pv.world) {      // one thread per destination: the release stores travel in parallel
       st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.base[threadIdx.x] + off_msg_flags) + pv.rank, pv.epoch);
+    }
   }
 }
 
@@ -350,8 +354,10 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
     }
     const float part_dls = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
     if (pv.world > 1) {                     // peer-memory transport: {epoch, partial} into every rank's slot of this rank,
-      if ((int)threadIdx.x < pv.world) {    // one thread per destination
-        const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
+      const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
+      if (pv.mc) {
+        if (threadIdx.x == 0) mc_st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.mc + off_dls) + pv.rank, w);
+      } else if ((int)threadIdx.x < pv.world) {    // one thread per destination
         st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[threadIdx.x] + off_dls) + pv.rank, w);
       }
     } else if (threadIdx.x == 0) {

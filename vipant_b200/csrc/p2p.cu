@@ -21,6 +21,9 @@
 // ones.  Every spin is bounded (8 s of %globaltimer) and traps: a missing peer is an error on the stream, not a hang.
 #include "p2p.cuh"
 
+#include <cuda.h>
+#include <unistd.h>
+
 #include <cstring>
 #include <new>
 
@@ -86,7 +89,13 @@ struct P2PHandle {
   cudaEvent_t fork = nullptr, join = nullptr;
   bool join_pending = false;
   int push_groups = 8, push_ctas = 4, push_rounds = 8;
-  int pull = 1, pull_ctas = 64;      // pull: 0 = push kernel, 1 = pull kernel, 2 = copy engines, 3 = streaming push kernel
+  int pull = 1, pull_ctas = 64;      // pull: 0 = push kernel, 1 = pull kernel, 2 = copy engines, 3 = streaming push kernel,
+                                     //       4 = NVLS multicast stores (segment allocated with the VMM API, see below)
+  CUmemGenericAllocationHandle vmm_mem = 0, vmm_mc = 0;
+  CUdeviceptr uc_va = 0, mc_va = 0;
+  size_t vmm_size = 0;
+  bool mc_added = false, mc_bound = false;
+  int mc_ctas = 24;
   int stream_ctas = 96;
   cudaStream_t side2 = nullptr;
   cudaEvent_t ready_ev = nullptr, join2 = nullptr;
@@ -334,6 +343,7 @@ __global__ void p2p_dls_sum_kernel(const unsigned long long* __restrict__ slots,
 static P2PView make_view(const P2PHandle* h, uint32_t epoch) {
   P2PView v{};
   for (int q = 0; q < kMaxPeers; ++q) v.base[q] = h->base[q];
+  v.mc = reinterpret_cast<char*>(h->mc_va);
   v.rank = h->rank;
   v.world = h->world;
   v.epoch = epoch;
@@ -350,6 +360,207 @@ static void launch_pull(const P2PHandle* h, const PullArgs& G, int ctas) {
   }
 }
 
+// ---------------------------------------------------------------- NVLS (NVSwitch multicast) variant of the segment
+// VPA_P2P_MODE=nvls.  EXPERIMENTAL: compiles, written ahead of the hardware time to debug it.
+// Every rank backs its segment with VMM physical memory (cuMemCreate) and binds it, at offset 0, into ONE multicast object
+// created by rank 0 and shared as a POSIX file descriptor (the host passes it between the processes, SCM_RIGHTS).  The
+// multicast mapping `mc_va` then aliases all R segments: a multimem.st to mc_va + off lands at `off` in every rank's copy,
+// replicated inside the NVSwitch -- one store and 1/(R-1) of the egress of the unicast transports.  Reads and flag polls
+// use the local unicast mapping; no rank maps another rank's memory.
+struct DriverApi {
+  bool ok = false;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
+  CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+};
+static DriverApi& driver_api() {
+  static DriverApi d;
+  static bool tried = false;
+  if (tried) return d;
+  tried = true;
+  bool all = true;
+  auto get = [&](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) {
+      all = false;
+      cudaGetLastError();
+    }
+  };
+#define VPA_DRV(field, name) get(name, reinterpret_cast<void**>(&d.field))
+  VPA_DRV(MemCreate, "cuMemCreate"); VPA_DRV(MemRelease, "cuMemRelease");
+  VPA_DRV(MemAddressReserve, "cuMemAddressReserve"); VPA_DRV(MemAddressFree, "cuMemAddressFree");
+  VPA_DRV(MemMap, "cuMemMap"); VPA_DRV(MemUnmap, "cuMemUnmap"); VPA_DRV(MemSetAccess, "cuMemSetAccess");
+  VPA_DRV(MemExportToShareableHandle, "cuMemExportToShareableHandle");
+  VPA_DRV(MemImportFromShareableHandle, "cuMemImportFromShareableHandle");
+  VPA_DRV(MulticastCreate, "cuMulticastCreate"); VPA_DRV(MulticastAddDevice, "cuMulticastAddDevice");
+  VPA_DRV(MulticastBindMem, "cuMulticastBindMem"); VPA_DRV(MulticastUnbind, "cuMulticastUnbind");
+  VPA_DRV(MulticastGetGranularity, "cuMulticastGetGranularity");
+  VPA_DRV(DeviceGet, "cuDeviceGet"); VPA_DRV(DeviceGetAttribute, "cuDeviceGetAttribute");
+#undef VPA_DRV
+  d.ok = all;
+  return d;
+}
+#define VPA_DRV_CALL(expr)                                                                     \
+  do {                                                                                         \
+    CUresult r__ = (expr);                                                                     \
+    if (r__ != CUDA_SUCCESS) return ::vpa::set_error(VPA_E_COMM, "%s failed (CUresult %d)", #expr, (int)r__); \
+  } while (0)
+
+static CUmulticastObjectProp nvls_mc_prop(const P2PHandle* h) {
+  CUmulticastObjectProp mp{};
+  mp.numDevices = (unsigned)h->world;
+  mp.size = h->vmm_size;
+  mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  mp.flags = 0;
+  return mp;
+}
+
+// physical memory + local unicast mapping of the segment; size rounded up to the multicast granularity
+static int nvls_alloc(P2PHandle* h) {
+  DriverApi& d = driver_api();
+  if (!d.ok) return set_error(VPA_E_NO_DEVICE, "nvls: CUDA driver entry points (cuMem* / cuMulticast*) unavailable");
+  CUdevice dev;
+  VPA_DRV_CALL(d.DeviceGet(&dev, h->dev));
+  int mc_ok = 0;
+  VPA_DRV_CALL(d.DeviceGetAttribute(&mc_ok, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev));
+  if (!mc_ok) return set_error(VPA_E_UNSUPPORTED, "nvls: device %d does not support multicast objects", h->dev);
+  h->vmm_size = h->L.total;
+  CUmulticastObjectProp mp = nvls_mc_prop(h);
+  size_t gran = 0;
+  VPA_DRV_CALL(d.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  if (gran == 0) gran = (size_t)2 << 20;
+  h->vmm_size = align_up(h->L.total, gran);
+  CUmemAllocationProp ap{};
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = h->dev;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  VPA_DRV_CALL(d.MemCreate(&h->vmm_mem, h->vmm_size, &ap, 0));
+  VPA_DRV_CALL(d.MemAddressReserve(&h->uc_va, h->vmm_size, gran, 0, 0));
+  VPA_DRV_CALL(d.MemMap(h->uc_va, h->vmm_size, 0, h->vmm_mem, 0));
+  CUmemAccessDesc ad{};
+  ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ad.location.id = h->dev;
+  ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  VPA_DRV_CALL(d.MemSetAccess(h->uc_va, h->vmm_size, &ad, 1));
+  h->base[h->rank] = reinterpret_cast<char*>(h->uc_va);
+  return 0;
+}
+
+static void nvls_free(P2PHandle* h) {
+  DriverApi& d = driver_api();
+  if (!d.ok) return;
+  if (h->mc_va) { d.MemUnmap(h->mc_va, h->vmm_size); d.MemAddressFree(h->mc_va, h->vmm_size); }
+  if (h->mc_bound) { CUdevice dev; if (d.DeviceGet(&dev, h->dev) == CUDA_SUCCESS) d.MulticastUnbind(h->vmm_mc, dev, 0, h->vmm_size); }
+  if (h->vmm_mc) d.MemRelease(h->vmm_mc);
+  if (h->uc_va) { d.MemUnmap(h->uc_va, h->vmm_size); d.MemAddressFree(h->uc_va, h->vmm_size); }
+  if (h->vmm_mem) d.MemRelease(h->vmm_mem);
+  h->mc_va = h->uc_va = 0;
+  h->vmm_mc = h->vmm_mem = 0;
+  h->base[h->rank] = nullptr;
+}
+
+int p2p_mode(void* handle) { return handle ? static_cast<P2PHandle*>(handle)->pull : -1; }
+
+// rank 0: create the multicast object and export it; the host hands the descriptor to the other ranks' processes
+int p2p_nvls_export(void* handle, int* fd_out) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  VPA_CHECK_ARG(h && fd_out && h->pull == 4 && h->vmm_mem, "nvls_export: not an NVLS handle");
+  DriverApi& d = driver_api();
+  CUmulticastObjectProp mp = nvls_mc_prop(h);
+  VPA_DRV_CALL(d.MulticastCreate(&h->vmm_mc, &mp));
+  int fd = -1;
+  VPA_DRV_CALL(d.MemExportToShareableHandle(&fd, h->vmm_mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  *fd_out = fd;
+  return 0;
+}
+
+// every rank (fd < 0 on the rank that created the object): import, then add this device to the multicast team
+int p2p_nvls_attach(void* handle, int fd) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  VPA_CHECK_ARG(h && h->pull == 4 && h->vmm_mem, "nvls_attach: not an NVLS handle");
+  DriverApi& d = driver_api();
+  if (fd >= 0) {
+    VPA_CHECK_ARG(h->vmm_mc == 0, "nvls_attach: this rank already holds the multicast object");
+    VPA_DRV_CALL(d.MemImportFromShareableHandle(&h->vmm_mc, reinterpret_cast<void*>(static_cast<intptr_t>(fd)),
+                                                CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+    close(fd);
+  }
+  VPA_CHECK_ARG(h->vmm_mc != 0, "nvls_attach: no multicast object (rank 0 exports it, the others pass its descriptor)");
+  CUdevice dev;
+  VPA_DRV_CALL(d.DeviceGet(&dev, h->dev));
+  VPA_DRV_CALL(d.MulticastAddDevice(h->vmm_mc, dev));
+  h->mc_added = true;
+  return 0;
+}
+
+// after EVERY rank has attached (host barrier): bind the local memory and map the multicast view
+int p2p_nvls_bind(void* handle) {
+  P2PHandle* h = static_cast<P2PHandle*>(handle);
+  VPA_CHECK_ARG(h && h->pull == 4 && h->mc_added, "nvls_bind: attach first");
+  DriverApi& d = driver_api();
+  VPA_DRV_CALL(d.MulticastBindMem(h->vmm_mc, 0, h->vmm_mem, 0, h->vmm_size, 0));
+  h->mc_bound = true;
+  CUmulticastObjectProp mp = nvls_mc_prop(h);
+  size_t gran = 0;
+  VPA_DRV_CALL(d.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  VPA_DRV_CALL(d.MemAddressReserve(&h->mc_va, h->vmm_size, gran, 0, 0));
+  VPA_DRV_CALL(d.MemMap(h->mc_va, h->vmm_size, 0, h->vmm_mc, 0));
+  CUmemAccessDesc ad{};
+  ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ad.location.id = h->dev;
+  ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  VPA_DRV_CALL(d.MemSetAccess(h->mc_va, h->vmm_size, &ad, 1));
+  return 0;
+}
+
+// operands through the multicast mapping: every CTA takes whole 256-row chunks of THIS rank's block (x2 operands first),
+// one multimem.st per 16 bytes reaches all ranks, then one system fence and the chunk's flag -- again one store for all.
+__global__ void __launch_bounds__(256) p2p_mc_push_kernel(const PullArgs A) {
+  const int me = A.v.rank;
+  char* mine = A.v.base[me];
+  const int total = 2 * A.cpr;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int m = item / A.cpr, c = item - m * A.cpr;
+    const int64_t row0 = (int64_t)c * kPushRows;
+    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
+    const int n16 = rows * (A.row_bytes / 16);
+    const size_t off = A.off_mat[m] + ((size_t)me * A.b + row0) * A.row_bytes;
+    const uint4* from = reinterpret_cast<const uint4*>(mine + off);
+    uint4* to = reinterpret_cast<uint4*>(A.v.mc + off);
+    for (int i = threadIdx.x; i < n16; i += 256 * kPullUnroll) {
+      uint4 val[kPullUnroll];
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * 256;
+        if (idx < n16) val[u] = __ldg(from + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * 256;
+        if (idx < n16) mc_st_v4(to + idx, val[u]);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.mc + A.off_flags[m]) + me * A.cpr + c, A.v.epoch);
+  }
+}
+
 int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out, void* ipc_handle64) {
   VPA_CHECK_ARG(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, "p2p: world must be 2..%d", kMaxPeers);
   VPA_CHECK_ARG(b > 0 && D > 0 && out && ipc_handle64, "p2p_create: bad argument");
@@ -360,19 +571,33 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   h->L = seg_layout(b, world, D, precision);
   auto fail = [&](cudaError_t e, const char* what) {
     const int rc = set_error((int)e, "p2p_create: %s failed: %s", what, cudaGetErrorString(e));
-    if (h->base[rank]) cudaFree(h->base[rank]);
+    if (h->pull == 4) nvls_free(h);
+    else if (h->base[rank]) cudaFree(h->base[rank]);
     delete h;
     return rc;
   };
   cudaError_t e;
   if ((e = cudaGetDevice(&h->dev)) != cudaSuccess) return fail(e, "cudaGetDevice");
+  const char* mode_env = getenv("VPA_P2P_MODE");
   void* p = nullptr;
-  if ((e = cudaMalloc(&p, h->L.total)) != cudaSuccess) return fail(e, "cudaMalloc");
-  h->base[rank] = static_cast<char*>(p);
+  if (mode_env && strcmp(mode_env, "nvls") == 0) {      // VMM memory bound into a multicast object; no IPC handle
+    h->pull = 4;
+    cudaFree(nullptr);                                  // make sure the primary context is current for the driver calls
+    if (int rc = nvls_alloc(h)) {
+      nvls_free(h);
+      delete h;
+      return rc;
+    }
+    p = h->base[rank];
+    memset(ipc_handle64, 0, 64);
+  } else {
+    if ((e = cudaMalloc(&p, h->L.total)) != cudaSuccess) return fail(e, "cudaMalloc");
+    h->base[rank] = static_cast<char*>(p);
+    cudaIpcMemHandle_t ih;
+    if ((e = cudaIpcGetMemHandle(&ih, p)) != cudaSuccess) return fail(e, "cudaIpcGetMemHandle");
+    memcpy(ipc_handle64, &ih, 64);
+  }
   if ((e = cudaMemset(p, 0, h->L.mat[0][0])) != cudaSuccess) return fail(e, "cudaMemset");      // flags, slots, counters
-  cudaIpcMemHandle_t ih;
-  if ((e = cudaIpcGetMemHandle(&ih, p)) != cudaSuccess) return fail(e, "cudaIpcGetMemHandle");
-  memcpy(ipc_handle64, &ih, 64);
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   if ((e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return fail(e, "cudaStreamCreate");
@@ -380,7 +605,8 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreate");
   if (const char* s = getenv("VPA_P2P_PUSH_GROUPS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_groups = v; }
   if (const char* s = getenv("VPA_P2P_PUSH_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 32) h->push_ctas = v; }
-  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : (strcmp(s, "stream") == 0 ? 3 : 1));
+  if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : (strcmp(s, "stream") == 0 ? 3 : (strcmp(s, "nvls") == 0 ? 4 : 1)));
+  if (const char* s = getenv("VPA_P2P_MC_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 148) h->mc_ctas = v; }
   if (const char* s = getenv("VPA_P2P_STREAM_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->stream_ctas = v; }
   if (const char* s = getenv("VPA_P2P_PULL_THREADS")) { const int v = atoi(s); if (v == 128 || v == 256) h->pull_threads = v; }
   if (const char* s = getenv("VPA_P2P_PULL_LD")) h->strong_ld = strcmp(s, "weak") != 0;
@@ -406,7 +632,8 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
       if (fwd_regs + pull_regs > 65536) {
         const int rc = set_error(VPA_E_UNSUPPORTED, "p2p: pull kernel (%d regs/CTA) cannot co-reside with the forward sweep (%d regs/CTA)",
                                  pull_regs, fwd_regs);
-        cudaFree(h->base[rank]);
+        if (h->pull == 4) nvls_free(h);
+        else cudaFree(h->base[rank]);
         delete h;
         return rc;
       }
@@ -420,8 +647,13 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
 
 int p2p_connect(void* handle, const void* all_handles) {
   P2PHandle* h = static_cast<P2PHandle*>(handle);
-  VPA_CHECK_ARG(h && all_handles, "p2p_connect: bad argument");
+  VPA_CHECK_ARG(h && (all_handles || h->pull == 4), "p2p_connect: bad argument");
   if (h->connected) return 0;
+  if (h->pull == 4) {      // NVLS: nothing to map -- every exchange goes through the multicast view
+    VPA_CHECK_ARG(h->mc_va != 0, "p2p_connect: NVLS segment is not bound yet (export / attach / bind first)");
+    h->connected = true;
+    return 0;
+  }
   for (int q = 0; q < h->world; ++q) {
     if (q == h->rank) continue;
     cudaIpcMemHandle_t ih;
@@ -441,7 +673,8 @@ int p2p_destroy(void* handle) {
   cudaDeviceSynchronize();
   for (int q = 0; q < h->world; ++q)
     if (h->opened[q]) cudaIpcCloseMemHandle(h->base[q]);
-  if (h->base[h->rank]) cudaFree(h->base[h->rank]);
+  if (h->pull == 4) nvls_free(h);
+  else if (h->base[h->rank]) cudaFree(h->base[h->rank]);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
   if (h->ready_ev) cudaEventDestroy(h->ready_ev);
@@ -563,7 +796,17 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
     prof_end(PROF_PUSH, h->side);
   } else {
   prof_begin(PROF_PUSH, h->side);
-  if (h->pull == 3) {
+  if (h->pull == 4) {
+    PullArgs G{};
+    G.v = A.v;
+    G.off_mat[0] = A.off_mat[0]; G.off_mat[1] = A.off_mat[1];
+    G.off_flags[0] = A.off_flags[0]; G.off_flags[1] = A.off_flags[1];
+    G.off_ready = L.ready;
+    G.b = h->b; G.row_bytes = A.row_bytes; G.cpr = L.cpr;
+    G.m0 = 0; G.m1 = 2;
+    const int items = 2 * L.cpr;
+    p2p_mc_push_kernel<<<items < h->mc_ctas ? items : h->mc_ctas, 256, 0, h->side>>>(G);
+  } else if (h->pull == 3) {
     PullArgs G{};
     G.v = A.v;
     G.off_mat[0] = A.off_mat[0]; G.off_mat[1] = A.off_mat[1];

@@ -14,9 +14,26 @@ constexpr int kPushRows = 256;        // flag granularity of the operand push ==
 
 struct P2PView {
   char* base[kMaxPeers];              // base[rank] is the local segment
+  char* mc;                           // NVLS transport: multicast mapping of the segment (a store lands in EVERY rank's
+                                      // copy at the same offset, replicated by the NVSwitch); nullptr otherwise
   int rank, world;
   uint32_t epoch;                     // step number (monotonic, starts at 1); flags carry the epoch of the data they publish
 };
+
+// stores to a multicast address (multimem.st: one store, every replica)
+__device__ __forceinline__ void mc_st_f32(float* p, float v) {
+  asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_st_v4(uint4* p, uint4 v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+__device__ __forceinline__ void mc_st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("multimem.st.release.sys.global.f32 [%0], %1;" ::"l"(p), "f"(__uint_as_float(v)) : "memory");
+}
+__device__ __forceinline__ void mc_st_release_sys_u64(unsigned long long* p, unsigned long long v) {      // one 8-byte element
+  asm volatile("multimem.st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(__longlong_as_double((long long)v)) : "memory");
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
@@ -103,5 +120,9 @@ int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st);
 int p2p_join_push(void* handle, cudaStream_t st);
 int p2p_wait_operands(void* handle, uint32_t epoch, const float* gate_scale, float scale_cap, cudaStream_t st);
 int p2p_dls_sum(const P2PStep& s, float* dlogit_scale, cudaStream_t st);
+int p2p_mode(void* handle);
+int p2p_nvls_export(void* handle, int* fd_out);
+int p2p_nvls_attach(void* handle, int fd);
+int p2p_nvls_bind(void* handle);
 
 }  // namespace vpa

@@ -330,10 +330,12 @@ def _get_p2p(group, b, D, precision, dev):
     rc = lib.vpa_p2p_create(b, world, rank, D, precision, ctypes.byref(handle), mine)
     err = "" if rc == 0 else (lib.vpa_last_error_string() or b"").decode()
     everyone = [None] * world
-    dist.all_gather_object(everyone, (rc, bytes(mine.raw)), group=group)
-    ok = all(r == 0 for r, _ in everyone)
-    if ok:
-        rc = lib.vpa_p2p_connect(handle, b"".join(h for _, h in everyone))
+    dist.all_gather_object(everyone, (rc, bytes(mine.raw), os.getpid()), group=group)
+    ok = all(r == 0 for r, _, _ in everyone)
+    if ok and lib.vpa_p2p_mode(handle) == 4:
+        rc, err = _nvls_setup(lib, handle, rank, world, everyone[0][2], group)
+    elif ok:
+        rc = lib.vpa_p2p_connect(handle, b"".join(h for _, h, _ in everyone))
         err = "" if rc == 0 else (lib.vpa_last_error_string() or b"").decode()
     status = [None] * world
     dist.all_gather_object(status, rc if ok else 1, group=group)    # also: nobody stores into a peer before all have mapped
@@ -353,6 +355,56 @@ def _get_p2p(group, b, D, precision, dev):
 
 
 _P2P_ATEXIT = []
+
+
+def _nvls_setup(lib, handle, rank, world, pid0, group):
+    """EXPERIMENTAL NVLS transport: rank 0 creates the multicast object and passes its file descriptor to every other rank's
+    process over an abstract UNIX socket (SCM_RIGHTS); all attach their device, barrier, bind their memory."""
+    import socket
+    import time
+
+    def err():
+        return (lib.vpa_last_error_string() or b"").decode()
+    fd = ctypes.c_int(-1)
+    name = f"\0vipant-b200-nvls-{pid0}-{id(group) & 0xffff}"
+    rc = 0
+    if rank == 0:
+        rc = lib.vpa_p2p_nvls_export(handle, ctypes.byref(fd))
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(name)
+        srv.listen(world)
+    dist.barrier(group=group)                      # the socket exists
+    if rank == 0:
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            if rc == 0:
+                socket.send_fds(conn, [b"fd"], [fd.value])
+            else:
+                conn.sendall(b"no")
+            conn.close()
+        srv.close()
+        if rc == 0:
+            os.close(fd.value)
+            rc = lib.vpa_p2p_nvls_attach(handle, -1)
+    else:
+        cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        for _ in range(200):
+            try:
+                cli.connect(name)
+                break
+            except OSError:
+                time.sleep(0.05)
+        msg, fds, _, _ = socket.recv_fds(cli, 16, 1)
+        cli.close()
+        rc = lib.vpa_p2p_nvls_attach(handle, fds[0]) if fds else 1
+    flags = [None] * world
+    dist.all_gather_object(flags, rc, group=group)      # every device is in the multicast team (or someone failed)
+    if any(flags):
+        return 1, err()
+    rc = lib.vpa_p2p_nvls_bind(handle)
+    if rc == 0:
+        rc = lib.vpa_p2p_connect(handle, None)
+    return rc, ("" if rc == 0 else err())
 
 
 def _destroy_p2p():

@@ -357,19 +357,12 @@ def _get_p2p(group, b, D, precision, dev):
 _P2P_ATEXIT = []
 
 
-def _nvls_setup(lib, handle, rank, world, pid0, group):
-    """EXPERIMENTAL NVLS transport: rank 0 creates the multicast object and passes its file descriptor to every other rank's
-    process over an abstract UNIX socket (SCM_RIGHTS); all attach their device, barrier, bind their memory."""
+def _share_fd_from_rank0(rank, world, fd, name, group):
+    """Rank 0 hands the open file descriptor `fd` (or None: "nothing to share") to every other rank's process over an abstract
+    UNIX socket `name` (SCM_RIGHTS).  Returns the received descriptor on the other ranks (None if rank 0 had none), `fd` on 0."""
     import socket
     import time
-
-    def err():
-        return (lib.vpa_last_error_string() or b"").decode()
-    fd = ctypes.c_int(-1)
-    name = f"\0vipant-b200-nvls-{pid0}-{id(group) & 0xffff}"
-    rc = 0
     if rank == 0:
-        rc = lib.vpa_p2p_nvls_export(handle, ctypes.byref(fd))
         srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
         srv.bind(name)
         srv.listen(world)
@@ -377,26 +370,40 @@ def _nvls_setup(lib, handle, rank, world, pid0, group):
     if rank == 0:
         for _ in range(world - 1):
             conn, _ = srv.accept()
-            if rc == 0:
-                socket.send_fds(conn, [b"fd"], [fd.value])
+            if fd is not None:
+                socket.send_fds(conn, [b"fd"], [fd])
             else:
                 conn.sendall(b"no")
             conn.close()
         srv.close()
+        return fd
+    cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    for _ in range(200):
+        try:
+            cli.connect(name)
+            break
+        except OSError:
+            time.sleep(0.05)
+    _, fds, _, _ = socket.recv_fds(cli, 16, 1)
+    cli.close()
+    return fds[0] if fds else None
+
+
+def _nvls_setup(lib, handle, rank, world, pid0, group):
+    """EXPERIMENTAL NVLS transport: rank 0 creates the multicast object and passes its file descriptor to every other rank's
+    process; all attach their device, agree, then bind their memory and map the multicast view."""
+    def err():
+        return (lib.vpa_last_error_string() or b"").decode()
+    fd = ctypes.c_int(-1)
+    rc = lib.vpa_p2p_nvls_export(handle, ctypes.byref(fd)) if rank == 0 else 0
+    got = _share_fd_from_rank0(rank, world, fd.value if (rank == 0 and rc == 0) else None,
+                               f"\0vipant-b200-nvls-{pid0}-{id(group) & 0xffff}", group)
+    if rank == 0:
         if rc == 0:
             os.close(fd.value)
             rc = lib.vpa_p2p_nvls_attach(handle, -1)
     else:
-        cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        for _ in range(200):
-            try:
-                cli.connect(name)
-                break
-            except OSError:
-                time.sleep(0.05)
-        msg, fds, _, _ = socket.recv_fds(cli, 16, 1)
-        cli.close()
-        rc = lib.vpa_p2p_nvls_attach(handle, fds[0]) if fds else 1
+        rc = lib.vpa_p2p_nvls_attach(handle, got) if got is not None else 1      # (the library closes the descriptor)
     flags = [None] * world
     dist.all_gather_object(flags, rc, group=group)      # every device is in the multicast team (or someone failed)
     if any(flags):

@@ -114,3 +114,17 @@ def test_sharded_matches_global_batch(precision, B, D, transport):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), B, D, precision, transport, False, 4, out), nprocs=world, join=True)
     _check(out, world, B, D, precision)
+
+
+def test_nvls_multicast_transport_two_gpus():
+    """EXPERIMENTAL transport (VPA_P2P_MODE=nvls): segment bound into an NVSwitch multicast object, every exchange a
+    multimem.st.  Needs 2 GPUs behind an NVSwitch; VIPANT_REQUIRE_P2P turns a failed setup into an error instead of the
+    NCCL fallback."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs 2 GPUs")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    env = {"VPA_P2P_MODE": "nvls", "VIPANT_REQUIRE_P2P": "1"}
+    mp.spawn(_worker, args=(world, _free_port(), 1024, 512, "bf16", "p2p", False, 4, out, env), nprocs=world, join=True)
+    _check(out, world, 1024, 512, "bf16", env)

@@ -342,6 +342,8 @@ def _get_p2p(group, b, D, precision, dev):
     if not all(r == 0 for r in status):
         if handle:
             lib.vpa_p2p_destroy(handle)
+        if os.environ.get("VIPANT_REQUIRE_P2P"):          # tests / A-B runs: no silent change of transport
+            raise _cabi.VipantB200Error(f"peer-memory transport unavailable on rank {rank}: {err or 'a peer failed'}")
         import warnings
         warnings.warn(f"vipant_b200: peer-memory transport unavailable on rank {rank} ({err or 'a peer failed'}); using NCCL")
         _P2P[key] = None

@@ -233,6 +233,9 @@ int vpa_p2p_destroy(void* p2p);
  * every rank calls vpa_p2p_nvls_attach (fd < 0 on rank 0); after a host barrier every rank calls vpa_p2p_nvls_bind, then
  * vpa_p2p_connect(p2p, NULL-able). */
 int vpa_p2p_mode(void* p2p);
+/* Diagnostics / tests (host only): the pull kernel's work-item map.  out5 = matrix (0: x2 operands, 1: x1), source rank, chunk
+ * index, first row within the source's block, row count.  Items 0 .. n_matrices * chunks_per_rank * (world-1) * slices - 1. */
+int vpa_debug_pull_item(int item, int m0, int world, int me, int chunks_per_rank, int slices, int64_t rows_local, int* out5);
 int vpa_p2p_nvls_export(void* p2p, int* fd_out);
 int vpa_p2p_nvls_attach(void* p2p, int fd);
 int vpa_p2p_nvls_bind(void* p2p);

@@ -616,6 +616,14 @@ int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles) { return p2p_connect(p2p, all_ipc_handles); }
 int vpa_p2p_destroy(void* p2p) { return p2p_destroy(p2p); }
 int vpa_p2p_mode(void* p2p) { return p2p_mode(p2p); }
+// the pull kernel's item -> (matrix, source rank, chunk, first row, rows) map, evaluated on the host (tests)
+int vpa_debug_pull_item(int item, int m0, int world, int me, int chunks_per_rank, int slices, int64_t rows_local, int* out5) {
+  VPA_CHECK_ARG(out5 && world >= 2 && me >= 0 && me < world && chunks_per_rank >= 1 && slices >= 1 && rows_local >= 1 && item >= 0,
+                "debug_pull_item: bad argument");
+  const PullItem it = pull_item_decode(item, m0, world, me, chunks_per_rank, slices, rows_local);
+  out5[0] = it.m; out5[1] = it.src; out5[2] = it.c; out5[3] = it.row0; out5[4] = it.rows;
+  return 0;
+}
 int vpa_p2p_nvls_export(void* p2p, int* fd_out) { return p2p_nvls_export(p2p, fd_out); }
 int vpa_p2p_nvls_attach(void* p2p, int fd) { return p2p_nvls_attach(p2p, fd); }
 int vpa_p2p_nvls_bind(void* p2p) { return p2p_nvls_bind(p2p); }

@@ -35,6 +35,7 @@ struct SegLayout {
   size_t ready;             // [world] uint32: rank q's operands of epoch e are complete in ITS segment (pull mode)
   size_t dls_slots;         // [2][world] uint64 {epoch << 32 | float bits}
   size_t counters;          // local only: [2][cpr] push arrivals, [1] pack arrivals, [1] loss arrivals
+  size_t pull_counters;     // local only: [2][world][cpr] slice arrivals of the pull kernel
   size_t loss_part;         // local only: per-block loss partials (doubles)
   size_t mat[2][2];         // [parity][m]: (B, D) operands
   size_t msgs[2];           // [parity]: (world, B + 3b) floats
@@ -60,6 +61,7 @@ static SegLayout seg_layout(int64_t b, int world, int D, int precision) {
   L.ready = take((size_t)world * 4);
   L.dls_slots = take((size_t)2 * world * 8);
   L.counters = take((size_t)(2 * L.cpr + 2) * 4);
+  L.pull_counters = take((size_t)2 * world * L.cpr * 4);
   L.loss_part = take((size_t)((B + 255) / 256) * 8);
   for (int p = 0; p < 2; ++p) {
     for (int m = 0; m < 2; ++m) L.mat[p][m] = take((size_t)B * D * es);
@@ -100,6 +102,7 @@ struct P2PHandle {
   cudaStream_t side2 = nullptr;
   cudaEvent_t ready_ev = nullptr, join2 = nullptr;
   int ce_streams = 2;
+  int pull_slices = 4;      // items per 256-row chunk of the pull (VPA_P2P_PULL_SLICES); 1 = one CTA pulls a whole chunk
   int pull_threads = 256;   // threads per pull CTA (VPA_P2P_PULL_THREADS: lighter CTAs when many SMs pull)
   int strong_ld = 1;        // system-scope relaxed loads of peer rows (VPA_P2P_PULL_LD=weak: L1::no_allocate weak loads, same speed at N=2)
   int serial = 0, pull_ctas_alone = 148;    // serial plan: x2 operands alone before the forward, x1 operands after it
@@ -178,6 +181,8 @@ struct PullArgs {
   int64_t b;
   int row_bytes, cpr;
   int m0, m1;               // matrices [m0, m1) of {0: x2 operands, 1: x1 operands}; the ready signal goes out with m0 == 0
+  int slices;               // pull kernel: items per chunk (see pull_item_decode)
+  size_t off_pull_counters;
 };
 constexpr int kPullUnroll = 8;
 
@@ -197,9 +202,9 @@ __device__ __forceinline__ uint4 ld_peer_v4(const uint4* p) {
 
 // Register budget: a pull CTA must fit beside a resident single-pass forward CTA (320 threads x 104 registers = 33280 of
 // the SM's 65536), or ranks polling for rows could starve the kernels that deliver them: <= 126 registers at 256 threads.
-// __maxnreg__(112) pins that (ptxas -v: 112 registers, no spills).
+// __maxnreg__(96) pins that (ptxas -v: 80 registers, no spills); p2p_create re-checks the budget of the actual build.
 template <int STRONG, int THREADS>
-__global__ void __maxnreg__(112) p2p_pull_kernel(const PullArgs A) {
+__global__ void __maxnreg__(96) p2p_pull_kernel(const PullArgs A) {
   const int me = A.v.rank, world = A.v.world;
   char* mine = A.v.base[me];
   if (A.m0 == 0 && blockIdx.x == 0 && (int)threadIdx.x < world && (int)threadIdx.x != me) {
@@ -208,44 +213,43 @@ __global__ void __maxnreg__(112) p2p_pull_kernel(const PullArgs A) {
     st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[threadIdx.x] + A.off_ready) + me, A.v.epoch);
   }
   const uint32_t* ready = reinterpret_cast<const uint32_t*>(mine + A.off_ready);
-  const int per_m = (world - 1) * A.cpr, total = (A.m1 - A.m0) * per_m;
+  uint32_t* arrivals = reinterpret_cast<uint32_t*>(mine + A.off_pull_counters);
+  const int total = (A.m1 - A.m0) * A.cpr * (world - 1) * A.slices;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
-    const int m = A.m0 + item / per_m, r = item % per_m;
-    const int c = r / (world - 1), q = r - c * (world - 1) + 1;
-    const int src = (me + q) % world;
+    const PullItem it = pull_item_decode(item, A.m0, world, me, A.cpr, A.slices, A.b);
+    const int m = it.m, c = it.c, src = it.src;
     if (threadIdx.x == 0) p2p_wait_ge(ready + src, A.v.epoch);
     __syncthreads();
-    const int64_t row0 = (int64_t)c * kPushRows;
-    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
-    const int n16 = rows * (A.row_bytes / 16);
-    const size_t off = A.off_mat[m] + ((size_t)src * A.b + row0) * A.row_bytes;
+    const int n16 = it.rows * (A.row_bytes / 16);
+    const size_t off = A.off_mat[m] + ((size_t)src * A.b + it.row0) * A.row_bytes;
     const uint4* from = reinterpret_cast<const uint4*>(A.v.base[src] + off);
     uint4* to = reinterpret_cast<uint4*>(mine + off);
-    // software pipeline: the loads of batch k+1 are in flight while batch k is stored (2 x 8 x 16 B per thread outstanding)
+    // 8 x 16 B per thread in flight; a deeper software pipeline measured no faster (the rate is set by the requests an SM
+    // can keep outstanding over NVLink, not by the per-thread dependency chain) and costs registers the forward needs
     constexpr int nthr = THREADS, stride = nthr * kPullUnroll;
-    uint4 cur[kPullUnroll], nxt[kPullUnroll];
-    auto load = [&](uint4 (&v)[kPullUnroll], int i0) {
-#pragma unroll
-      for (int u = 0; u < kPullUnroll; ++u) {
-        const int idx = i0 + u * nthr;
-        if (idx < n16) v[u] = ld_peer_v4<STRONG>(from + idx);
-      }
-    };
-    load(cur, threadIdx.x);
     for (int i = threadIdx.x; i < n16; i += stride) {
-      if (i + stride < n16) load(nxt, i + stride);
+      uint4 val[kPullUnroll];
 #pragma unroll
       for (int u = 0; u < kPullUnroll; ++u) {
         const int idx = i + u * nthr;
-        if (idx < n16) to[idx] = cur[u];
+        if (idx < n16) val[u] = ld_peer_v4<STRONG>(from + idx);
       }
 #pragma unroll
-      for (int u = 0; u < kPullUnroll; ++u) cur[u] = nxt[u];
+      for (int u = 0; u < kPullUnroll; ++u) {
+        const int idx = i + u * nthr;
+        if (idx < n16) to[idx] = val[u];
+      }
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0)
-      st_release_sys_u32(reinterpret_cast<uint32_t*>(mine + A.off_flags[m]) + src * A.cpr + c, A.v.epoch);
+    if (threadIdx.x == 0) {
+      // the chunk is complete when all its slices are: monotonic arrival counter (every step adds `slices`), last one publishes
+      const uint32_t old = atomicAdd(&arrivals[(m * world + src) * A.cpr + c], 1u);
+      if ((old + 1) % (uint32_t)A.slices == 0) {
+        __threadfence();
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(mine + A.off_flags[m]) + src * A.cpr + c, A.v.epoch);
+      }
+    }
   }
 }
 
@@ -608,6 +612,7 @@ int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out,
   if (const char* s = getenv("VPA_P2P_MODE")) h->pull = strcmp(s, "push") == 0 ? 0 : (strcmp(s, "ce") == 0 ? 2 : (strcmp(s, "stream") == 0 ? 3 : (strcmp(s, "nvls") == 0 ? 4 : 1)));
   if (const char* s = getenv("VPA_P2P_MC_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 148) h->mc_ctas = v; }
   if (const char* s = getenv("VPA_P2P_STREAM_CTAS")) { const int v = atoi(s); if (v >= 1 && v <= 1024) h->stream_ctas = v; }
+  if (const char* s = getenv("VPA_P2P_PULL_SLICES")) { const int v = atoi(s); if (v >= 1 && v <= 16) h->pull_slices = v; }
   if (const char* s = getenv("VPA_P2P_PULL_THREADS")) { const int v = atoi(s); if (v == 128 || v == 256) h->pull_threads = v; }
   if (const char* s = getenv("VPA_P2P_PULL_LD")) h->strong_ld = strcmp(s, "weak") != 0;
   if (const char* s = getenv("VPA_P2P_PLAN")) h->serial = strcmp(s, "serial") == 0;
@@ -825,7 +830,8 @@ int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st) {
     G.b = h->b; G.row_bytes = A.row_bytes; G.cpr = L.cpr;
     const bool serial = h->serial && h->pull == 1;
     G.m0 = 0; G.m1 = serial ? 1 : 2;
-    const int items = (G.m1 - G.m0) * (h->world - 1) * L.cpr;
+    G.slices = h->pull_slices; G.off_pull_counters = L.pull_counters;
+    const int items = (G.m1 - G.m0) * (h->world - 1) * L.cpr * G.slices;
     const int ctas = serial ? h->pull_ctas_alone : h->pull_ctas;
     launch_pull(h, G, items < ctas ? items : ctas);
     if (serial) {      // the forward starts when all x2 operands are here: the transfer has the fabric and the L2s to itself
@@ -856,9 +862,10 @@ int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st) {
   G.off_ready = L.ready;
   G.b = h->b; G.row_bytes = h->D * (h->precision == VPA_PREC_BF16_TC ? 2 : 4); G.cpr = L.cpr;
   G.m0 = 1; G.m1 = 2;
+  G.slices = h->pull_slices; G.off_pull_counters = L.pull_counters;
   VPA_CUDA(cudaEventRecord(h->fwd_done, st));
   VPA_CUDA(cudaStreamWaitEvent(h->side, h->fwd_done, 0));
-  const int items = (h->world - 1) * L.cpr;
+  const int items = (h->world - 1) * L.cpr * G.slices;
   launch_pull(h, G, items < h->pull_ctas_alone ? items : h->pull_ctas_alone);
   VPA_LAUNCH_CHECK("p2p_pull_kernel");
   VPA_CUDA(cudaEventRecord(h->join, h->side));

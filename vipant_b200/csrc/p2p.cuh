@@ -92,6 +92,35 @@ __device__ __forceinline__ void p2p_wait_rows(const P2PRowFlags& f, int r0, int 
   }
 }
 
+// One item of the pull kernel: `rows` rows starting at row `row0` of rank `src`'s block of matrix `m` (chunk `c`).
+// Items are ordered matrix-major (x2 operands first), then chunk-major, then slice-major, then over the peers: the first
+// (world-1)*slices items are chunk 0 of EVERY peer, so with ~64 CTAs taking items round-robin the early chunks of all peer
+// blocks land first and the forward sweep (which visits its tiles chunk-major) finds data a few microseconds after it
+// starts, instead of waiting for whole 256-row chunks that one CTA needs ~45 us to pull.  A chunk is complete when its
+// `slices` items are (arrival counter).  Shared by the kernel and, host side, vpa_debug_pull_item (CPU test).
+struct PullItem { int m, src, c, row0, rows; };
+__host__ __device__ inline PullItem pull_item_decode(int item, int m0, int world, int me, int cpr, int slices, int64_t b) {
+  const int per_c = (world - 1) * slices;
+  const int per_m = cpr * per_c;
+  PullItem it;
+  it.m = m0 + item / per_m;
+  int r = item % per_m;
+  it.c = r / per_c;
+  r -= it.c * per_c;
+  const int s = r / (world - 1);
+  const int q = r - s * (world - 1) + 1;
+  it.src = (me + q) % world;
+  const int64_t crow0 = (int64_t)it.c * kPushRows;
+  const int64_t left = b - crow0;
+  const int crows = left < kPushRows ? (int)left : kPushRows;
+  const int per = (crows + slices - 1) / slices;
+  const int lo = s * per < crows ? s * per : crows;
+  const int hi = lo + per < crows ? lo + per : crows;
+  it.row0 = (int)crow0 + lo;
+  it.rows = hi - lo;
+  return it;
+}
+
 // Host-side description of one step's buffers inside the local segment (p2p.cu::p2p_step) + what kernels need to reach
 // the same buffers in the peers (offsets are identical in every segment).
 struct P2PStep {

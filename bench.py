@@ -413,7 +413,8 @@ def main():
             "roofline": roofline, "clocks": clocks, "e2e": e2e,
             # kernels of libvipant_b200.so per step: normalise, single-pass fwd, exact fwd (device-gated), column reduce / pack,
             # merge+loss, bwd sweep, finalize (+ operand pull, 2 flag waits, d logit_scale sum on the peer-memory transport)
-            "gpu_launches": {"local": 8, "p2p": 11, "nccl": 8, "host": 9}[transport] * args.steps,
+            # (the separate column-reduce kernel only runs when a rank holds more than 256 32-row groups, i.e. b > 8192)
+            "gpu_launches": ({"local": 7, "p2p": 11, "nccl": 7, "host": 8}[transport] + (1 if b > 8192 else 0)) * args.steps,
         }
         if world == 1 and not args.no_e2e:
             try:

@@ -15,9 +15,14 @@ value   inputs already resident in HBM, CUDA-event timed, max over ranks
 e2e     the same step through the host-buffer entry (C-ABI vpa_infonce_step_host at N=1 -- pipelined over row shards on
         three streams --, the Python public API with pinned host tensors at N>1): H2D of the embeddings and D2H of
         loss + gradients inside the timed region
-roofline  the backward sweep kernel (tcgen05), algorithmic 6*b*B*D flops per launch / its CUDA-event time; traffic = DRAM
-        bytes per launch from the committed ncu capture (profiles/traffic.json)
-cpu_baseline  the oracle's torch-CPU port of the reference arithmetic on a bounded row-block sample
+roofline  the backward sweep kernel (tcgen05), algorithmic 6*b*B*D flops per launch / its CUDA-event time, against the
+        measured cuBLAS bf16 peak: the BURST figure unless this run's own clock samples show a power-capped median (then
+        the sustained one); both fractions are printed.  traffic = DRAM bytes per launch from the committed ncu capture
+parity  every rank compares its loss, d logit_scale and gradients (Frobenius norm of every 4096-row block + 32 sampled rows
+        per block) with the fp64 ground truth committed in tests/golden/bench_parity_b32768.npz (oracle/make_bench_parity.py);
+        the run FAILS (exit code 3) outside the bf16-mode bars (loss 1e-3, gradients 1e-2)
+eager_b200  the reference's formula (loss_head.py:271-283) in PyTorch eager on the same B200: fp32 and bf16 autocast
+cpu_baseline  the oracle's torch-CPU port of the reference arithmetic on a bounded, FIXED row-block sample
 c2_batch512_latency  BASELINE.json configs[1] (per-GPU batch 512 x 512): microseconds per step, eager and CUDA-graph replay
 --impl reference   times that CPU port as the main line (the reference itself cannot travel to the GPU box)
 """
@@ -56,17 +61,27 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
     return ap.parse_args()
 
 
-def peaks():
+def peaks(clocks=None):
+    """Measured peaks (driver-written MEASURED_PEAKS.json).  bf16: the burst figure is the roofline of a kernel that runs at
+    the boost clock; only when this run's own clock samples show a power-capped median (< 85 % of max) does the sustained
+    figure (measured at a ~1.34 GHz median) apply."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fr:
             p = json.load(fr)
-        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))),
-                    hbm=float(p.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+        burst = float(p.get("bf16_tflops", 1660.0))
+        sustained = float(p.get("bf16_tflops_sustained", burst))
+        capped = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz")
+                      and clocks["sm_mhz"] < 0.85 * clocks["sm_max_mhz"])
+        return dict(tflops=sustained if capped else burst, burst=burst, sustained=sustained,
+                    hbm=float(p.get("hbm_gbs", 6650.0)),
+                    source="measured (MEASURED_PEAKS.json, " + ("sustained bf16: power-capped clocks in this run)" if capped
+                                                               else "burst bf16: boost clocks in this run)"))
+    return dict(tflops=1590.0, burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
 def make_inputs(B, D, lo, hi):
@@ -132,24 +147,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_block_sample(B, D, target_s=12.0, reps=None):
-    """Reference arithmetic (oracle torch-CPU port) on a bounded row block of the SAME global batch."""
-    from oracle import infonce_oracle as io
+CPU_SAMPLE_ROWS = 2048      # fixed: 12 * 2048 * B * D executed flops per step (1/16 of the reference's full step at B = 32768)
+
+
+def cpu_block_sample(B, D):
+    """Reference arithmetic (oracle torch-CPU port) on a FIXED row block of the SAME global batch, all host threads."""
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(cores)          # (torch.distributed.run exports OMP_NUM_THREADS=1; this call overrides it)
     x1, x2 = make_inputs(B, D, 0, B)
     x1.requires_grad_(True)
     x2.requires_grad_(True)
     ls = torch.tensor(math.log(1 / 0.07), requires_grad=True)
-    b = min(B, 1024)
-    t0 = time.perf_counter()
-    io.infonce_port_block_step(x1, x2, ls, slice(0, b))           # warm-up + calibration
-    t_cal = time.perf_counter() - t0
-    # grow the block so that one step is ~ target_s / 3, capped by memory (4 b x B fp32 buffers live)
-    per_row = t_cal / b
-    b = int(min(B, max(b, (target_s / 3.0) / max(per_row, 1e-9))))
-    b = max(256, min(b, 8192, B) // 256 * 256) if B >= 256 else B
-    return x1, x2, ls, b, cores
+    return x1, x2, ls, min(B, CPU_SAMPLE_ROWS), torch.get_num_threads()
 
 
 def run_cpu_steps(x1, x2, ls, b, steps):
@@ -178,15 +187,16 @@ def reference_arm(args, rank, world):
             break
     ms = float(np.mean(times) * 1e3)
     value = b / (ms * 1e-3)
-    sample = (f"row block of {b} of the {B} global rows per step (both logits blocks {b}x{B}, 2x cross entropy, autograd "
-              f"backward; 12*b*B*D executed flops = b/B of the reference's full step), fp32 torch CPU")
+    sample = (f"fixed row block of {b} of the {B} global rows per step (both logits blocks {b}x{B}, 2x cross entropy, autograd "
+              f"backward; 12*b*B*D executed flops = b/B of the reference's full step), fp32 torch CPU, {cores} torch threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"InfoNCE fwd+bwd, global batch {B} x {D}, fp32 CPU reference arithmetic", "global_batch": B,
                    "dim": D, "sample_rows": b},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "torch_threads": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -214,7 +224,7 @@ def c2_latency(lib, dev, iters=300):
                                                 0.0, prec, state.data_ptr(), nbytes, loss.data_ptr(), st), "fwd")
         _cabi.check(lib.vpa_infonce_bwd_sharded(None, x1.data_ptr(), x2.data_ptr(), _cabi.F32, B, 1, 0, D, D, D, 0, prec,
                                                 g.data_ptr(), state.data_ptr(), nbytes, dx1.data_ptr(), dx2.data_ptr(),
-                                                dls.data_ptr(), st), "bwd")
+                                                dls.data_ptr(), 1, st), "bwd")
 
     def timed(fn):
         for _ in range(20):
@@ -243,6 +253,95 @@ def c2_latency(lib, dev, iters=300):
     except Exception as exc:          # reported, never fatal for the headline line
         out["cuda_graph_us_per_step"] = None
         out["cuda_graph_error"] = str(exc)[:200]
+    return out
+
+
+# ------------------------------------------------------------------------------------------- parity (driver-visible, every N)
+def parity_check(B, D, rank, b, loss_val, dls_val, dx1, dx2, dev, world):
+    """Compare this rank's results with the committed fp64 ground truth; all-reduce the worst case over the ranks."""
+    path = os.path.join(ROOT, "tests", "golden", f"bench_parity_b{B}.npz")
+    if D != 512 or not os.path.exists(path):
+        return None
+    ref = np.load(path)
+    blk = int(ref["block"])
+    lo, hi = rank * b, (rank + 1) * b
+    worst_rows = worst_norm = 0.0
+    rows = ref["rows"]
+    sel = (rows >= lo) & (rows < hi)
+    for dx, key in ((dx1, "dx1"), (dx2, "dx2")):
+        if sel.any():
+            got = dx[torch.from_numpy(rows[sel] - lo).to(dev)].double().cpu().numpy()
+            want = ref[key + "_rows"][sel].astype(np.float64)
+            worst_rows = max(worst_rows, float(np.linalg.norm(got - want) / np.linalg.norm(want)))
+        for k in range(lo // blk, hi // blk):       # (b is a multiple of the block for N <= 8)
+            n = float(dx[k * blk - lo:(k + 1) * blk - lo].double().norm().item())
+            want = float(ref[key + "_block_norm"][k])
+            worst_norm = max(worst_norm, abs(n - want) / want)
+    loss_rel = abs(loss_val - float(ref["loss"])) / abs(float(ref["loss"]))
+    dls_rel = abs(dls_val - float(ref["dlogit_scale"])) / abs(float(ref["dlogit_scale"]))
+    v = torch.tensor([loss_rel, dls_rel, worst_rows, worst_norm], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    loss_rel, dls_rel, worst_rows, worst_norm = (float(x) for x in v.tolist())
+    ok = loss_rel <= 1e-3 and dls_rel <= 1e-2 and worst_rows <= 1e-2 and worst_norm <= 1e-2
+    return {"loss_rel": loss_rel, "dls_rel": dls_rel, "grad_rel": worst_rows, "grad_block_norm_rel": worst_norm, "ok": bool(ok),
+            "bars": {"loss": 1e-3, "grad": 1e-2}, "rows_per_rank_checked": int(sel.sum()), "ranks": world,
+            "reference": "fp64 closed form of loss_head.py:271-283 on the same inputs (tests/golden/bench_parity_b%d.npz, "
+                         "oracle/make_bench_parity.py)" % B}
+
+
+# ------------------------------------------------------------------------------------------- same-box PyTorch eager baseline
+def eager_b200(dev, D, sizes=(32768, 512), steps=5):
+    """The reference's formula (loss_head.py:271-283: normalise, exp, BOTH logits matrices, 2 x CrossEntropyLoss, autograd)
+    executed by PyTorch eager on this B200 -- fp32 (TF32 off: torch's default for matmul) and under bf16 autocast.  This is
+    the same-hardware baseline; it materialises the B x B logits (2 x 4 GiB fp32 at 32768 plus softmax buffers)."""
+    out = {}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ce = torch.nn.CrossEntropyLoss()
+    try:
+        for B in sizes:
+            h1, h2 = make_inputs(B, D, 0, B)
+            x1, x2 = h1.to(dev).requires_grad_(True), h2.to(dev).requires_grad_(True)
+            ls = torch.tensor(math.log(1 / 0.07), device=dev, requires_grad=True)
+            labels = torch.arange(B, device=dev)
+
+            def step():
+                x1.grad = x2.grad = ls.grad = None
+                a = x1 / x1.norm(dim=-1, keepdim=True)
+                t = x2 / x2.norm(dim=-1, keepdim=True)
+                sc = ls.exp()
+                loss = ce(sc * a @ t.t(), labels) + ce(sc * t @ a.t(), labels)
+                loss.backward()
+                return loss
+
+            def amp():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return step()
+
+            rec = {}
+            for name, fn in (("fp32_ms", step), ("bf16_autocast_ms", amp)):
+                try:
+                    n = steps if B > 4096 else 100
+                    for _ in range(3):
+                        fn()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(n):
+                        loss = fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    rec[name] = e0.elapsed_time(e1) / n
+                    rec[name.replace("_ms", "_loss")] = float(loss)
+                except Exception as exc:      # e.g. out of memory for the materialised logits
+                    rec[name] = None
+                    rec[name.replace("_ms", "_error")] = str(exc)[:160]
+            out[f"B{B}"] = rec
+            del x1, x2
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
     return out
 
 
@@ -294,6 +393,7 @@ def main():
     barrier()
 
     lib.vpa_profile_enable(1)
+    launches0 = lib.vpa_launch_count()
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -304,6 +404,7 @@ def main():
         loss = step()
     e1.record()
     host_ms = (time.perf_counter() - th0) / args.steps * 1e3       # host enqueue time per step (no sync inside)
+    launches = int(lib.vpa_launch_count() - launches0)             # counted by the library at every launch site
     barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
@@ -314,6 +415,8 @@ def main():
         prof[name] = (tot.value, n.value)
     lib.vpa_profile_enable(0)
     loss_val = float(loss.item())
+    # ---- parity of the timed step's results against the committed fp64 ground truth (outside the timed region)
+    parity = parity_check(B, D, rank, b, loss_val, float(ls.grad.item()), x1.grad.detach(), x2.grad.detach(), dev, world)
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -371,7 +474,7 @@ def main():
                "loss": e2e_loss}
 
     if rank == 0:
-        pk = peaks()
+        pk = peaks(clocks)
         bwd_ms, bwd_n = prof["bwd_sweep"]
         fwd_ms, fwd_n = prof["fwd_sweep"]
         nrm_ms, nrm_n = prof["normalize"]
@@ -385,7 +488,8 @@ def main():
             flops = 6.0 * b * B * D                         # S recompute + dX1 + dX2 contractions
             ach = flops / (bwd_ms / bwd_n * 1e-3) / 1e12
             roofline = {"kernel": "pair_kernel<BWD> (tcgen05 cta_group::2)", "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
-                        "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
+                        "unit": "TFLOP/s", "frac": ach / pk["tflops"], "frac_burst": ach / pk["burst"],
+                        "frac_sustained": ach / pk["sustained"], "traffic": traffic, "peak_source": pk["source"],
                         "algorithmic_flops_per_launch": flops, "avg_launch_ms": bwd_ms / bwd_n, "launches": bwd_n}
         step_flops = 8.0 * b * B * D
         line = {
@@ -410,28 +514,39 @@ def main():
                              if prof["finalize"][1] else None, "peak_gbs": pk["hbm"]},
             "normalize_hbm": {"achieved_gbs": (2 * b * D * (4 + 2) + 12 * b) / (nrm_ms / max(nrm_n, 1) * 1e-3) / 1e9 if nrm_n else None,
                               "peak_gbs": pk["hbm"]},
-            "roofline": roofline, "clocks": clocks, "e2e": e2e,
-            # kernels of libvipant_b200.so per step: normalise, single-pass fwd, exact fwd (device-gated), column reduce / pack,
-            # merge+loss, bwd sweep, finalize (+ operand pull, 2 flag waits, d logit_scale sum on the peer-memory transport)
-            # (the separate column-reduce kernel only runs when a rank holds more than 256 32-row groups, i.e. b > 8192)
-            "gpu_launches": ({"local": 7, "p2p": 11, "nccl": 7, "host": 8}[transport] + (1 if b > 8192 else 0)) * args.steps,
+            "roofline": roofline, "clocks": clocks, "e2e": e2e, "parity": parity,
+            # kernels of libvipant_b200.so inside the timed region, counted by the library itself (vpa_launch_count).  Per step:
+            # normalise, single-pass forward (its first CTAs are the operand all-gather on the peer-memory transport), exact
+            # forward (device-gated), [column reduce when b > 8192], statistics (pack + merge; one kernel over peer memory),
+            # backward sweep, finalize (+ d logit_scale exchange)
+            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
         }
         if world == 1 and not args.no_e2e:
             try:
                 line["c2_batch512_latency"] = c2_latency(lib, dev)
             except Exception as exc:
                 line["c2_batch512_latency"] = {"error": str(exc)[:200]}
+        if world == 1 and not args.no_eager:
+            try:
+                line["eager_b200"] = eager_b200(dev, D)
+            except Exception as exc:
+                line["eager_b200"] = {"error": str(exc)[:200]}
         if not args.no_cpu_baseline and world == 1:
             cx1, cx2, cls_, cb, cores = cpu_block_sample(B, D)
-            times = run_cpu_steps(cx1, cx2, cls_, cb, 2)
+            run_cpu_steps(cx1, cx2, cls_, cb, 1)
+            times = run_cpu_steps(cx1, cx2, cls_, cb, 4)
             v = cb / float(np.mean(times))
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"row block of {cb} of the {B} global rows x2 steps (torch fp32 CPU port of "
-                                              f"loss_head.py:271-283 + autograd; 12*b*B*D flops = b/B of a full step)"}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+                                    "sample": f"fixed row block of {cb} of the {B} global rows, 4 steps after 1 warm-up (torch "
+                                              f"fp32 CPU port of loss_head.py:271-283 + autograd; 12*b*B*D flops = b/B of a "
+                                              f"full step), {cores} torch threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write(f"bench.py: PARITY FAILED on rank {rank}: {parity}\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

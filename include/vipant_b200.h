@@ -58,8 +58,10 @@ const char* vpa_last_error_string(void);
 #define VPA_PROF_RANK 4
 #define VPA_PROF_FWD_GENERAL 5 /* the exact two-sweep forward when the single-pass one is also enqueued */
 #define VPA_PROF_FINALIZE 6
-#define VPA_PROF_PUSH 7 /* peer-memory transport: the operand push kernel (side stream) */
+#define VPA_PROF_PUSH 7 /* peer-memory transport: the stand-alone operand relay kernel (shapes without the fused forward) */
 int vpa_profile_enable(int on);
+/* Kernel launches of this library since it was loaded (every launch site counts itself): bench.py's `gpu_launches`. */
+unsigned long long vpa_launch_count(void);
 /* Work decomposition chosen for a shape (diagnostics / tests; host only, no device needed): out10 = n_tiles, single-pass
  * forward {chunks, tiles per equal chunk, tiles of the short tail chunk}, backward {same three}, forward row blocks,
  * backward row blocks, impl (1 = CTA-pair kernels). */
@@ -185,7 +187,10 @@ int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int 
  *   sweeps -> per-rank message [column sums (B) | row_lse (b) | col_lse (b) | diag (b)] -> ONE all-gather ->
  *   statistics of all rows + the global loss (identical on every rank).  Everything the backward needs stays in `state`.
  * backward: recompute sweeps for the local rows, d(global loss)/d(local rows) into dx1 / dx2 (dtype / ld of x1 / x2),
- *   d logit_scale all-reduced over the ranks.
+ *   d logit_scale: dls_reduce != 0 -> summed over the ranks (the full derivative, identical on every rank); dls_reduce == 0
+ *   -> this rank's partial (the sum over its own rows), for trainers that reduce parameter gradients themselves: under
+ *   DistributedDataParallel (which AVERAGES) the feature gradients are per-rank partials too, so `loss * world` together with
+ *   the partial d logit_scale reproduces the single-process update exactly.
  * ------------------------------------------------------------------------------------------ */
 int vpa_comm_load(const char* libnccl_path);
 int vpa_comm_unique_id(void* out128);
@@ -202,40 +207,44 @@ int vpa_infonce_fwd_sharded(void* comm, const void* x1, const void* x2, int in_d
 int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t rows_local, int world,
                             int rank, int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
                             const float* grad_out, void* state, size_t state_bytes, void* dx1, void* dx2,
-                            float* dlogit_scale, void* stream);
+                            float* dlogit_scale, int dls_reduce, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * The same row-sharded step over NVLink PEER MEMORY instead of NCCL: the all-gather of the normalised operands is fused
- * with the forward sweep (the kernel starts on the local block and consumes the peers' rows, pushed 256-row chunk by
- * chunk by a side-stream kernel, as their system-scope arrival flags flip), and the statistics / d logit_scale
- * exchanges are plain stores into the peers' segments published with epoch flags.  No collective library call on the
- * data path; results are bitwise identical on every rank and to the NCCL transport.
+ * The same row-sharded step over NVLink PEER MEMORY instead of NCCL.  The all-gather of the normalised operands is FUSED INTO
+ * the forward kernel: the first CTAs of its grid are relays that pull the peers' rows with TMA bulk copies through a shared-
+ * memory ring (x2 operands first, 256-row chunks) and raise one arrival flag per chunk; the sweep CTAs of the same grid start
+ * on the local block and consume the peers' tiles as their flags flip.  The statistics exchange is one kernel (message into
+ * every peer, wait for R messages, merge, loss) and the d logit_scale exchange rides in the backward's finalize kernel: six
+ * launches per step, no collective library call on the data path; results are bitwise identical on every rank and to the
+ * NCCL transport.
  *
- * Setup (once per (rows_local, world, D, precision)): every rank calls vpa_p2p_create -- the library cudaMalloc's its
- * symmetric segment (gathered operands x 2 steps, messages, flags, workspace) and returns a 64-byte CUDA IPC handle --
- * the host exchanges the handles (e.g. torch.distributed all_gather, any backend), every rank calls vpa_p2p_connect with
- * the world x 64 bytes in rank order.  Ranks may share a device (tests) or own one each (peer access is enabled lazily).
- * world <= 8 (one NVSwitch node).  vpa_p2p_destroy synchronises the device and frees everything.
+ * Setup (once per (rows_local, world, D, precision) and call site): every rank calls vpa_p2p_create -- the library
+ * cudaMalloc's its symmetric segment (gathered operands x 2 steps, messages, flags, workspace) and returns a 64-byte CUDA IPC
+ * handle -- the host exchanges the handles (e.g. torch.distributed all_gather, any backend), every rank calls
+ * vpa_p2p_connect with the world x 64 bytes in rank order.  Ranks may share a device (tests) or own one each (peer access is
+ * enabled lazily).  world <= 8 (one NVSwitch node).  vpa_p2p_destroy synchronises the device and frees everything.
  *
  * vpa_infonce_fwd_p2p returns the step number in *epoch_out; pass it to vpa_infonce_bwd_p2p.  The segment keeps the two
- * most recent steps: a backward for an older step returns VPA_E_INVALID.  A peer that never arrives trips a device-side
- * timeout (8 s) and the kernel traps -- an error on the stream, not a hang.
+ * most recent steps: a backward for an older step returns VPA_E_INVALID (a module that runs several InfoNCE pairs per step
+ * uses one segment per pair).  A peer that never arrives trips a device-side timeout (8 s) and the kernel traps -- an error
+ * on the stream, not a hang.
  * ------------------------------------------------------------------------------------------ */
 int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision, void** p2p_out,
                    void* ipc_handle_out64);
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles /* world x 64 bytes, rank order */);
 int vpa_p2p_destroy(void* p2p);
 
-/* EXPERIMENTAL (VPA_P2P_MODE=nvls at vpa_p2p_create time; compiled, not yet exercised on hardware): the segment is backed by
- * VMM memory bound into one NVSwitch multicast object, and every exchange is a multimem.st (one store, all ranks).
- * vpa_p2p_mode: 0 push, 1 pull (default), 2 copy engines, 3 streaming push, 4 NVLS.  Setup in mode 4 replaces the IPC handle
- * exchange: rank 0 calls vpa_p2p_nvls_export and passes the POSIX file descriptor to the other ranks' processes (SCM_RIGHTS);
- * every rank calls vpa_p2p_nvls_attach (fd < 0 on rank 0); after a host barrier every rank calls vpa_p2p_nvls_bind, then
+/* VPA_P2P_MODE=nvls at vpa_p2p_create time: the segment is backed by VMM memory bound into one NVSwitch multicast object, and
+ * every exchange is a multimem.st (one store, all ranks): the relay CTAs store this rank's OWN rows once instead of pulling.
+ * vpa_p2p_mode: 1 TMA pull relay (default), 4 NVLS.  Setup in mode 4 replaces the IPC handle exchange: rank 0 calls
+ * vpa_p2p_nvls_export and passes the POSIX file descriptor to the other ranks' processes (SCM_RIGHTS); every rank calls
+ * vpa_p2p_nvls_attach (fd < 0 on rank 0); after a host barrier every rank calls vpa_p2p_nvls_bind, then
  * vpa_p2p_connect(p2p, NULL-able). */
 int vpa_p2p_mode(void* p2p);
-/* Diagnostics / tests (host only): the pull kernel's work-item map.  out5 = matrix (0: x2 operands, 1: x1), source rank, chunk
- * index, first row within the source's block, row count.  Items 0 .. n_matrices * chunks_per_rank * (world-1) * slices - 1. */
-int vpa_debug_pull_item(int item, int m0, int world, int me, int chunks_per_rank, int slices, int64_t rows_local, int* out5);
+/* Diagnostics / tests (host only): the relay CTAs' work-item map.  out5 = matrix (0: x2 operands, 1: x1), source rank, chunk
+ * index, first row within the source's block, row count.  Items 0 .. 2 * chunks_per_rank * (world-1) - 1; relay CTA k of n
+ * takes items k, k + n, ... */
+int vpa_debug_relay_item(int item, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5);
 int vpa_p2p_nvls_export(void* p2p, int* fd_out);
 int vpa_p2p_nvls_attach(void* p2p, int fd);
 int vpa_p2p_nvls_bind(void* p2p);
@@ -246,7 +255,7 @@ int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype,
 
 int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x2, int in_dtype, int64_t rows_local,
                         int world, int rank, int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
-                        const float* grad_out, void* dx1, void* dx2, float* dlogit_scale, void* stream);
+                        const float* grad_out, void* dx1, void* dx2, float* dlogit_scale, int dls_reduce, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (the end-to-end call timed as `e2e` in bench.py): pageable or

@@ -119,7 +119,7 @@ def test_peer_memory_entry_points_reject_bad_arguments(lib):
     p = ctypes.addressof(one)
     epoch = ctypes.c_uint32()
     assert lib.vpa_infonce_fwd_p2p(None, p, p, 0, 512, 2, 0, 512, 512, 512, 0, p, 0.0, 0, p, ctypes.byref(epoch), None) == -1
-    assert lib.vpa_infonce_bwd_p2p(None, 1, p, p, 0, 512, 2, 0, 512, 512, 512, 0, 0, p, p, p, p, None) == -1
+    assert lib.vpa_infonce_bwd_p2p(None, 1, p, p, 0, 512, 2, 0, 512, 512, 512, 0, 0, p, p, p, p, 1, None) == -1
 
 
 def test_transport_selection(monkeypatch):
@@ -153,30 +153,28 @@ def test_transport_selection(monkeypatch):
     assert F_._transport(object()) == "host"
 
 
-@pytest.mark.parametrize("world,b,slices", [(8, 4096, 4), (8, 4096, 1), (4, 8192, 4), (2, 16384, 4), (3, 384, 4), (2, 300, 8),
-                                            (4, 512, 16), (2, 64, 4), (5, 1000, 3)])
-def test_pull_items_cover_every_peer_row_once(lib, world, b, slices):
-    """The pull kernel's item map (the compiled pull_item_decode, evaluated on the host): every row of every peer block is
-    pulled exactly once per matrix, every chunk is made of exactly `slices` items (what its arrival counter counts), the
-    x2 operands come first and chunk k of all peers comes before chunk k+1 of any."""
+@pytest.mark.parametrize("world,b", [(8, 4096), (4, 8192), (2, 16384), (3, 384), (2, 300), (4, 512), (2, 64), (5, 1000)])
+def test_relay_items_cover_every_peer_row_once(lib, world, b):
+    """The relay CTAs' item map (the compiled relay_item_decode, evaluated on the host): every row of every peer block is
+    pulled exactly once per matrix, one item per 256-row chunk (what its arrival flag stands for), the x2 operands come
+    first and chunk k of all peers comes before chunk k+1 of any; out-of-range items are rejected."""
     cpr = -(-b // 256)
     out = (ctypes.c_int * 5)()
     for me in (0, world - 1):
-        total = 2 * cpr * (world - 1) * slices
+        total = 2 * cpr * (world - 1)
         seen = np.zeros((2, world, b), dtype=np.int32)
-        per_chunk = {}
+        chunks = set()
         order = []
         for item in range(total):
-            assert lib.vpa_debug_pull_item(item, 0, world, me, cpr, slices, b, out) == 0
+            assert lib.vpa_debug_relay_item(item, world, me, cpr, b, out) == 0
             m, src, c, row0, rows = list(out)
-            assert 0 <= m < 2 and 0 <= src < world and src != me and 0 <= c < cpr and rows >= 0
-            assert c * 256 <= row0 and row0 + rows <= min(b, (c + 1) * 256)
+            assert 0 <= m < 2 and 0 <= src < world and src != me and 0 <= c < cpr and rows >= 1
+            assert row0 == c * 256 and row0 + rows == min(b, (c + 1) * 256)
             seen[m, src, row0:row0 + rows] += 1
-            per_chunk[(m, src, c)] = per_chunk.get((m, src, c), 0) + 1
+            chunks.add((m, src, c))
             order.append((m, c))
         peers = [q for q in range(world) if q != me]
         assert np.all(seen[:, peers, :] == 1) and np.all(seen[:, me, :] == 0)
-        assert len(per_chunk) == 2 * (world - 1) * cpr and set(per_chunk.values()) == {slices}
+        assert len(chunks) == total
         assert order == sorted(order)                       # matrix-major, then chunk-major
-        # the second matrix alone (serial plan: m0 = 1) maps onto the same items
-        assert lib.vpa_debug_pull_item(0, 1, world, me, cpr, slices, b, out) == 0 and out[0] == 1 and out[2] == 0
+        assert lib.vpa_debug_relay_item(total, world, me, cpr, b, out) == -1

@@ -86,15 +86,15 @@ def _check(out, world, B, D, precision, env=None):
 
 
 # env: VPA_FWD1_CHUNKS=1 makes one CTA pair sweep ALL rank blocks (the chunk-major tile order over several peer blocks);
-# VPA_P2P_MODE=push / stream select the store-based operand transports instead of the default pull; VPA_P2P_PLAN=serial moves
-# the x2 operands before and the x1 operands after the forward sweep instead of overlapping them with it
+# VPA_P2P_RELAY_CTAS=2 leaves one relay CTA pair to move every chunk (long item lists, ring wrap-around); D = 128 / 384 and
+# fp32 take the stand-alone relay kernel (shapes without the fused forward); TEST_SCALE100 the exact two-sweep regime, in
+# which the fused kernel's sweep CTAs return at once and only its relays work
 @pytest.mark.parametrize("world,precision,B,D,env", [
     (2, "bf16", 1024, 512, None), (2, "bf16", 600, 256, None), (2, "fp32", 256, 128, None),
     (4, "bf16", 2048, 512, {"VPA_FWD1_CHUNKS": "1"}), (3, "bf16", 1152, 512, None),
-    (4, "bf16", 4096, 256, {"VPA_FWD1_CHUNKS": "2", "VPA_P2P_MODE": "push"}),
+    (4, "bf16", 4096, 256, {"VPA_FWD1_CHUNKS": "2", "VPA_P2P_RELAY_CTAS": "2"}),
     (2, "bf16", 1024, 512, {"TEST_SCALE100": "1"}),
-    (4, "bf16", 2048, 512, {"VPA_P2P_MODE": "stream", "VPA_FWD1_CHUNKS": "1"}),
-    (2, "bf16", 1024, 512, {"VPA_P2P_PLAN": "serial"})])
+    (2, "bf16", 640, 384, None), (3, "bf16", 768, 128, {"TEST_SCALE100": "1"})])
 def test_p2p_transport_ranks_sharing_one_gpu(world, precision, B, D, env):
     """The peer-memory transport (CUDA IPC segments, operand transfer + arrival flags consumed by the forward sweep,
     message and d logit_scale exchange by peer stores) between processes that share GPU 0: runs on a single-GPU box."""
@@ -117,12 +117,11 @@ def test_sharded_matches_global_batch(precision, B, D, transport):
 
 
 def test_nvls_multicast_transport_two_gpus():
-    """EXPERIMENTAL transport (VPA_P2P_MODE=nvls): segment bound into an NVSwitch multicast object, every exchange a
-    multimem.st.  Needs 2 GPUs behind an NVSwitch; VIPANT_REQUIRE_P2P turns a failed setup into an error instead of the
-    NCCL fallback."""
+    """VPA_P2P_MODE=nvls: segment bound into an NVSwitch multicast object, every exchange a multimem.st.  Needs 2 GPUs behind
+    an NVSwitch; VIPANT_REQUIRE_P2P turns a failed setup into an error instead of the NCCL fallback."""
     world = 2
     if not os.environ.get("VIPANT_TEST_NVLS"):
-        pytest.skip("experimental transport, not yet brought up on hardware: opt in with VIPANT_TEST_NVLS=1")
+        pytest.skip("opt in with VIPANT_TEST_NVLS=1 (needs an NVSwitch fabric with multicast enabled)")
     if torch.cuda.device_count() < world:
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()

@@ -135,3 +135,23 @@ def test_rank_and_topk_tie_semantics():
     assert ro.rank_of(S, np.array([[3]]))[0, 0] == 3
     idx, val = ro.topk(S, 3)
     assert idx.tolist() == [[1, 2, 4]] and val.tolist() == [[3.0, 3.0, 3.0]]
+
+
+def test_bench_parity_fixture_generator_matches_closed_form():
+    """oracle/make_bench_parity.py (the fp64 ground truth bench.py's `parity` object is checked against) evaluates the
+    logits blockwise; on a size the dense closed form handles it must give the same numbers, and the committed
+    B = 32768 fixture must be the one the generator's sampling scheme describes."""
+    import torch
+    from oracle import make_bench_parity as mb
+    x1n, x2n = io.make_pair(640, 512, 0.3, 1213)
+    ref = io.infonce_closed_form(x1n.astype(np.float64), x2n.astype(np.float64), float(np.float32(np.log(1 / 0.07))))
+    loss, dls, dx1, dx2 = mb.blockwise_truth(torch.from_numpy(x1n), torch.from_numpy(x2n), rb=256)
+    # (the generator takes s = expf(fp32 parameter) as the kernels do, the closed form exp() in double: 1e-8 apart)
+    assert abs(loss - ref.loss) < 1e-6 * abs(ref.loss)
+    assert abs(dls - ref.dlogit_scale) < 1e-6 * abs(ref.dlogit_scale)
+    assert np.linalg.norm(dx1.numpy() - ref.dx1) < 1e-6 * np.linalg.norm(ref.dx1)
+    assert np.linalg.norm(dx2.numpy() - ref.dx2) < 1e-6 * np.linalg.norm(ref.dx2)
+    fx = np.load(os.path.join(GOLDEN, "bench_parity_b32768.npz"))
+    assert int(fx["B"]) == 32768 and int(fx["block"]) == mb.BLOCK
+    assert np.array_equal(fx["rows"], mb.sample_rows(32768)) and fx["dx1_rows"].shape == (8 * mb.SAMPLES, 512)
+    assert fx["dx1_block_norm"].shape == (8,) and abs(float(fx["loss"]) - 9.96007) < 1e-4

@@ -20,6 +20,7 @@ _SIGNATURES = {
     "vpa_last_error_string": (c_char_p, []),
     "vpa_plan_query": (c_int, [c_int64, c_int64, c_int, c_int, POINTER(c_int)]),
     "vpa_profile_enable": (c_int, [c_int]),
+    "vpa_launch_count": (ctypes.c_ulonglong, []),
     "vpa_profile_read": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),
     "vpa_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_normalize_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int,
@@ -45,19 +46,19 @@ _SIGNATURES = {
     "vpa_infonce_fwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
                                         c_void_p, c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vpa_infonce_bwd_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
-                                        c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vpa_p2p_create": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p]),
     "vpa_p2p_connect": (c_int, [c_void_p, c_void_p]),
     "vpa_p2p_destroy": (c_int, [c_void_p]),
     "vpa_p2p_mode": (c_int, [c_void_p]),
-    "vpa_debug_pull_item": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, POINTER(c_int)]),
+    "vpa_debug_relay_item": (c_int, [c_int, c_int, c_int, c_int, c_int64, POINTER(c_int)]),
     "vpa_p2p_nvls_export": (c_int, [c_void_p, POINTER(c_int)]),
     "vpa_p2p_nvls_attach": (c_int, [c_void_p, c_int]),
     "vpa_p2p_nvls_bind": (c_int, [c_void_p]),
     "vpa_infonce_fwd_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
                                     c_void_p, c_float, c_int, c_void_p, POINTER(c_uint32), c_void_p]),
     "vpa_infonce_bwd_p2p": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64,
-                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vpa_sim_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vpa_sim_rank_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

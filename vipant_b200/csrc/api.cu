@@ -25,6 +25,9 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;      // kernel launches of this library since it was loaded (not thread-safe: a statistic)
+void note_launch() { ++g_launches; }
+
 // ---- opt-in launch timing ---------------------------------------------------------------------------
 constexpr int kProfSlots = 512;
 struct ProfState {
@@ -66,39 +69,52 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
                          cudaStream_t st);
 int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
                       float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart, float* msg,
-                      const P2PStep* p2p, cudaStream_t st);
+                      cudaStream_t st);
 int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
-                       float* stats_all, float* scale_out, const P2PStep* p2p, double* loss_part, uint32_t* loss_counter,
-                       float* loss_out, cudaStream_t st);
+                       float* stats_all, float* scale_out, double* loss_part, uint32_t* loss_counter, float* loss_out,
+                       cudaStream_t st);
+int exchange_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
+                          float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart,
+                          const P2PStep& p2p, float* loss_out, cudaStream_t st);
 int loss_launch(const float* row_lse, const float* col_lse, const float* diag, int64_t B, float* loss,
                 cudaStream_t st);
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
                         const float* scale, const float* grad_out, const void* x1, const void* x2,
                         int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
-                        int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, cudaStream_t st);
+                        int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, int dls_sum,
+                        cudaStream_t st);
 int diag_cos_bf16_launch(const void* a_bf16, const void* t_bf16, int64_t rows, int D, float* diag_cos, cudaStream_t st);
 int sim_rank_topk_launch(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
                          const int32_t* gt_idx, int g, int k, int64_t* topk_idx, float* topk_val,
                          int32_t* ranks, float* S, cudaStream_t st);
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else
-      n = 148;   // B200
-    cudaGetLastError();
+static int sm_count() {      // of the CURRENT device (a process may drive several)
+  static int cached[64] = {};
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }      // CPU-only box (plan queries): B200
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); return 148; }
+  if (dev >= 0 && dev < 64) cached[dev] = v;
+  return v;
+}
+
+// Relay CTAs of the peer-memory transport (whole CTA pairs in front of the single-pass forward's grid, p2p.cuh): the sharded
+// forward plans its units on the SM pairs they leave free.
+int relay_ctas_default() {
+  static int v = 0;
+  if (v == 0) {
+    v = 20;
+    if (const char* e = getenv("VPA_P2P_RELAY_CTAS")) { const int q = atoi(e); if (q >= 2 && q <= 64) v = q & ~1; }   // tuning knob
   }
-  return n;
+  return v;
 }
 
 // Number of column chunks that minimises (waves x per-unit length) for `base_units` row-block units
 // sweeping `n_tiles` tiles; `fixed` = per-unit fixed cost in tile equivalents (X load, drain).
-static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int sms_per_unit = 1) {
-  const int sms = sm_count() / sms_per_unit;
+static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int sms_per_unit = 1,
+                        int reserved_sms = 0) {
+  int sms = (sm_count() - reserved_sms) / sms_per_unit;
+  if (sms < 1) sms = 1;
   long best_cost = -1;
   int best_c = 1;
   const int cmax = n_tiles < 64 ? n_tiles : 64;
@@ -156,8 +172,8 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
 // The split search costs milliseconds: plans are computed once per shape.
 SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision) {
   static std::mutex mu;
-  static std::map<std::tuple<int64_t, int64_t, int, int>, SweepPlan> cache;
-  const auto key = std::make_tuple(rows_local, rows_global, D, precision);
+  static std::map<std::tuple<int64_t, int64_t, int, int, int>, SweepPlan> cache;
+  const auto key = std::make_tuple(rows_local, rows_global, D, precision, sm_count());
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -181,7 +197,6 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
   }
   p.rows_per_blk = 128;
   p.impl = (D == 256 || D == 512) ? 1 : 0;
-  if (const char* e = getenv("VPA_TC_IMPL")) p.impl = (atoi(e) == 1 && (D == 256 || D == 512)) ? 1 : 0;   // A/B knob
   if (p.impl == 1) {
     p.cluster = 2;
     p.halves = 1;
@@ -191,17 +206,15 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
     p.n_tiles = (int)((rows_global + 255) / 256);
     pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
     // per-unit fixed cost (prologue, X load, pipeline fill, dX drain) measured at ~3.5 tiles of 256 columns (b=4096 sweep)
-    const bool uneven = !getenv("VPA_EVEN_CHUNKS");                                 // A/B knob: equal chunks only
-    if (uneven) pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small);
-    else pick_chunks(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, 2);
+    pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small);
     p.fast_fwd = 1;
-    if (const char* e = getenv("VPA_FAST_FWD")) p.fast_fwd = atoi(e) != 0;          // A/B knob
     // A row-sharded forward consumes operand rows while they arrive from the peers: it is gated by the transfer, not by
     // the tensor cores, and a second wave of tail units (which the LPT split adds) only starts when the first wave ends --
-    // measured at N = 8: forward sweep 0.178 ms with equal chunks in one wave, 0.193 ms with the split.  Equal chunks there.
+    // measured at N = 8: forward sweep 0.178 ms with equal chunks in one wave, 0.193 ms with the split.  Equal chunks there,
+    // planned on the SM pairs the relay CTAs leave free.
     const bool sharded = rows_local < rows_global;
-    if (uneven && !sharded) pick_split(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, &p.fwd1_small);
-    else pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2);
+    if (!sharded) pick_split(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, &p.fwd1_small);
+    else pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2, relay_ctas_default());
     p.n_rowgroups = p.pair_fwd_iblk * 8;
     auto force = [&](const char* name, int* chunks, int* tpc, int* small) {     // tuning knobs for measurements
       if (const char* e = getenv(name)) {
@@ -284,6 +297,8 @@ int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision
   return 0;
 }
 
+unsigned long long vpa_launch_count(void) { return g_launches; }
+
 int vpa_profile_enable(int on) {
   g_prof.on = on != 0;
   for (int k = 0; k < PROF_KINDS; ++k) g_prof.n[k] = 0;
@@ -329,7 +344,8 @@ size_t vpa_infonce_colsum_floats(int64_t rows_global) { return rows_global > 0 ?
 static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
                           int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
                           float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, bool allow_fast,
-                          int parts, cudaStream_t st, const P2PRowFlags* yflags = nullptr, bool reduce_cols = true) {
+                          int parts, cudaStream_t st, const P2PRowFlags* yflags = nullptr, bool reduce_cols = true,
+                          const RelayArgs* relay = nullptr) {
   // reduce_cols == false: the caller reduces the single-pass column partials itself (pack_stats); col_sum is not touched
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && workspace, "infonce_fwd_sweep: null pointer");
@@ -342,6 +358,7 @@ static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_al
   a.logit_scale = logit_scale;
   a.scale_cap = (scale_max > 0.f) ? scale_max : INFINITY;     // `cfg.scale_max or float("inf")`
   if (yflags) a.yflags = *yflags;
+  a.relay = relay;
   float* cs = col_sum ? col_sum : ws.colsum;
   const bool fast = precision == VPA_PREC_BF16_TC && plan.impl == 1 && plan.fast_fwd && allow_fast;
   if (parts & 1) {
@@ -416,7 +433,7 @@ static int bwd_impl(const void* a_loc, const void* t_loc, const void* a_all, con
                     const float* row_lse_all, const float* col_lse_all, const float* grad_out, const void* x1,
                     const void* x2, int in_dtype, int64_t ld1, int64_t ld2, const float* inv_norm1,
                     const float* inv_norm2, int already_normalized, void* workspace, size_t workspace_bytes,
-                    void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, void* stream) {
+                    void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, int dls_sum, void* stream) {
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && scale && row_lse_all && col_lse_all && grad_out && dx1 && dx2 && workspace,
                 "infonce_bwd: null pointer");
@@ -436,7 +453,7 @@ static int bwd_impl(const void* a_loc, const void* t_loc, const void* a_all, con
   if (int e = (precision == VPA_PREC_BF16_TC) ? (plan.impl == 1 ? pair_infonce_bwd(a, ws, plan, st) : tc_infonce_bwd(a, ws, plan, st))
                                               : simt_infonce_bwd(a, ws, plan, st)) return e;
   return finalize_bwd_launch(ws, plan, rows_local, D, scale, grad_out, x1, x2, in_dtype, ld1, ld2, inv_norm1, inv_norm2,
-                             already_normalized, dx1, dx2, dlogit_scale, p2p, st);
+                             already_normalized, dx1, dx2, dlogit_scale, p2p, dls_sum, st);
 }
 
 int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, const void* t_all, int precision,
@@ -447,7 +464,7 @@ int vpa_infonce_bwd(const void* a_loc, const void* t_loc, const void* a_all, con
                     void* dx1, void* dx2, float* dlogit_scale, void* stream) {
   return bwd_impl(a_loc, t_loc, a_all, t_all, precision, rows_local, rows_global, D, row_offset, scale, row_lse_all,
                   col_lse_all, grad_out, x1, x2, in_dtype, ld1, ld2, inv_norm1, inv_norm2, already_normalized, workspace,
-                  workspace_bytes, dx1, dx2, dlogit_scale, nullptr, stream);
+                  workspace_bytes, dx1, dx2, dlogit_scale, nullptr, 0, stream);
 }
 
 size_t vpa_sim_workspace_bytes(int64_t N, int64_t M) {
@@ -583,19 +600,19 @@ int vpa_infonce_fwd_sharded(void* comm, const void* x1, const void* x2, int in_d
                              h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
   const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
   const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
-  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, from_colpart, h.msg, nullptr, st)) return e;
+  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, from_colpart, h.msg, st)) return e;
   if (world > 1) {
     if (int e = comm_all_gather(comm, h.msg, h.msgs, (size_t)(B + 3 * b), 7, st)) return e;
   }
   // statistics of all rows + the global loss in one kernel
-  return merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, nullptr, h.loss_part,
-                            h.loss_counter, loss_out, st);
+  return merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, h.loss_part, h.loss_counter,
+                            loss_out, st);
 }
 
 int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank,
                             int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
                             const float* grad_out, void* state, size_t state_bytes, void* dx1, void* dx2,
-                            float* dlogit_scale, void* stream) {
+                            float* dlogit_scale, int dls_reduce, void* stream) {
   VPA_CHECK_ARG(world >= 1 && rank >= 0 && rank < world && (world == 1 || comm), "bwd_sharded: bad world / rank / comm");
   const int64_t B = b * world, off = (int64_t)rank * b;
   VPA_CHECK_ARG(state && grad_out && dx1 && dx2 && dlogit_scale, "bwd_sharded: null pointer");
@@ -608,7 +625,7 @@ int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_d
   if (int e = vpa_infonce_bwd(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B,
                               grad_out, x1, x2, in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes,
                               dx1, dx2, dlogit_scale, st)) return e;
-  if (world > 1) return comm_all_reduce_sum_f32(comm, dlogit_scale, dlogit_scale, 1, st);
+  if (world > 1 && dls_reduce) return comm_all_reduce_sum_f32(comm, dlogit_scale, dlogit_scale, 1, st);
   return 0;
 }
 
@@ -620,11 +637,11 @@ int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles) { return p2p_connect(p2p, all_ipc_handles); }
 int vpa_p2p_destroy(void* p2p) { return p2p_destroy(p2p); }
 int vpa_p2p_mode(void* p2p) { return p2p_mode(p2p); }
-// the pull kernel's item -> (matrix, source rank, chunk, first row, rows) map, evaluated on the host (tests)
-int vpa_debug_pull_item(int item, int m0, int world, int me, int chunks_per_rank, int slices, int64_t rows_local, int* out5) {
-  VPA_CHECK_ARG(out5 && world >= 2 && me >= 0 && me < world && chunks_per_rank >= 1 && slices >= 1 && rows_local >= 1 && item >= 0,
-                "debug_pull_item: bad argument");
-  const PullItem it = pull_item_decode(item, m0, world, me, chunks_per_rank, slices, rows_local);
+// the relay CTAs' item -> (matrix, source rank, chunk, first row, rows) map, evaluated on the host (tests)
+int vpa_debug_relay_item(int item, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5) {
+  VPA_CHECK_ARG(out5 && world >= 2 && me >= 0 && me < world && chunks_per_rank >= 1 && rows_local >= 1 && item >= 0 &&
+                item < 2 * chunks_per_rank * (world - 1), "debug_relay_item: bad argument");
+  const RelayItem it = relay_item_decode(item, world, me, chunks_per_rank, rows_local);
   out5[0] = it.m; out5[1] = it.src; out5[2] = it.c; out5[3] = it.row0; out5[4] = it.rows;
   return 0;
 }
@@ -647,36 +664,33 @@ int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype,
   const size_t es = tcp ? 2 : 4;
   char* a_loc = static_cast<char*>(h.a_all) + (size_t)off * D * es;
   char* t_loc = static_cast<char*>(h.t_all) + (size_t)off * D * es;
-  if (int e = p2p_join_push(p2p, st)) return e;          // an earlier push still reading this rank's block
   if (int e = normalize_pair_launch(x1, x2, in_dtype, b, D, ld1, ld2, already_normalized, tcp ? a_loc : nullptr,
                                     tcp ? t_loc : nullptr, tcp ? nullptr : (float*)a_loc, tcp ? nullptr : (float*)t_loc,
                                     h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
-  if (int e = p2p_push_operands(p2p, epoch, st)) return e;      // side stream: x2 operand chunks first, then x1
-  // single-pass kernel: starts on the local block, consumes the peers' x2 rows chunk by chunk as their flags flip
   const SweepPlan plan = plan_sweep(b, B, D, precision);
   const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
   const bool from_colpart = pack_reduces_columns(plan, precision);
-  if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, 1, st, &h.yflags, !from_colpart)) return e;
-  if (int e = p2p_pull_rest(p2p, epoch, st)) return e;          // (serial plan only: x1 operands after the forward sweep)
-  // The exact two-sweep kernel (other regime) also reads the peers' x1 operands: wait for everything, but only then.  In
-  // the single-pass regime nothing of the forward needs them -- their transfer keeps overlapping the statistics exchange
-  // and the backward waits for it.
   const bool single_pass = tcp && plan.impl == 1 && plan.fast_fwd;
-  if (int e = p2p_wait_operands(p2p, epoch, single_pass ? logit_scale : nullptr, (scale_max > 0.f) ? scale_max : INFINITY, st)) return e;
+  if (single_pass) {
+    // ONE kernel is the all-gather and the contraction: its first CTAs relay the peers' rows (x2 operands first, then the
+    // x1 operands the backward needs), its sweep CTAs start on the local block and consume remote tiles as their flags flip.
+    // When it has finished, every operand of the step has landed.
+    if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
+                               h.colsum8, true, 1, st, &h.yflags, !from_colpart, &h.relay)) return e;
+  } else {
+    if (int e = p2p_relay_standalone(p2p, epoch, st)) return e;
+  }
+  // the exact two-sweep kernel (other temperature regime / other shapes); device-gated when the single-pass kernel exists
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
-  const int fast = (tcp && plan.impl == 1 && plan.fast_fwd) ? 1 : 0;
+                             h.colsum8, true, single_pass ? 2 : 3, st, nullptr, !from_colpart)) return e;
   const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
-  if (int e = pack_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, fast, h.colsum8, from_colpart, nullptr, &h, st)) return e;
-  // waits for every rank's message, then statistics of all rows + the global loss in one kernel
-  return merge_stats_launch(h.msgs, world, b, B, logit_scale, cap, fast, h.stats_all, h.scale, &h, h.loss_part, h.loss_counter,
-                            loss_out, st);
+  // message out, every rank's message in, statistics of all rows + the global loss
+  return exchange_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, single_pass ? 1 : 0, h.colsum8, from_colpart, h, loss_out, st);
 }
 
 int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x2, int in_dtype, int64_t b, int world,
                         int rank, int D, int64_t ld1, int64_t ld2, int already_normalized, int precision,
-                        const float* grad_out, void* dx1, void* dx2, float* dlogit_scale, void* stream) {
+                        const float* grad_out, void* dx1, void* dx2, float* dlogit_scale, int dls_reduce, void* stream) {
   const int64_t B = b * world, off = (int64_t)rank * b;
   VPA_CHECK_ARG(grad_out && dx1 && dx2 && dlogit_scale, "bwd_p2p: null pointer");
   if (int e = p2p_check(p2p, b, world, rank, D, precision)) return e;
@@ -684,17 +698,13 @@ int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x
   VPA_CHECK_ARG(epoch != 0 && cur - epoch <= 1u,
                 "bwd_p2p: the forward of step %u is no longer resident (current step %u; the segment keeps two steps)", epoch, cur);
   const P2PStep h = p2p_step(p2p, epoch);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
   const char* a_loc = static_cast<const char*>(h.a_all) + (size_t)off * D * es;
   const char* t_loc = static_cast<const char*>(h.t_all) + (size_t)off * D * es;
-  if (cur == epoch) {       // (a later forward has already waited for this step's transfer: stream order)
-    if (int e = p2p_wait_operands(p2p, epoch, nullptr, INFINITY, st)) return e;      // all operands of the peers have landed
-  }
-  if (int e = bwd_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B,
-                       grad_out, x1, x2, in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes, dx1, dx2,
-                       dlogit_scale, &h, st)) return e;
-  return p2p_dls_sum(h, dlogit_scale, st);
+  // (the forward's kernels on this stream have gathered every operand; finalize_bwd exchanges the d logit_scale partials)
+  return bwd_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B, grad_out, x1, x2,
+                  in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes, dx1, dx2, dlogit_scale, &h,
+                  dls_reduce ? 1 : 0, stream);
 }
 
 // ---- host-buffer end-to-end step ---------------------------------------------------------------------
@@ -853,17 +863,17 @@ int vpa_infonce_step_host(const float* x1_host, const float* x2_host, int64_t ro
                                h.ws[k], h.ws_bytes, h.colsum8, true, 2, st, nullptr, !from_colpart)) return e;
     const Workspace ws = carve_workspace(h.ws[k], b, rows, D, plan);
     if (int e = pack_stats_launch(ws, plan, b, rows, h.lsc, cap, h.dcos + off, 1, h.colsum8, from_colpart,
-                                  h.msgs + (size_t)k * (rows + 3 * b), nullptr, st)) return e;
+                                  h.msgs + (size_t)k * (rows + 3 * b), st)) return e;
   }
-  if (int e = merge_stats_launch(h.msgs, V, b, rows, h.lsc, cap, 1, h.stats_all, h.sc, nullptr, h.loss_part, h.loss_counter,
-                                 h.loss, st)) return e;
+  if (int e = merge_stats_launch(h.msgs, V, b, rows, h.lsc, cap, 1, h.stats_all, h.sc, h.loss_part, h.loss_counter, h.loss,
+                                 st)) return e;
   // ---- backward, shard by shard; gradients leave on the copy-out stream while the next shard computes
   for (int k = 0; k < V; ++k) {
     const int64_t off = (int64_t)k * b;
     if (int e = bwd_impl(ab + off * D * 2, tb + off * D * 2, h.ab, h.tb, precision, b, rows, D, off, h.sc, h.stats_all,
                          h.stats_all + rows, h.gout, h.x1 + k * shard_elems, h.x2 + k * shard_elems, VPA_F32, D, D,
                          h.inv1 + off, h.inv2 + off, 0, h.ws[k], h.ws_bytes, h.dx1 + k * shard_elems, h.dx2 + k * shard_elems,
-                         h.dls + k, nullptr, st)) return e;
+                         h.dls + k, nullptr, 0, st)) return e;
     VPA_CUDA(cudaEventRecord(hp->bwd_done[k], st));
     VPA_CUDA(cudaStreamWaitEvent(hp->cout, hp->bwd_done[k], 0));
     if (dx1_host) VPA_CUDA(cudaMemcpyAsync(dx1_host + k * shard_elems, h.dx1 + k * shard_elems, shard_bytes, cudaMemcpyDeviceToHost, hp->cout));

@@ -25,8 +25,11 @@ int set_error(int code, const char* fmt, ...);
       return ::vpa::set_error((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
   } while (0)
 
+void note_launch();      // api.cu: every kernel launch of the library is counted (vpa_launch_count)
+
 #define VPA_LAUNCH_CHECK(name)                                                              \
   do {                                                                                      \
+    ::vpa::note_launch();                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                   \
     if (e__ != cudaSuccess)                                                                 \
       return ::vpa::set_error((int)e__, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
@@ -106,6 +109,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: a process that drives several GPUs (the
+// reference's `dp` mode is single-process multi-GPU) must set it on each.  One cache per call site, indexed by device.
+struct SmemAttrCache { bool done[64] = {}; };
+template <typename F>
+inline int ensure_dynamic_smem(SmemAttrCache& cache, F func, int bytes) {
+  int dev = 0;
+  VPA_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && cache.done[dev]) return 0;
+  VPA_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev >= 0 && dev < 64) cache.done[dev] = true;
+  return 0;
+}
+
 // ---- NCCL binding (comm.cu) ----------------------------------------------------------------
 struct ncclUniqueIdBlob { char internal[128]; };
 int comm_load(const char* path);
@@ -137,6 +153,7 @@ struct SweepPlan {
 };
 constexpr int kColSumSplit = 8;   // column sums are reduced to [kColSumSplit][rows_global] (fixed order) before any all-reduce
 SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision);
+int relay_ctas_default();      // relay CTAs of the peer-memory transport (api.cu)
 
 // Scratch layout shared by both precisions.
 struct Workspace {
@@ -169,13 +186,13 @@ struct SweepArgs {
   const float* lse_x[2];       // backward: lse of the X rows' direction, GLOBAL vector (rows_global)
   const float* lse_y[2];       // backward: lse of the other direction, GLOBAL vector
   P2PRowFlags yflags;          // single-pass forward over peer memory: arrival flags of y[0]'s rows (zero: none)
+  const struct RelayArgs* relay;   // single-pass forward over peer memory: relay CTAs in front of the grid (p2p.cuh; nullptr: none)
 };
 
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int tc_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int which, cudaStream_t st);
 float pair_fast_s2_limit();
-int pair_fwd1_regs_per_cta();
 int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int simt_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);

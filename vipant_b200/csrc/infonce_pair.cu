@@ -64,6 +64,7 @@ struct Params {
   int gate;                 // 0: always run; 1: run only if s*log2e <= kFastS2Limit; 2: run only if it is larger
   float* colpart;           // FWD1: float[n_iblk*8][n_y] column sums of exp2(S*s2 - s2) per 32-row group
   P2PRowFlags yflags;       // FWD1 over peer memory: arrival flags of the Y rows (nullptr: everything is already there)
+  RelayArgs relay;          // FWD1 over peer memory: the first relay.n_ctas CTAs of the grid are the operand all-gather (p2p.cuh)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -231,7 +232,16 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
-  if (sbase - smem_u32(smem_raw) + L.total > (MODE == MODE_FWD1 ? L.total + 1024 : kSmemLimit)) asm volatile("trap;");     // alignment pad does not fit
+  if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
+  if (MODE == MODE_FWD1 && (int)blockIdx.x < P.relay.n_ctas) {
+    // Relay CTAs: the all-gather of the operand rows over NVLink, in the same grid as the sweep that consumes them.  They
+    // come first in blockIdx order, i.e. they are resident before any sweep CTA that polls their flags, and they run in
+    // both temperature regimes (the exact forward and the backward read the gathered rows too).
+    if (blockIdx.x == 0) relay_signal_ready(P.relay);
+    if (P.relay.multicast) relay_multicast(P.relay, blockIdx.x);
+    else relay_pull(P.relay, blockIdx.x, sptr);
+    return;
+  }
   if (P.gate != 0) {       // regime gate on the DEVICE value of the temperature (no host sync): uniform over the grid
     const float gs2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
     if ((P.gate == 1) != (gs2 <= kFastS2Limit)) return;
@@ -240,7 +250,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
   const bool is_leader = crank == 0;
 
-  int u = blockIdx.x >> 1;                             // pair index
+  int u = ((int)blockIdx.x - (MODE == MODE_FWD1 ? P.relay.n_ctas : 0)) >> 1;      // pair index (after the relay CTAs)
   int prob_, chunk_, iblk_, tile0_, nt_;
   {
     const int per = P.n_iblk * P.n_big, big_units = P.n_prob * per;
@@ -745,6 +755,8 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.gate = gate;
   P.colpart = ws.colpart;
   if (fwd1) P.yflags = a.yflags;
+  if (fwd1 && a.relay) P.relay = *a.relay;
+  static_assert(kRelaySmemBytes + 1024 <= kSmemLimit, "the relay ring must fit into the forward kernel's shared memory");
   for (int p = 0; p < 2; ++p) {
     P.p[p].n_x = (int)a.rows_local;
     P.p[p].n_y = (int)a.rows_global;
@@ -761,18 +773,11 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   }
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (L.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", L.total);
-  // the layout plus whatever pad aligns the dynamic base to 1024 B.  The single-pass forward asks for 2 KB less than the
-  // SM has: a CTA of the operand push kernel (p2p.cu, no shared memory of its own, 1 KB system reservation) must be able
-  // to become resident beside it, or ranks waiting for each other's rows could starve the kernels that deliver them.
-  const uint32_t dyn_smem = fwd1 ? L.total + 1024 : kSmemLimit;
-  if (fwd1 && dyn_smem > kSmemLimit - 1024) return set_error(VPA_E_UNSUPPORTED, "single-pass forward: %u bytes of shared memory leave no room for the push kernel", dyn_smem);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[MODE]) {
-    VPA_CUDA(cudaFuncSetAttribute(pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    attr_set[MODE] = true;
-  }
+  const uint32_t dyn_smem = kSmemLimit;      // the layout plus whatever pad aligns the dynamic base to 1024 B
+  static SmemAttrCache attr_cache[3];
+  if (int e = ensure_dynamic_smem(attr_cache[MODE], pair_kernel<MODE>, (int)kSmemLimit)) return e;
   // FWD1 sweeps one problem only (local x1 rows against all x2 rows)
-  dim3 grid((fwd1 ? 1 : 2) * 2 * P.pairs_per_problem), block(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd);
+  dim3 grid((fwd1 ? 1 : 2) * 2 * P.pairs_per_problem + P.relay.n_ctas), block(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd);
   const int kind = bwd ? PROF_BWD_SWEEP : (fwd1 ? PROF_FWD_SWEEP : (gate == 2 ? PROF_FWD_GENERAL : PROF_FWD_SWEEP));
   prof_begin(kind, st);
   pair_kernel<MODE><<<grid, block, dyn_smem, st>>>(maps[0], maps[1], maps[2], maps[3], P);
@@ -795,15 +800,5 @@ int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& p
   return pr::launch<pr::MODE_BWD>(a, ws, plan, 0, st);
 }
 float pair_fast_s2_limit() { return pr::kFastS2Limit; }
-
-// registers one resident CTA of the single-pass forward takes (allocation granularity: 8 per thread); 0 if unknown
-int pair_fwd1_regs_per_cta() {
-  cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, pr::pair_kernel<pr::MODE_FWD1>) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return (fa.numRegs + 7) / 8 * 8 * pr::kThreadsBwd;
-}
 
 }  // namespace vpa

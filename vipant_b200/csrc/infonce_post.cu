@@ -74,41 +74,51 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
   if (p == 0 && diag) diag[row] = s * diag_cos[row];
 }
 
-// ---- row-sharded step: the per-rank message around the ONE statistics all-gather --------------------------------
+// ---- row-sharded step: the per-rank message around the ONE statistics exchange -----------------------------------
 // msg = [ col_sum (B) | row_lse (b) | col_lse_local (b) | diag (b) ]:  col_sum = this rank's column sums over its own
 // rows (single-pass regime; zero otherwise), col_lse_local = column lse of the local rows (exact regime; zero otherwise).
-__global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks, int n_chunks_fast, int64_t b, int64_t B,
-                                  const float* __restrict__ logit_scale, float scale_cap,
-                                  const float* __restrict__ diag_cos, int fast, float s2_limit,
-                                  const float* __restrict__ colsum8, const float* __restrict__ colpart, int n_groups,
-                                  float* __restrict__ msg, const P2PView pv,
-                                  size_t off_msgs, size_t off_msg_flags, uint32_t* __restrict__ pack_counter) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const float s = fminf(expf(*logit_scale), scale_cap);
+struct PackArgs {
+  const float2* part;
+  int n_chunks, n_chunks_fast;
+  int64_t b, B;
+  const float* logit_scale;
+  float scale_cap;
+  const float* diag_cos;
+  int fast;
+  float s2_limit;
+  const float* colsum8;
+  const float* colpart;
+  int n_groups;
+  float* msg;               // local message buffer (NCCL / single-GPU); peer-memory transport: stores go to every rank's msgs[rank]
+  P2PView pv;
+  size_t off_msgs, off_msg_flags;
+  uint32_t* pack_counter;
+};
+__device__ __forceinline__ void pack_one(const PackArgs& A, int64_t idx, float s, bool fastr) {
+  const int64_t b = A.b, B = A.B;
   const float s2 = s * kLog2e;
-  const bool fastr = fast && s2 <= s2_limit;
-  const bool p2p = pv.world > 1;          // peer-memory transport: the message goes straight into every rank's msgs[rank]
-  const int64_t slot = (int64_t)pv.rank * (B + 3 * b);
+  const bool p2p = A.pv.world > 1;          // peer-memory transport: the message goes straight into every rank's msgs[rank]
+  const int64_t slot = (int64_t)A.pv.rank * (B + 3 * b);
   auto put = [&](int64_t pos, float v) {
-    if (!p2p) { msg[pos] = v; return; }
-    if (pv.mc) { mc_st_f32(reinterpret_cast<float*>(pv.mc + off_msgs) + slot + pos, v); return; }      // NVLS: one store, all ranks
-    for (int q = 0; q < pv.world; ++q) reinterpret_cast<float*>(pv.base[q] + off_msgs)[slot + pos] = v;
+    if (!p2p) { A.msg[pos] = v; return; }
+    if (A.pv.mc) { mc_st_f32(reinterpret_cast<float*>(A.pv.mc + A.off_msgs) + slot + pos, v); return; }      // NVLS: one store, all ranks
+    for (int q = 0; q < A.pv.world; ++q) reinterpret_cast<float*>(A.pv.base[q] + A.off_msgs)[slot + pos] = v;
   };
   if (idx < B) {
     float L = 0.f;
-    if (fastr && colpart) {                 // few row groups (sharded batch): reduce the sweep's partials here, fixed order
+    if (fastr && A.colpart) {                 // few row groups (sharded batch): reduce the sweep's partials here, fixed order
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int g = 0;
-      for (; g + 4 <= n_groups; g += 4) {
-        a0 += __ldg(colpart + (int64_t)(g + 0) * B + idx);
-        a1 += __ldg(colpart + (int64_t)(g + 1) * B + idx);
-        a2 += __ldg(colpart + (int64_t)(g + 2) * B + idx);
-        a3 += __ldg(colpart + (int64_t)(g + 3) * B + idx);
+      for (; g + 4 <= A.n_groups; g += 4) {
+        a0 += __ldg(A.colpart + (int64_t)(g + 0) * B + idx);
+        a1 += __ldg(A.colpart + (int64_t)(g + 1) * B + idx);
+        a2 += __ldg(A.colpart + (int64_t)(g + 2) * B + idx);
+        a3 += __ldg(A.colpart + (int64_t)(g + 3) * B + idx);
       }
-      for (; g < n_groups; ++g) a0 += __ldg(colpart + (int64_t)g * B + idx);
+      for (; g < A.n_groups; ++g) a0 += __ldg(A.colpart + (int64_t)g * B + idx);
       L = (a0 + a1) + (a2 + a3);
     } else if (fastr) {
-      for (int g = 0; g < kColSumSplit; ++g) L += colsum8[(int64_t)g * B + idx];
+      for (int g = 0; g < kColSumSplit; ++g) L += A.colsum8[(int64_t)g * B + idx];
     }
     put(idx, L);
   }
@@ -116,19 +126,19 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
     float rl, cl = 0.f;
     if (fastr) {
       float L = 0.f;
-      for (int c = 0; c < n_chunks_fast; ++c) {
-        const float2 h = part[(int64_t)c * b + idx];
+      for (int c = 0; c < A.n_chunks_fast; ++c) {
+        const float2 h = A.part[(int64_t)c * b + idx];
         L += h.x + h.y;
       }
       rl = (s2 + log2f(L)) * kLn2;
     } else {
       float lse[2];
       for (int p = 0; p < 2; ++p) {
-        const float2* base = part + (int64_t)p * n_chunks * b + idx;
+        const float2* base = A.part + (int64_t)p * A.n_chunks * b + idx;
         float M = -INFINITY;
-        for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, base[(int64_t)c * b].x);
+        for (int c = 0; c < A.n_chunks; ++c) M = fmaxf(M, base[(int64_t)c * b].x);
         float L = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = 0; c < A.n_chunks; ++c) {
           const float2 ml = base[(int64_t)c * b];
           L += ml.y * exp2f(ml.x - M);
         }
@@ -139,68 +149,76 @@ __global__ void pack_stats_kernel(const float2* __restrict__ part, int n_chunks,
     }
     put(B + idx, rl);
     put(B + b + idx, cl);
-    put(B + 2 * b + idx, s * diag_cos[idx]);
-  }
-  if (p2p) {                                // last block done -> publish the message to every rank (system-scope epoch flag)
-    __shared__ bool last;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      last = ((atomicAdd(pack_counter, 1u) + 1) % gridDim.x) == 0;
-      __threadfence();
-    }
-    __syncthreads();
-    if (last && pv.mc) {
-      if (threadIdx.x == 0) mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.mc + off_msg_flags) + pv.rank, pv.epoch);
-    } else if (last && (int)threadIdx.x < pv.world) {      // one thread per destination: the release stores travel in parallel
-      st_release_sys_u32(reinterpret_cast<uint32_t*>(pv.base[threadIdx.x] + off_msg_flags) + pv.rank, pv.epoch);
-    }
+    put(B + 2 * b + idx, s * A.diag_cos[idx]);
   }
 }
+// peer-memory transport: last block done -> publish the message to every rank (system-scope epoch flag)
+__device__ __forceinline__ void pack_publish(const PackArgs& A) {
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    last = ((atomicAdd(A.pack_counter, 1u) + 1) % gridDim.x) == 0;
+    __threadfence();
+  }
+  __syncthreads();
+  if (last && A.pv.mc) {
+    if (threadIdx.x == 0) mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(A.pv.mc + A.off_msg_flags) + A.pv.rank, A.pv.epoch);
+  } else if (last && (int)threadIdx.x < A.pv.world) {      // one thread per destination: the release stores travel in parallel
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(A.pv.base[threadIdx.x] + A.off_msg_flags) + A.pv.rank, A.pv.epoch);
+  }
+}
+__global__ void pack_stats_kernel(const PackArgs A) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float s = fminf(expf(*A.logit_scale), A.scale_cap);
+  pack_one(A, idx, s, A.fast && s * kLog2e <= A.s2_limit);
+}
 
-// msgs[R][B + 3b] (all-gathered) -> stats_all = [row_lse (B) | col_lse (B) | diag (B)], scale_out
+// msgs[R][B + 3b] (all-gathered) -> stats_all = [row_lse (B) | col_lse (B) | diag (B)], scale_out, loss
 __device__ __forceinline__ float ld_cg(const float* p) {      // L2 only: the messages may have been written by a peer GPU
   float v;
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
-__global__ void merge_stats_kernel(const float* msgs, int R, int64_t b, int64_t B,
-                                   const float* __restrict__ logit_scale, float scale_cap, int fast, float s2_limit,
-                                   float* __restrict__ stats_all, float* __restrict__ scale_out,
-                                   const uint32_t* msg_flags, uint32_t epoch, double* __restrict__ loss_part,
-                                   uint32_t* __restrict__ loss_counter, float* __restrict__ loss_out) {
-  if (msg_flags) {                          // peer-memory transport: every rank's message for this step has landed
-    if ((int)threadIdx.x < R) p2p_wait_ge(msg_flags + threadIdx.x, epoch);
-    __syncthreads();
-  }
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const float e = expf(*logit_scale);
-  const float s = fminf(e, scale_cap);
-  if (j == 0 && scale_out) {
-    scale_out[0] = s;
-    scale_out[1] = (e <= scale_cap) ? 1.0f : 0.0f;
-  }
-  double term = 0.0;
-  if (j < B) {
-  const int64_t stride = B + 3 * b;
+struct MergeArgs {
+  const float* msgs;
+  int R;
+  int64_t b, B;
+  const float* logit_scale;
+  float scale_cap;
+  int fast;
+  float s2_limit;
+  float *stats_all, *scale_out;
+  const uint32_t* msg_flags;      // peer-memory transport: wait for every rank's message of `epoch` (nullptr otherwise)
+  uint32_t epoch;
+  double* loss_part;
+  uint32_t* loss_counter;
+  float* loss_out;
+};
+__device__ __forceinline__ double merge_one(const MergeArgs& A, int64_t j, float s) {
+  const int64_t b = A.b, B = A.B, stride = B + 3 * b;
   const int r = (int)(j / b);
   const int64_t i = j - (int64_t)r * b;
-  const float* own = msgs + (int64_t)r * stride;
-  stats_all[j] = ld_cg(own + B + i);
-  stats_all[2 * B + j] = ld_cg(own + B + 2 * b + i);
+  const float* own = A.msgs + (int64_t)r * stride;
+  const float rl = ld_cg(own + B + i), dg = ld_cg(own + B + 2 * b + i);
+  float cl;
   const float s2 = s * kLog2e;
-  if (fast && s2 <= s2_limit) {
+  if (A.fast && s2 <= A.s2_limit) {
     float L = 0.f;
-    for (int q = 0; q < R; ++q) L += ld_cg(msgs + (int64_t)q * stride + j);      // fixed rank order
-    stats_all[B + j] = (s2 + log2f(L)) * kLn2;
+    for (int q = 0; q < A.R; ++q) L += ld_cg(A.msgs + (int64_t)q * stride + j);      // fixed rank order
+    cl = (s2 + log2f(L)) * kLn2;
   } else {
-    stats_all[B + j] = ld_cg(own + B + b + i);
+    cl = ld_cg(own + B + b + i);
   }
-  term = ((double)stats_all[j] - (double)stats_all[2 * B + j]) + ((double)stats_all[B + j] - (double)stats_all[2 * B + j]);
-  }
-  // loss = mean(row_lse - diag) + mean(col_lse - diag): per-block partials, summed in block order by the last block to
-  // finish (fixed order -> bitwise deterministic and identical on every rank)
-  if (loss_out == nullptr) return;
+  A.stats_all[j] = rl;
+  A.stats_all[B + j] = cl;
+  A.stats_all[2 * B + j] = dg;
+  return ((double)rl - (double)dg) + ((double)cl - (double)dg);
+}
+// loss = mean(row_lse - diag) + mean(col_lse - diag): per-block partials, summed in block order by the last block to
+// finish (fixed order -> bitwise deterministic and identical on every rank)
+__device__ __forceinline__ void merge_loss(const MergeArgs& A, double term) {
+  if (A.loss_out == nullptr) return;
   __shared__ double red[8];
   __shared__ bool last;
 #pragma unroll
@@ -210,19 +228,54 @@ __global__ void merge_stats_kernel(const float* msgs, int R, int64_t b, int64_t 
   if (threadIdx.x == 0) {
     double v = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
-    loss_part[blockIdx.x] = v;
+    A.loss_part[blockIdx.x] = v;
     __threadfence();
-    last = ((atomicAdd(loss_counter, 1u) + 1) % gridDim.x) == 0;
+    last = ((atomicAdd(A.loss_counter, 1u) + 1) % gridDim.x) == 0;
   }
   __syncthreads();
   if (last && threadIdx.x < 32) {
     __threadfence();
     double v = 0.0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) v += *reinterpret_cast<volatile double*>(loss_part + i);
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) v += *reinterpret_cast<volatile double*>(A.loss_part + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) *loss_out = (float)(v / (double)B);
+    if (threadIdx.x == 0) *A.loss_out = (float)(v / (double)A.B);
   }
+}
+__global__ void __launch_bounds__(256) merge_stats_kernel(const MergeArgs A) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float e = expf(*A.logit_scale);
+  const float s = fminf(e, A.scale_cap);
+  if (j == 0 && A.scale_out) {
+    A.scale_out[0] = s;
+    A.scale_out[1] = (e <= A.scale_cap) ? 1.0f : 0.0f;
+  }
+  merge_loss(A, j < A.B ? merge_one(A, j, s) : 0.0);
+}
+
+// Peer-memory transport: the whole statistics exchange in ONE kernel.  Every block first writes its share of this rank's
+// message into all ranks' segments (the last block to finish publishes it with one system-scope epoch flag per rank), then
+// waits for the R messages of this step and merges its share of the rows.  The grid is bounded (<= 2 blocks per SM, grid-
+// stride loops) so that all blocks are resident at once: a block spinning for the messages never keeps a block that
+// still has to write this rank's message off the machine.
+constexpr int kExchangeMaxBlocks = 2 * 148;
+__global__ void __launch_bounds__(256) exchange_stats_kernel(const PackArgs P, const MergeArgs A) {
+  const float e = expf(*A.logit_scale);
+  const float s = fminf(e, A.scale_cap);
+  const bool fastr = P.fast && s * kLog2e <= P.s2_limit;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n = P.B > P.b ? P.B : P.b;
+  for (int64_t idx = first; idx < n; idx += stride) pack_one(P, idx, s, fastr);
+  pack_publish(P);
+  if ((int)threadIdx.x < A.R) p2p_wait_ge(A.msg_flags + threadIdx.x, A.epoch);
+  __syncthreads();
+  if (first == 0 && A.scale_out) {
+    A.scale_out[0] = s;
+    A.scale_out[1] = (e <= A.scale_cap) ? 1.0f : 0.0f;
+  }
+  double term = 0.0;
+  for (int64_t j = first; j < A.B; j += stride) term += merge_one(A, j, s);
+  merge_loss(A, term);
 }
 
 // ---- loss = mean(row_lse - diag) + mean(col_lse - diag), fixed-order fp64 reduction ---------------
@@ -272,6 +325,34 @@ loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse
 }
 
 // ---- backward finalisation -------------------------------------------------------------------------
+// peer-memory transport (block 0 of the finalize kernel): {epoch, partial} into every rank's slot of this rank, then the sum
+// of the R partials in rank order (bitwise identical on every rank).  Every rank's block stores before it waits: no cycle.
+static __device__ __noinline__ void dls_exchange(const P2PView& pv, size_t off_dls, float part_dls, float* dlogit_scale) {
+  const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
+  if (pv.mc) {
+    if (threadIdx.x == 0) mc_st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.mc + off_dls) + pv.rank, w);
+  } else if ((int)threadIdx.x < pv.world) {    // one thread per destination
+    st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[threadIdx.x] + off_dls) + pv.rank, w);
+  }
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const unsigned long long* slots = reinterpret_cast<const unsigned long long*>(pv.base[pv.rank] + off_dls);
+    float v = 0.f;
+    if (lane < pv.world) {
+      const unsigned long long t0 = global_timer_ns();
+      uint32_t spins = 0;
+      while (true) {
+        const unsigned long long got = ld_acquire_sys_u64(slots + lane);
+        if ((uint32_t)(got >> 32) == pv.epoch) { v = __uint_as_float((uint32_t)got); break; }
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > kP2PTimeoutNs) p2p_timeout(slots + lane, pv.epoch, (uint32_t)(got >> 32));
+      }
+    }
+    double acc = 0.0;
+    for (int q = 0; q < pv.world; ++q) acc += (double)__shfl_sync(0xffffffffu, v, q);
+    if (lane == 0) *dlogit_scale = (float)acc;
+  }
+}
+
 constexpr int kFinWarps = 8;
 constexpr int kFinMaxVec = 8;   // D <= 1024
 
@@ -283,7 +364,7 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
                     const float* __restrict__ inv1, const float* __restrict__ inv2, int already,
                     void* __restrict__ dx1, void* __restrict__ dx2,
                     const float* __restrict__ dscale_part, int n_dscale, float* __restrict__ dlogit_scale,
-                    const P2PView pv, size_t off_dls) {
+                    const P2PView pv, size_t off_dls, int dls_sum) {
   const float s = scale[0], g = grad_out[0];
   const int lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * kFinWarps + (threadIdx.x >> 5);   // (problem, row)
@@ -353,13 +434,8 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
       __syncthreads();
     }
     const float part_dls = (float)(red[0] * (double)s * (double)g * (double)scale[1]);
-    if (pv.world > 1) {                     // peer-memory transport: {epoch, partial} into every rank's slot of this rank,
-      const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
-      if (pv.mc) {
-        if (threadIdx.x == 0) mc_st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.mc + off_dls) + pv.rank, w);
-      } else if ((int)threadIdx.x < pv.world) {    // one thread per destination
-        st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[threadIdx.x] + off_dls) + pv.rank, w);
-      }
+    if (pv.world > 1 && dls_sum) {
+      dls_exchange(pv, off_dls, part_dls, dlogit_scale);
     } else if (threadIdx.x == 0) {
       *dlogit_scale = part_dls;
     }
@@ -390,30 +466,64 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
   return 0;
 }
 
+static PackArgs make_pack_args(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
+                               float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart,
+                               float* msg, const P2PStep* p2p) {
+  PackArgs A{};
+  A.part = reinterpret_cast<const float2*>(ws.fwd_part);
+  A.n_chunks = plan.fwd_chunks; A.n_chunks_fast = plan.fwd1_chunks;
+  A.b = b; A.B = B;
+  A.logit_scale = logit_scale; A.scale_cap = scale_cap; A.diag_cos = diag_cos;
+  A.fast = fast; A.s2_limit = pair_fast_s2_limit();
+  A.colsum8 = colsum8; A.colpart = from_colpart ? ws.colpart : nullptr; A.n_groups = plan.n_rowgroups;
+  A.msg = msg;
+  if (p2p) {
+    A.pv = p2p->view; A.off_msgs = p2p->off_msgs; A.off_msg_flags = p2p->off_msg_flags; A.pack_counter = p2p->pack_counter;
+  }
+  return A;
+}
+static MergeArgs make_merge_args(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap,
+                                 int fast, float* stats_all, float* scale_out, const P2PStep* p2p, double* loss_part,
+                                 uint32_t* loss_counter, float* loss_out) {
+  MergeArgs M{};
+  M.msgs = msgs; M.R = R; M.b = b; M.B = B;
+  M.logit_scale = logit_scale; M.scale_cap = scale_cap; M.fast = fast; M.s2_limit = pair_fast_s2_limit();
+  M.stats_all = stats_all; M.scale_out = scale_out;
+  M.msg_flags = p2p ? p2p->msg_flags : nullptr; M.epoch = p2p ? p2p->view.epoch : 0u;
+  M.loss_part = loss_part; M.loss_counter = loss_counter; M.loss_out = loss_out;
+  return M;
+}
+
 int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
                       float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart, float* msg,
-                      const P2PStep* p2p, cudaStream_t st) {
+                      cudaStream_t st) {
   const int64_t n = B > b ? B : b;
-  P2PView pv{};
-  if (p2p) pv = p2p->view;
-  pack_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
-                                                                  plan.fwd1_chunks, b, B, logit_scale, scale_cap, diag_cos, fast,
-                                                                  pair_fast_s2_limit(), colsum8,
-                                                                  from_colpart ? ws.colpart : nullptr, plan.n_rowgroups, msg, pv,
-                                                                  p2p ? p2p->off_msgs : 0, p2p ? p2p->off_msg_flags : 0,
-                                                                  p2p ? p2p->pack_counter : nullptr);
+  const PackArgs A = make_pack_args(ws, plan, b, B, logit_scale, scale_cap, diag_cos, fast, colsum8, from_colpart, msg, nullptr);
+  pack_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A);
   VPA_LAUNCH_CHECK("pack_stats_kernel");
   return 0;
 }
 
 int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const float* logit_scale, float scale_cap, int fast,
-                       float* stats_all, float* scale_out, const P2PStep* p2p, double* loss_part, uint32_t* loss_counter,
-                       float* loss_out, cudaStream_t st) {
-  merge_stats_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(msgs, R, b, B, logit_scale, scale_cap, fast,
-                                                                  pair_fast_s2_limit(), stats_all, scale_out,
-                                                                  p2p ? p2p->msg_flags : nullptr, p2p ? p2p->view.epoch : 0u,
-                                                                  loss_part, loss_counter, loss_out);
+                       float* stats_all, float* scale_out, double* loss_part, uint32_t* loss_counter, float* loss_out,
+                       cudaStream_t st) {
+  const MergeArgs M = make_merge_args(msgs, R, b, B, logit_scale, scale_cap, fast, stats_all, scale_out, nullptr, loss_part,
+                                      loss_counter, loss_out);
+  merge_stats_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(M);
   VPA_LAUNCH_CHECK("merge_stats_kernel");
+  return 0;
+}
+
+// peer-memory transport: message out, R messages in, statistics of all rows + the global loss -- one launch
+int exchange_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int64_t B, const float* logit_scale,
+                          float scale_cap, const float* diag_cos, int fast, const float* colsum8, bool from_colpart,
+                          const P2PStep& p2p, float* loss_out, cudaStream_t st) {
+  const PackArgs A = make_pack_args(ws, plan, b, B, logit_scale, scale_cap, diag_cos, fast, colsum8, from_colpart, nullptr, &p2p);
+  const MergeArgs M = make_merge_args(p2p.msgs, p2p.view.world, b, B, logit_scale, scale_cap, fast, p2p.stats_all, p2p.scale, &p2p,
+                                      p2p.loss_part, p2p.loss_counter, loss_out);
+  const int64_t blocks = (B + 255) / 256;
+  exchange_stats_kernel<<<(unsigned)(blocks < kExchangeMaxBlocks ? blocks : kExchangeMaxBlocks), 256, 0, st>>>(A, M);
+  VPA_LAUNCH_CHECK("exchange_stats_kernel");
   return 0;
 }
 
@@ -427,7 +537,8 @@ int loss_launch(const float* row_lse, const float* col_lse, const float* diag, i
 int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_local, int D,
                         const float* scale, const float* grad_out, const void* x1, const void* x2,
                         int in_dtype, int64_t ld1, int64_t ld2, const float* inv1, const float* inv2,
-                        int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, cudaStream_t st) {
+                        int already, void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, int dls_sum,
+                        cudaStream_t st) {
   P2PView pv{};
   if (p2p) pv = p2p->view;
   const size_t off_dls = p2p ? p2p->off_dls : 0;
@@ -438,7 +549,7 @@ int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows
 #define VPA_FIN(DT, NV)                                                                                            \
   finalize_bwd_kernel<DT, NV><<<grid, block, 0, st>>>(ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, grad_out, \
                                                       x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2,             \
-                                                      ws.dscale_part, plan.n_dscale, dlogit_scale, pv, off_dls)
+                                                      ws.dscale_part, plan.n_dscale, dlogit_scale, pv, off_dls, dls_sum)
 #define VPA_FIN_NV(DT)                 \
   switch (nv) {                        \
     case 1: VPA_FIN(DT, 1); break;     \

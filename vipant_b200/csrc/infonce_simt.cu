@@ -165,11 +165,8 @@ int simt_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& p
 
 int simt_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
   const size_t smem = (size_t)kRB * (a.D + kJC) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    VPA_CUDA(cudaFuncSetAttribute(simt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  static SmemAttrCache attr_cache;
+  if (int e = ensure_dynamic_smem(attr_cache, simt_bwd_kernel, 96 * 1024)) return e;
   dim3 grid(2 * plan.n_iblk), block(kThreads);
   simt_bwd_kernel<<<grid, block, smem, st>>>(
       (const float*)a.x[0], (const float*)a.y[0], (const float*)a.x[1], (const float*)a.y[1], a.rows_local,

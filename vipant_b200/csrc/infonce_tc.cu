@@ -620,11 +620,8 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
     }
   }
   const SmemLayout L = smem_layout(MODE, P.kboxes, P.stages);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[MODE]) {
-    VPA_CUDA(cudaFuncSetAttribute(sweep_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-    attr_set[MODE] = true;
-  }
+  static SmemAttrCache attr_cache[2];
+  if (int e = ensure_dynamic_smem(attr_cache[MODE], sweep_kernel<MODE>, (int)kSmemLimit)) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * P.units_per_problem);
   cfg.blockDim = dim3(kThreads);

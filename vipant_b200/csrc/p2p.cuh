@@ -92,34 +92,189 @@ __device__ __forceinline__ void p2p_wait_rows(const P2PRowFlags& f, int r0, int 
   }
 }
 
-// One item of the pull kernel: `rows` rows starting at row `row0` of rank `src`'s block of matrix `m` (chunk `c`).
-// Items are ordered matrix-major (x2 operands first), then chunk-major, then slice-major, then over the peers: the first
-// (world-1)*slices items are chunk 0 of EVERY peer, so with ~64 CTAs taking items round-robin the early chunks of all peer
-// blocks land first and the forward sweep (which visits its tiles chunk-major) finds data a few microseconds after it
-// starts, instead of waiting for whole 256-row chunks that one CTA needs ~45 us to pull.  A chunk is complete when its
-// `slices` items are (arrival counter).  Shared by the kernel and, host side, vpa_debug_pull_item (CPU test).
-struct PullItem { int m, src, c, row0, rows; };
-__host__ __device__ inline PullItem pull_item_decode(int item, int m0, int world, int me, int cpr, int slices, int64_t b) {
-  const int per_c = (world - 1) * slices;
-  const int per_m = cpr * per_c;
-  PullItem it;
-  it.m = m0 + item / per_m;
-  int r = item % per_m;
-  it.c = r / per_c;
-  r -= it.c * per_c;
-  const int s = r / (world - 1);
-  const int q = r - s * (world - 1) + 1;
-  it.src = (me + q) % world;
-  const int64_t crow0 = (int64_t)it.c * kPushRows;
-  const int64_t left = b - crow0;
-  const int crows = left < kPushRows ? (int)left : kPushRows;
-  const int per = (crows + slices - 1) / slices;
-  const int lo = s * per < crows ? s * per : crows;
-  const int hi = lo + per < crows ? lo + per : crows;
-  it.row0 = (int)crow0 + lo;
-  it.rows = hi - lo;
+// ---------------------------------------------------------------- operand relay (the all-gather of the row-sharded step)
+// The gathered operand matrices are filled by RELAY CTAs: whole CTAs that do nothing but move rows, driven by one thread
+// and the TMA engine.  They run as the first CTAs of the single-pass forward's grid (infonce_pair.cu: one kernel does the
+// all-gather and the contraction; CTAs are dispatched in blockIdx order, so the relays are resident before any sweep CTA
+// that polls their flags) or as a kernel of their own for the shapes the CTA-pair sweeps do not cover.
+//   pull (default)  cp.async.bulk peer-global -> shared-memory ring -> cp.async.bulk local-global: up to kRelaySlots x 32 KB
+//                   of NVLink reads in flight per CTA (an LDG copy loop holds ~32 KB per CTA and measured 260-360 GB/s at
+//                   8 GPUs); one local arrival flag per 256-row chunk once its stores have completed.
+//   multicast       (NVLS segment) every rank stores its OWN rows once through the multicast mapping; the NVSwitch
+//                   replicates them to all ranks: 1/(R-1) of the egress.  Flags travel the same way.
+// Items are ordered matrix-major (x2 operands first: the forward needs only them), then chunk-major over the peers, so
+// the early chunks of every peer block land first -- the order in which the sweep visits its tiles.
+struct RelayArgs {
+  P2PView v;
+  size_t off_mat[2], off_flags[2], off_ready;      // this step's parity; m = 0: x2 operands (t_all), 1: x1 operands (a_all)
+  int64_t b;                                       // rows per rank
+  int row_bytes, cpr;                              // bytes per operand row; 256-row chunks per rank block
+  int n_ctas;                                      // relay CTAs (0: no relay)
+  int multicast;                                   // 1: NVLS stores of the own block instead of pulls
+};
+constexpr int kRelaySlots = 6;
+constexpr int kRelayPieceBytes = 32768;
+constexpr uint32_t kRelaySmemBytes = kRelaySlots * kRelayPieceBytes + 64;      // ring + mbarriers (1024-byte aligned base)
+
+struct RelayItem { int m, src, c, row0, rows; };
+// item -> (matrix, source rank, chunk): shared by the device code and, host side, vpa_debug_relay_item (CPU test)
+__host__ __device__ inline RelayItem relay_item_decode(int item, int world, int me, int cpr, int64_t b) {
+  const int per_m = cpr * (world - 1);
+  RelayItem it;
+  it.m = item / per_m;
+  const int r = item - it.m * per_m;
+  it.c = r / (world - 1);
+  const int q = r - it.c * (world - 1) + 1;
+  it.src = (me + q) % world;                       // rotate: the ranks do not all read the same peer at the same time
+  const int64_t row0 = (int64_t)it.c * kPushRows;
+  const int64_t left = b - row0;
+  it.row0 = (int)row0;
+  it.rows = left < kPushRows ? (int)left : kPushRows;
   return it;
 }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t relay_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool relay_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+static __device__ __noinline__ void relay_timeout(int what, int a, int b) {
+  printf("vipant_b200(relay): wait %d timed out (block %d, %d %d)\n", what, blockIdx.x, a, b);
+  asm volatile("trap;");
+}
+
+// "my rows of this step are complete in my segment" -> every peer (called by ONE relay CTA; the normalise kernel that wrote
+// the rows finished before this kernel started: stream order)
+__device__ __forceinline__ void relay_signal_ready(const RelayArgs& A) {
+  const int q = threadIdx.x;
+  if (q < A.v.world && q != A.v.rank) {
+    __threadfence_system();
+    if (A.multicast) return;                       // multicast mode: nobody pulls
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[q] + A.off_ready) + A.v.rank, A.v.epoch);
+  }
+}
+
+// Pull role of relay CTA `cta` of `A.n_ctas`.  `ring` = 1024-byte aligned shared memory of kRelaySmemBytes.  One thread
+// drives the TMA engine; the caller lets the other threads of the CTA leave.
+__device__ __forceinline__ void relay_pull(const RelayArgs& A, int cta, uint8_t* ring) {
+  if (threadIdx.x != 0) return;
+  const int me = A.v.rank, world = A.v.world;
+  char* mine = A.v.base[me];
+  const uint32_t ring_u = relay_smem_u32(ring);
+  const uint32_t bars = ring_u + kRelaySlots * kRelayPieceBytes;
+  for (int s = 0; s < kRelaySlots; ++s)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const uint32_t* ready = reinterpret_cast<const uint32_t*>(mine + A.off_ready);
+  const int total = 2 * A.cpr * (world - 1);
+  const int piece_rows = kRelayPieceBytes / A.row_bytes > 0 ? kRelayPieceBytes / A.row_bytes : 1;
+  unsigned seen = 1u << me;                        // sources whose ready flag this thread has already observed
+  struct Cursor { int item, piece, npieces; RelayItem it; };
+  auto open = [&](Cursor& c) {                     // position on the first piece of item c.item (if any)
+    if (c.item < total) {
+      c.it = relay_item_decode(c.item, world, me, A.cpr, A.b);
+      c.npieces = (c.it.rows + piece_rows - 1) / piece_rows;
+      c.piece = 0;
+    }
+  };
+  auto advance = [&](Cursor& c) {
+    if (++c.piece == c.npieces) { c.item += A.n_ctas; open(c); }
+  };
+  auto geometry = [&](const Cursor& c, size_t* off, uint32_t* bytes) {
+    const int r0 = c.it.row0 + c.piece * piece_rows;
+    const int rows = min(piece_rows, c.it.row0 + c.it.rows - r0);
+    *off = A.off_mat[c.it.m] + ((size_t)c.it.src * A.b + r0) * A.row_bytes;
+    *bytes = (uint32_t)rows * A.row_bytes;
+  };
+  Cursor ld{}, st{};
+  ld.item = st.item = cta;
+  open(ld);
+  open(st);
+  uint32_t n_ld = 0, n_st = 0;                     // pieces issued / retired (slot = n % kRelaySlots)
+  auto issue_load = [&]() {
+    if (!(seen >> ld.it.src & 1u)) { p2p_wait_ge(ready + ld.it.src, A.v.epoch); seen |= 1u << ld.it.src; }
+    size_t off; uint32_t bytes;
+    geometry(ld, &off, &bytes);
+    const uint32_t slot = n_ld % kRelaySlots, bar = bars + 8u * slot, dst = ring_u + slot * kRelayPieceBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(A.v.base[ld.it.src] + off), "r"(bytes), "r"(bar) : "memory");
+    ++n_ld;
+    advance(ld);
+  };
+  while (ld.item < total && n_ld < (uint32_t)kRelaySlots) issue_load();
+  while (st.item < total) {
+    const uint32_t slot = n_st % kRelaySlots, bar = bars + 8u * slot, parity = (n_st / kRelaySlots) & 1u;
+    if (!relay_mbar_try(bar, parity)) {
+      const unsigned long long t0 = global_timer_ns();
+      uint32_t spins = 0;
+      while (!relay_mbar_try(bar, parity))
+        if ((++spins & 255u) == 0 && global_timer_ns() - t0 > kP2PTimeoutNs) relay_timeout(0, st.item, st.piece);
+    }
+    size_t off; uint32_t bytes;
+    geometry(st, &off, &bytes);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(mine + off), "r"(ring_u + slot * kRelayPieceBytes), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    const bool chunk_done = st.piece + 1 == st.npieces;
+    const int m = st.it.m, src = st.it.src, c = st.it.c;
+    ++n_st;
+    advance(st);
+    if (chunk_done) {
+      // the chunk is complete in local memory once its stores are: publish its flag (the loads of the next pieces are
+      // tracked by mbarriers and stay in flight meanwhile)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");            // async-proxy writes -> ordered before the flag store
+      __threadfence();
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(mine + A.off_flags[m]) + src * A.cpr + c, A.v.epoch);
+    } else {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the slot may be overwritten
+    }
+    if (ld.item < total) issue_load();
+  }
+}
+
+// Multicast role (NVLS segment): chunks of THIS rank's block, all threads of the CTA storing through the multicast mapping.
+__device__ __forceinline__ void relay_multicast(const RelayArgs& A, int cta) {
+  const int me = A.v.rank;
+  char* mine = A.v.base[me];
+  const int total = 2 * A.cpr;
+  const int nthr = blockDim.x;
+  for (int item = cta; item < total; item += A.n_ctas) {
+    const int m = item / A.cpr, c = item - m * A.cpr;
+    const int64_t row0 = (int64_t)c * kPushRows;
+    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
+    const int n16 = rows * (A.row_bytes / 16);
+    const size_t off = A.off_mat[m] + ((size_t)me * A.b + row0) * A.row_bytes;
+    const uint4* from = reinterpret_cast<const uint4*>(mine + off);
+    uint4* to = reinterpret_cast<uint4*>(A.v.mc + off);
+    constexpr int kU = 8;
+    for (int i = threadIdx.x; i < n16; i += nthr * kU) {
+      uint4 val[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int idx = i + u * nthr;
+        if (idx < n16) val[u] = __ldg(from + idx);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int idx = i + u * nthr;
+        if (idx < n16) mc_st_v4(to + idx, val[u]);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.mc + A.off_flags[m]) + me * A.cpr + c, A.v.epoch);
+  }
+}
+#endif  // __CUDACC__
 
 // Host-side description of one step's buffers inside the local segment (p2p.cu::p2p_step) + what kernels need to reach
 // the same buffers in the peers (offsets are identical in every segment).
@@ -135,6 +290,7 @@ struct P2PStep {
   void* ws;
   size_t ws_bytes;
   P2PRowFlags yflags;       // chunk flags of the x2 operands (the Y stream of the single-pass forward)
+  RelayArgs relay;          // the operand all-gather of this step (n_ctas: relay CTAs in front of the forward grid)
 };
 
 int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out, void* ipc_handle64);
@@ -144,11 +300,8 @@ int p2p_check(void* handle, int64_t b, int world, int rank, int D, int precision
 uint32_t p2p_next_epoch(void* handle);
 uint32_t p2p_current_epoch(void* handle);
 P2PStep p2p_step(void* handle, uint32_t epoch);
-int p2p_push_operands(void* handle, uint32_t epoch, cudaStream_t st);
-int p2p_pull_rest(void* handle, uint32_t epoch, cudaStream_t st);
-int p2p_join_push(void* handle, cudaStream_t st);
-int p2p_wait_operands(void* handle, uint32_t epoch, const float* gate_scale, float scale_cap, cudaStream_t st);
-int p2p_dls_sum(const P2PStep& s, float* dlogit_scale, cudaStream_t st);
+int p2p_relay_standalone(void* handle, uint32_t epoch, cudaStream_t st);
+int p2p_relay_ctas(void* handle);
 int p2p_mode(void* handle);
 int p2p_nvls_export(void* handle, int* fd_out);
 int p2p_nvls_attach(void* handle, int fd);

@@ -41,19 +41,45 @@ def _require_cuda(*tensors):
 
 
 def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    """(rows, D) view the kernels can read in place: unit column stride, 16-byte aligned rows.  Row-strided views
+    (``feats[:, :512]``, the CLS token ``hidden[:, 0, :]``) pass through uncopied -- the kernels take a leading dimension."""
     if x.dim() != 2:
         raise ValueError(f"expected a (rows, D) matrix, got shape {tuple(x.shape)}")
     if x.dtype not in _DTYPES:
         x = x.float()
-    if x.stride(1) != 1 or x.stride(0) % 4 != 0 or x.data_ptr() % 16 != 0:
+    esz = x.element_size()
+    if (x.stride(1) != 1 or x.stride(0) < x.shape[1] or (x.stride(0) * esz) % 16 != 0 or x.data_ptr() % 16 != 0):
         x = x.contiguous()
     return x
+
+
+def _grad_like(x: torch.Tensor) -> torch.Tensor:
+    """Gradient buffer with the SAME leading dimension as x: the backward kernels address x and dx with one `ld`
+    (include/vipant_b200.h: "dx1/dx2 same dtype and ld"); `empty_like` would densify a row-strided view."""
+    g = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
+    assert g.stride(0) == x.stride(0) and g.stride(1) == 1
+    return g
 
 
 def _resolve_precision(precision: str, D: int) -> int:
     if precision not in PRECISIONS:
         raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
     return PRECISIONS[precision]
+
+
+_SCALARS = {}
+
+
+def _device_scalar(value: torch.Tensor, dev) -> torch.Tensor:
+    """A constant scalar (the `scaling=False` temperature, a plain CPU tensor in the reference: loss_head.py:252) on the
+    device, cached by value: no blocking pageable H2D copy on every step."""
+    key = (float(value), dev.type, dev.index)
+    t = _SCALARS.get(key)
+    if t is None:
+        if len(_SCALARS) > 64:
+            _SCALARS.clear()
+        t = _SCALARS[key] = torch.tensor(key[0], dtype=torch.float32, device=dev)
+    return t
 
 
 def tensor_core_supported(D: int) -> bool:
@@ -142,13 +168,13 @@ class _CudaKernels:
         B = a_all.shape[0]
         dev = a.device
         g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        dx1 = torch.empty_like(x1)
-        dx2 = torch.empty_like(x2)
+        dx1 = _grad_like(x1)
+        dx2 = _grad_like(x2)
         dls = torch.empty((), dtype=torch.float32, device=dev)
         _cabi.check(lib.vpa_infonce_bwd(
             _ptr(a), _ptr(t), _ptr(a_all), _ptr(t_all), precision, b, B, D, row_offset, _ptr(scale),
             _ptr(stats_all[0]), _ptr(stats_all[1]), _ptr(g), _ptr(x1), _ptr(x2), _DTYPES[x1.dtype],
-            dx1.stride(0), dx2.stride(0), _ptr(inv[0]), _ptr(inv[1]), int(normalized), _ptr(ws), ws.numel(),
+            x1.stride(0), x2.stride(0), _ptr(inv[0]), _ptr(inv[1]), int(normalized), _ptr(ws), ws.numel(),
             _ptr(dx1), _ptr(dx2), _ptr(dls), _stream()), "vpa_infonce_bwd")
         return dx1, dx2, dls
 
@@ -194,14 +220,14 @@ def _sharded_forward(kern, x1, x2, logit_scale, scale_max, normalized, precision
     return loss, saved, (ws, rank * b, world)
 
 
-def _sharded_backward(kern, saved, extra, grad_out, normalized, precision, group):
+def _sharded_backward(kern, saved, extra, grad_out, normalized, precision, group, dls_sum=True):
     """dL/d(local rows): two local sweeps (x1 rows vs all x2, x2 rows vs all x1); only the replicated
-    logit_scale gradient needs a (scalar) all-reduce."""
+    logit_scale gradient needs a (scalar) all-reduce (skipped when the caller wants this rank's partial)."""
     x1, x2, a, t, a_all, t_all, inv, stats_all, scale = saved
     ws, row_offset, world = extra
     dx1, dx2, dls = kern.backward(x1, x2, a, t, a_all, t_all, inv, stats_all, scale, ws, row_offset, grad_out,
                                   normalized, precision)
-    if world > 1:
+    if world > 1 and dls_sum:
         dist.all_reduce(dls, group=group)
     return dx1, dx2, dls
 
@@ -211,22 +237,23 @@ class _InfoNCEFunction(torch.autograd.Function):
     not NCCL and as the reference orchestration the gloo tests exercise; CUDA + NCCL / single GPU use _FusedStep."""
 
     @staticmethod
-    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
+    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group, dls_sum, seg_key):
         with torch.cuda.device(x1.device):
             loss, saved, extra = _sharded_forward(_KERNELS, x1, x2, logit_scale, scale_max, normalized, precision, group)
         ctx.save_for_backward(*saved)
-        ctx.cfg = (extra, normalized, precision, group)
+        ctx.cfg = (extra, normalized, precision, group, dls_sum)
         ctx.set_materialize_grads(False)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         if grad_out is None:
-            return None, None, None, None, None, None, None
-        extra, normalized, precision, group = ctx.cfg
+            return (None,) * 9
+        extra, normalized, precision, group, dls_sum = ctx.cfg
         with torch.cuda.device(ctx.saved_tensors[0].device):
-            dx1, dx2, dls = _sharded_backward(_KERNELS, ctx.saved_tensors, extra, grad_out, normalized, precision, group)
-        return dx1, dx2, dls, None, None, None, None
+            dx1, dx2, dls = _sharded_backward(_KERNELS, ctx.saved_tensors, extra, grad_out, normalized, precision, group,
+                                              dls_sum)
+        return (dx1, dx2, dls) + (None,) * 6
 
 
 # ---------------------------------------------------------------------------- in-library orchestration (2 calls / step)
@@ -245,16 +272,16 @@ def _nccl_path():
     return None
 
 
-def _get_comm(group):
-    """NCCL communicator of the library for `group` (created once): rank 0's unique id is broadcast with torch.distributed."""
-    key = id(group)
+def _get_comm(group, dev):
+    """NCCL communicator of the library for (`group`, device) (created once; call with `dev` current): rank 0's unique id is
+    broadcast with torch.distributed.  The cache holds the group object, so its id cannot be recycled."""
+    key = (id(group), dev.index)
     if key in _COMMS:
-        return _COMMS[key]
+        return _COMMS[key][:3]
     lib = _cabi.lib()
     path = _nccl_path()
     _cabi.check(lib.vpa_comm_load(path.encode() if path else None), "vpa_comm_load")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    dev = torch.device("cuda", torch.cuda.current_device())
     uid = torch.zeros(128, dtype=torch.uint8)
     if rank == 0:
         buf = ctypes.create_string_buffer(128)
@@ -265,20 +292,20 @@ def _get_comm(group):
     raw = bytes(uid.cpu().numpy().tobytes())
     comm = ctypes.c_void_p()
     _cabi.check(lib.vpa_comm_init(raw, rank, world, ctypes.byref(comm)), "vpa_comm_init")
-    _COMMS[key] = (comm, rank, world)
-    return _COMMS[key]
+    _COMMS[key] = (comm, rank, world, group)
+    return _COMMS[key][:3]
 
 
 class _FusedStep(torch.autograd.Function):
     """vpa_infonce_fwd_sharded / vpa_infonce_bwd_sharded: the whole step, collectives included, in two C-ABI calls."""
 
     @staticmethod
-    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
+    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group, dls_sum, seg_key):
         lib = _cabi.lib()
-        comm, rank, world = (None, 0, 1) if group is None else _get_comm(group)
         b, D = x1.shape
         dev = x1.device
         with torch.cuda.device(dev):
+            comm, rank, world = (None, 0, 1) if group is None else _get_comm(group, dev)
             nbytes = lib.vpa_sharded_state_bytes(b, world, D, precision)
             state = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -287,40 +314,42 @@ class _FusedStep(torch.autograd.Function):
                 comm, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0), int(normalized),
                 _ptr(logit_scale), cap, precision, _ptr(state), nbytes, _ptr(loss), _stream()), "vpa_infonce_fwd_sharded")
         ctx.save_for_backward(x1, x2, state)
-        ctx.cfg = (comm, rank, world, normalized, precision)
+        ctx.cfg = (comm, rank, world, normalized, precision, dls_sum)
         ctx.set_materialize_grads(False)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         if grad_out is None:
-            return None, None, None, None, None, None, None
-        comm, rank, world, normalized, precision = ctx.cfg
+            return (None,) * 9
+        comm, rank, world, normalized, precision, dls_sum = ctx.cfg
         x1, x2, state = ctx.saved_tensors
         lib = _cabi.lib()
         dev = x1.device
         b, D = x1.shape
         with torch.cuda.device(dev):
             g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1)
-            dx1 = torch.empty_like(x1)
-            dx2 = torch.empty_like(x2)
+            dx1 = _grad_like(x1)
+            dx2 = _grad_like(x2)
             dls = torch.empty((), dtype=torch.float32, device=dev)
             _cabi.check(lib.vpa_infonce_bwd_sharded(
                 comm, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0), int(normalized),
-                precision, _ptr(g), _ptr(state), state.numel(), _ptr(dx1), _ptr(dx2), _ptr(dls), _stream()),
+                precision, _ptr(g), _ptr(state), state.numel(), _ptr(dx1), _ptr(dx2), _ptr(dls), int(dls_sum), _stream()),
                 "vpa_infonce_bwd_sharded")
-        return dx1, dx2, dls, None, None, None, None
+        return (dx1, dx2, dls) + (None,) * 6
 
 
 # ---------------------------------------------------------------------------- peer-memory transport (no NCCL on the data path)
 _P2P = {}
 
 
-def _get_p2p(group, b, D, precision, dev):
-    """Symmetric segment of the library for (group, shape): created once; the 64-byte CUDA IPC handles are exchanged with
-    torch.distributed (any backend: object all-gather), then every rank maps its peers' segments.  Returns None when some
-    rank cannot set it up (no peer access / IPC): the ranks agree on that and the caller uses the NCCL transport."""
-    key = (id(group), b, D, precision, dev.index)
+def _get_p2p(group, b, D, precision, dev, seg_key=None):
+    """Symmetric segment of the library for (group, shape, call site): created once; the 64-byte CUDA IPC handles are
+    exchanged with torch.distributed (any backend: object all-gather), then every rank maps its peers' segments.  A segment
+    keeps the forward state of its two most recent steps, so every call site that runs within one training step (the pairs
+    of a composite head) owns one: `seg_key` tells them apart.  Returns None when some rank cannot set it up (no peer
+    access / IPC): the ranks agree on that and the caller uses the NCCL transport."""
+    key = (id(group), b, D, precision, dev.index, seg_key)
     if key in _P2P:
         return _P2P[key]
     lib = _cabi.lib()
@@ -348,7 +377,7 @@ def _get_p2p(group, b, D, precision, dev):
         warnings.warn(f"vipant_b200: peer-memory transport unavailable on rank {rank} ({err or 'a peer failed'}); using NCCL")
         _P2P[key] = None
         return None
-    _P2P[key] = (handle, rank, world)
+    _P2P[key] = (handle, rank, world, group)      # (holds the group: its id cannot be recycled while the entry lives)
     if not _P2P_ATEXIT:
         import atexit
         atexit.register(_destroy_p2p)
@@ -429,12 +458,12 @@ class _P2PStep(torch.autograd.Function):
     the peers' memory (all-gather fused with the forward sweep); two C-ABI calls per step."""
 
     @staticmethod
-    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group):
+    def forward(ctx, x1, x2, logit_scale, scale_max, normalized, precision, group, dls_sum, seg_key):
         lib = _cabi.lib()
         b, D = x1.shape
         dev = x1.device
         with torch.cuda.device(dev):
-            handle, rank, world = _get_p2p(group, b, D, precision, dev)
+            handle, rank, world = _get_p2p(group, b, D, precision, dev, seg_key)[:3]
             loss = torch.empty((), dtype=torch.float32, device=dev)
             epoch = ctypes.c_uint32()
             cap = float(scale_max) if scale_max else 0.0
@@ -442,28 +471,29 @@ class _P2PStep(torch.autograd.Function):
                 handle, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0), int(normalized),
                 _ptr(logit_scale), cap, precision, _ptr(loss), ctypes.byref(epoch), _stream()), "vpa_infonce_fwd_p2p")
         ctx.save_for_backward(x1, x2)
-        ctx.cfg = (handle, epoch.value, rank, world, normalized, precision)
+        ctx.cfg = (handle, epoch.value, rank, world, normalized, precision, dls_sum)
         ctx.set_materialize_grads(False)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
         if grad_out is None:
-            return None, None, None, None, None, None, None
-        handle, epoch, rank, world, normalized, precision = ctx.cfg
+            return (None,) * 9
+        handle, epoch, rank, world, normalized, precision, dls_sum = ctx.cfg
         x1, x2 = ctx.saved_tensors
         lib = _cabi.lib()
         dev = x1.device
         b, D = x1.shape
         with torch.cuda.device(dev):
             g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1)
-            dx1 = torch.empty_like(x1)
-            dx2 = torch.empty_like(x2)
+            dx1 = _grad_like(x1)
+            dx2 = _grad_like(x2)
             dls = torch.empty((), dtype=torch.float32, device=dev)
             _cabi.check(lib.vpa_infonce_bwd_p2p(
                 handle, epoch, _ptr(x1), _ptr(x2), _DTYPES[x1.dtype], b, world, rank, D, x1.stride(0), x2.stride(0),
-                int(normalized), precision, _ptr(g), _ptr(dx1), _ptr(dx2), _ptr(dls), _stream()), "vpa_infonce_bwd_p2p")
-        return dx1, dx2, dls, None, None, None, None
+                int(normalized), precision, _ptr(g), _ptr(dx1), _ptr(dx2), _ptr(dls), int(dls_sum), _stream()),
+                "vpa_infonce_bwd_p2p")
+        return (dx1, dx2, dls) + (None,) * 6
 
 
 def _transport(group) -> str:
@@ -486,14 +516,23 @@ def _transport(group) -> str:
 
 def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, scale_max=None,
                  normalized: bool = False, precision: str = "bf16",
-                 group: Optional["dist.ProcessGroup"] = None) -> torch.Tensor:
+                 group: Optional["dist.ProcessGroup"] = None, logit_scale_grad: str = "sum",
+                 segment_key=None) -> torch.Tensor:
     """Symmetric InfoNCE  CE(s*a@t.T, arange) + CE(s*t@a.T, arange)  with s = min(exp(logit_scale), scale_max).
 
     x1, x2: (b, D) CUDA tensors (fp32 / bf16 / fp16), this process's rows.  With ``group`` the loss is the
     GLOBAL-batch loss over the concatenation of all ranks' rows in rank order (each rank must pass the same b);
-    the returned gradients are d(global loss)/d(local rows), and d/d logit_scale is all-reduced.
+    the returned feature gradients are d(global loss)/d(local rows).
+    logit_scale_grad: "sum" -- d/d logit_scale is summed over the ranks (the full derivative, identical everywhere; for
+    trainers that do NOT reduce the parameter's gradient again); "local" -- this rank's partial (sum over its own rows),
+    like the feature gradients: what a DistributedDataParallel trainer wants (DDP averages both kinds, so multiplying the
+    loss by the world size then reproduces the single-process update of the reference's `dp` mode exactly).
+    segment_key: any hashable that identifies the call site; call sites that run within one training step (the pairs of a
+    composite head) must use different keys -- each owns a peer-memory segment holding its forward state.
     precision "bf16": tcgen05 tensor cores (needs D in {64,128,192,256,384,512}); "fp32": exact FFMA path.
     """
+    if logit_scale_grad not in ("sum", "local"):
+        raise ValueError(f"logit_scale_grad must be 'sum' or 'local', got {logit_scale_grad!r}")
     _require_cuda(x1, x2)
     x1, x2 = _rows2d(x1), _rows2d(x2)
     if x1.shape != x2.shape:
@@ -511,16 +550,19 @@ def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, 
         ls = torch.tensor(float(ls))
     if ls.device != x1.device or ls.dtype != torch.float32:
         # `scaling=False` heads keep a plain CPU tensor (loss_head.py:252); its value is copied, no grad needed
-        ls = ls.to(device=x1.device, dtype=torch.float32)
+        if ls.device.type == "cpu" and not ls.requires_grad:
+            ls = _device_scalar(ls, x1.device)
+        else:
+            ls = ls.to(device=x1.device, dtype=torch.float32)
     transport = _transport(group)
     if transport == "local":
         group = None
     if transport == "p2p":
         with torch.cuda.device(x1.device):
-            if _get_p2p(group, x1.shape[0], x1.shape[1], prec, x1.device) is None:
+            if _get_p2p(group, x1.shape[0], x1.shape[1], prec, x1.device, segment_key) is None:
                 transport = "nccl" if dist.get_backend(group) == "nccl" else "host"
     fn = {"local": _FusedStep, "nccl": _FusedStep, "p2p": _P2PStep, "host": _InfoNCEFunction}[transport]
-    return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group)
+    return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group, logit_scale_grad == "sum", segment_key)
 
 
 def sim_rank_topk(q: torch.Tensor, k: torch.Tensor, gt: Optional[torch.Tensor] = None, topk: int = 0):

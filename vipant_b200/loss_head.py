@@ -6,14 +6,17 @@ same class names, constructor ``(cfg, **kwargs)``, ``forward(x1, x2, *args, **kw
 ``stats``, the ``logit_scale`` parameter name (checkpoint key) and the exact report strings
 (which ``cvap/monitor/esc50_clf.py:321`` regex-parses).  Differences, all by design:
   * arithmetic runs in libvipant_b200.so (no B x B logits, no argsort); CPU tensors raise;
-  * ``cfg.precision`` ("bf16" default | "fp32") and ``cfg.gather`` (False default) are optional extra
-    cfg fields; ``gather=True`` computes the GLOBAL-batch loss over the default process group, i.e. the
-    semantics of the reference's `dp` mode (loss on the gathered batch) under one process
-    per GPU;
+  * ``cfg.precision`` ("bf16" default | "fp32"), ``cfg.gather`` (False default) and ``cfg.ddp_average`` (False default)
+    are optional extra cfg fields; ``gather=True`` computes the GLOBAL-batch loss over the default process group, i.e. the
+    semantics of the reference's `dp` mode (loss on the gathered batch, SURVEY.md F5) under one process per GPU;
+    ``ddp_average=True`` is for a trainer that wraps the model in DistributedDataParallel (which AVERAGES gradients,
+    cvap/monitor/cvap.py:37): the loss is multiplied by the world size and d logit_scale stays a per-rank partial like the
+    feature gradients, so that after DDP's averaging every parameter gets exactly the `dp`-mode gradient;
   * BarlowLossHead / BarlowCELossHead and the BCE / LM heads of loss_more.py are out of scope.
 """
 from __future__ import annotations
 
+import itertools
 import json
 from collections import defaultdict
 
@@ -56,6 +59,9 @@ LOSS_HEADS_REGISTRY = _Registry("LOSS_HEADS")
 def build_loss_head(cfg, **kwargs):
     """Same contract as the reference factory (loss_head.py:22-23): keyed by ``cfg.name``."""
     return LOSS_HEADS_REGISTRY.get(cfg.name)(cfg, **kwargs)
+
+
+_HEAD_IDS = itertools.count()      # construction order: identical on every rank, names the peer-memory segment of a head
 
 
 def _is_primary():
@@ -222,6 +228,8 @@ class CELossHead(LossHead):
         self.scale_max = _cfg_get(cfg, "scale_max") or float("inf")
         self.precision = _cfg_get(cfg, "precision", "bf16")
         self.gather = bool(_cfg_get(cfg, "gather", False))
+        self.ddp_average = bool(_cfg_get(cfg, "ddp_average", False))
+        self._segment_key = next(_HEAD_IDS)
         self.reduce = False
 
     def copy_state_dict(self, state_dict):
@@ -241,8 +249,11 @@ class CELossHead(LossHead):
         precision = self.precision
         if precision == "bf16" and not F_.tensor_core_supported(x1.shape[-1]):
             precision = "fp32"      # embed dims the tcgen05 tiling does not cover run on the exact kernel
-        return F_.infonce_loss(x1, x2, self.logit_scale, scale_max=cap,
-                               normalized=bool(kwargs.get("normalized", False)), precision=precision, group=group)
+        ddp = self.ddp_average and group is not None
+        loss = F_.infonce_loss(x1, x2, self.logit_scale, scale_max=cap,
+                               normalized=bool(kwargs.get("normalized", False)), precision=precision, group=group,
+                               logit_scale_grad="local" if ddp else "sum", segment_key=self._segment_key)
+        return loss * dist.get_world_size() if ddp else loss
 
 
 class _LayerNormF32(nn.LayerNorm):

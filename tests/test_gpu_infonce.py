@@ -292,3 +292,93 @@ def test_composite_head_al_pair():
     assert abs(loss.item() - float(g["loss"])) <= 1e-3 * float(g["loss"])
     assert rel(aud.grad.cpu().numpy(), g["dx1"]) <= 1e-2 and rel(txt.grad.cpu().numpy(), g["dx2"]) <= 1e-2
     assert head.stats(nstep=1).startswith("al ")
+
+
+def test_row_strided_views_get_correct_gradients():
+    """Inputs that are row-strided views (`feats[:, :512]`, the CLS token `hidden[:, 0, :]`) are read in place; their
+    gradient buffers must carry the same leading dimension (`empty_like` densifies a view and the finalize
+    kernel addresses x and dx with one ld -> out-of-bounds writes)."""
+    import vipant_b200 as vb
+    B, D = 384, 512
+    x1n, x2n = io.make_pair(B, D, 0.3, 77)
+    ref = io.infonce_closed_form(x1n, x2n)
+    for precision in ("bf16", "fp32"):
+        wide = torch.zeros(B, 768, device="cuda")
+        wide[:, :D] = torch.from_numpy(x1n).cuda()
+        hidden = torch.zeros(B, 3, D, device="cuda")
+        hidden[:, 0, :] = torch.from_numpy(x2n).cuda()
+        guard1, guard2 = wide[:, D:].clone(), hidden[:, 1:, :].clone()
+        wide.requires_grad_(True)
+        hidden.requires_grad_(True)
+        v1, v2 = wide[:, :D], hidden[:, 0, :]
+        assert v1.stride(0) == 768 and v2.stride(0) == 3 * D
+        ls = torch.tensor(math.log(1 / 0.07), device="cuda", requires_grad=True)
+        loss = vb.infonce_loss(v1, v2, ls, precision=precision)
+        loss.backward()
+        tol = TOL[precision]
+        assert abs(loss.item() - ref.loss) <= tol["loss"] * abs(ref.loss)
+        assert rel(wide.grad[:, :D].cpu().numpy(), ref.dx1) <= tol["grad"]
+        assert rel(hidden.grad[:, 0, :].cpu().numpy(), ref.dx2) <= tol["grad"]
+        assert float(wide.grad[:, D:].abs().max()) == 0.0 and float(hidden.grad[:, 1:, :].abs().max()) == 0.0
+        assert torch.equal(wide.detach()[:, D:], guard1) and torch.equal(hidden.detach()[:, 1:, :], guard2)
+
+
+def test_constant_temperature_head_scaling_false():
+    """`scaling=False` (loss_head.py:252): logit_scale is a plain CPU tensor log(1) = 0, never moved by .cuda(), no gradient."""
+    import vipant_b200 as vb
+    x1n, x2n = io.make_pair(200, 512, 0.3, 5)
+    head = vb.build_loss_head(Cfg(name="CELossHead", scaling=False, scale_max=None)).cuda().train()
+    assert not isinstance(head.logit_scale, torch.nn.Parameter) and head.logit_scale.device.type == "cpu"
+    x1 = torch.from_numpy(x1n).cuda().requires_grad_(True)
+    x2 = torch.from_numpy(x2n).cuda().requires_grad_(True)
+    for _ in range(2):              # second call: the cached device copy of the constant
+        x1.grad = x2.grad = None
+        loss = head(x1, x2)
+        loss.backward()
+    ref = io.infonce_closed_form(x1n, x2n, 0.0)
+    assert abs(loss.item() - ref.loss) <= 1e-3 * abs(ref.loss)
+    assert rel(x1.grad.cpu().numpy(), ref.dx1) <= 1e-2 and rel(x2.grad.cpu().numpy(), ref.dx2) <= 1e-2
+
+
+def test_vace_head_forward_weighted_pairs():
+    """VACELossHead.forward (loss_head.py:497-598): five weighted InfoNCE pairs over five feature matrices, each pair with
+    its own temperature; gradients of a shared modality add up over its pairs."""
+    import vipant_b200 as vb
+    B, D = 256, 512
+    rng = np.random.default_rng(3)
+    feats = [rng.standard_normal((B, D)).astype(np.float32) for _ in range(5)]      # images, images_v1, audios_v1, images_v2, audios_v2
+    w = dict(vp_w=1.0, ap_w=0.5, va_w=2.0, vv_w=0.25, aa_w=0.75)
+    head = vb.build_loss_head(Cfg(name="VACELossHead", scaling=True, scale_max=None, vp=True, ap=True, va=True, vv=True, aa=True,
+                                  **w)).cuda().train()
+    xs = [torch.from_numpy(f).cuda().requires_grad_(True) for f in feats]
+    loss = head(*xs, normalized=False)
+    loss.backward()
+    pairs = [(1, 0, w["vp_w"]), (2, 0, w["ap_w"]), (1, 2, w["va_w"]), (1, 3, w["vv_w"]), (2, 4, w["aa_w"])]
+    want = 0.0
+    grads = [np.zeros((B, D)) for _ in range(5)]
+    for i, j, wt in pairs:
+        r = io.infonce_closed_form(feats[i], feats[j], grad_output=wt)
+        want += wt * r.loss
+        grads[i] += r.dx1
+        grads[j] += r.dx2
+    assert abs(loss.item() - want) <= 1e-3 * abs(want)
+    for x, g in zip(xs, grads):
+        assert rel(x.grad.cpu().numpy(), g) <= 1e-2
+    assert head.stats(nstep=1).split()[0::2] == ["vp", "ap", "va", "vv", "aa"]
+
+
+def test_one_process_two_devices():
+    """The reference's `dp` mode is one process driving several GPUs: per-device kernel attributes (232 KB dynamic shared
+    memory) and the SM-count cache must follow the current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import vipant_b200 as vb
+    x1n, x2n = io.make_pair(512, 512, 0.3, 9)
+    ref = io.infonce_closed_form(x1n, x2n)
+    for dev in (0, 1, 0):
+        x1 = torch.from_numpy(x1n).to(f"cuda:{dev}").requires_grad_(True)
+        x2 = torch.from_numpy(x2n).to(f"cuda:{dev}").requires_grad_(True)
+        ls = torch.tensor(math.log(1 / 0.07), device=f"cuda:{dev}", requires_grad=True)
+        loss = vb.infonce_loss(x1, x2, ls, precision="bf16")
+        loss.backward()
+        assert abs(loss.item() - ref.loss) <= 1e-3 * abs(ref.loss) and rel(x1.grad.cpu().numpy(), ref.dx1) <= 1e-2

@@ -129,3 +129,120 @@ def test_nvls_multicast_transport_two_gpus():
     env = {"VPA_P2P_MODE": "nvls", "VIPANT_REQUIRE_P2P": "1"}
     mp.spawn(_worker, args=(world, _free_port(), 1024, 512, "bf16", "p2p", False, 4, out, env), nprocs=world, join=True)
     _check(out, world, 1024, 512, "bf16", env)
+
+
+def _worker_many_steps(rank, world, port, B, D, steps, out):
+    """>= 50 steps with DIFFERENT data every step: shakes the parity buffers / epoch flags of the peer-memory transport.
+    Every rank holds the whole batch too and checks each step against the single-GPU path of the same library."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VIPANT_TRANSPORT="p2p", VIPANT_REQUIRE_P2P="1")
+    torch.cuda.set_device(0 if torch.cuda.device_count() < world else rank)
+    shared = torch.cuda.device_count() < world
+    dist.init_process_group("gloo" if shared else "nccl", rank=rank, world_size=world)
+    try:
+        import vipant_b200 as vb
+        b = B // world
+        gen = torch.Generator(device="cuda").manual_seed(7)           # same stream of batches on every rank
+        worst = 0.0
+        for i in range(steps):
+            f1 = torch.randn(B, D, device="cuda", generator=gen)
+            f2 = 0.3 * f1 + 0.7 * torch.randn(B, D, device="cuda", generator=gen)
+            ls_v = math.log(1 / 0.07) + 0.01 * i
+            x1 = f1[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+            x2 = f2[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+            ls = torch.tensor(ls_v, device="cuda", requires_grad=True)
+            loss = vb.infonce_loss(x1, x2, ls, group=dist.group.WORLD)
+            loss.backward()
+            g1, g2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+            ls2 = torch.tensor(ls_v, device="cuda", requires_grad=True)
+            full = vb.infonce_loss(g1, g2, ls2)
+            full.backward()
+            e = max(abs(loss.item() - full.item()) / abs(full.item()),
+                    float((x1.grad - g1.grad[rank * b:(rank + 1) * b]).norm() / g1.grad[rank * b:(rank + 1) * b].norm()),
+                    float((x2.grad - g2.grad[rank * b:(rank + 1) * b]).norm() / g2.grad[rank * b:(rank + 1) * b].norm()),
+                    abs(ls.grad.item() - ls2.grad.item()) / abs(ls2.grad.item()))
+            worst = max(worst, e)
+        torch.cuda.synchronize()
+        out[rank] = worst
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p2p_fifty_steps_changing_data():
+    """Sharded result == unsharded result of the same kernels on every one of 50 steps (fp32 summation order differs between
+    the two decompositions: 1e-4)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_many_steps, args=(world, _free_port(), 1024, 512, 50, out), nprocs=world, join=True)
+    assert len(out) == world and max(out.values()) <= 1e-4, dict(out)
+
+
+def _worker_composite(rank, world, port, out):
+    """Three InfoNCE pairs per step under gather=True (VALCELossHead va + lv + al): every pair owns a peer-memory segment
+    (one shared segment keeps two steps only and the first pair's backward failed), and ddp_average returns the
+    per-rank partial d logit_scale."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VIPANT_TRANSPORT="p2p", VIPANT_REQUIRE_P2P="1")
+    torch.cuda.set_device(0 if torch.cuda.device_count() < world else rank)
+    shared = torch.cuda.device_count() < world
+    dist.init_process_group("gloo" if shared else "nccl", rank=rank, world_size=world)
+    try:
+        import vipant_b200 as vb
+        from oracle.reference_loader import Cfg
+        B, D = 512, 512
+        b = B // world
+        rng = np.random.default_rng(11)
+        feats = [rng.standard_normal((B, D)).astype(np.float32) for _ in range(3)]
+        res = {}
+        for ddp in (False, True):
+            head = vb.build_loss_head(Cfg(name="VALCELossHead", scaling=True, scale_max=None, va=True, lv=True, al=True,
+                                          gather=True, ddp_average=ddp)).cuda().train()
+            xs = [torch.from_numpy(f[rank * b:(rank + 1) * b]).cuda().requires_grad_(True) for f in feats]
+            for _ in range(2):        # two steps: segments are reused
+                for x in xs:
+                    x.grad = None
+                head.zero_grad()
+                loss = head(*xs, normalized=False)
+                loss.backward()
+            torch.cuda.synchronize()
+            res[ddp] = (loss.item(), [x.grad.cpu().numpy() for x in xs],
+                        [getattr(head, a).logit_scale.grad.item() for a in ("loss_head_va", "loss_head_lv", "loss_head_al")])
+        out[rank] = res
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_three_pairs_per_step_and_ddp_average():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_composite, args=(world, _free_port(), out), nprocs=world, join=True)
+    B, D, b = 512, 512, 256
+    rng = np.random.default_rng(11)
+    feats = [rng.standard_normal((B, D)).astype(np.float32) for _ in range(3)]
+    pairs = [(0, 1), (0, 2), (1, 2)]            # va, lv, al
+    refs = [io.infonce_closed_form(feats[i], feats[j]) for i, j in pairs]
+    want_loss = sum(r.loss for r in refs)
+    grads = [np.zeros((B, D)) for _ in range(3)]
+    for (i, j), r in zip(pairs, refs):
+        grads[i] += r.dx1
+        grads[j] += r.dx2
+
+    def rel(a, r):
+        return float(np.linalg.norm(a.astype(np.float64) - r) / np.linalg.norm(r))
+    for rank in range(world):
+        loss, g, dls = out[rank][False]
+        assert abs(loss - want_loss) <= 1e-3 * want_loss
+        for m in range(3):
+            assert rel(g[m], grads[m][rank * b:(rank + 1) * b]) <= 1e-2
+        for k, r in enumerate(refs):
+            assert abs(dls[k] - r.dlogit_scale) <= 1e-2 * abs(r.dlogit_scale)
+    # ddp_average: loss x world, gradients x world, d logit_scale = world x (per-rank partial): the MEAN over ranks (what DDP
+    # computes) equals the single-process gradient for the features' encoders and for logit_scale alike
+    for k, r in enumerate(refs):
+        mean_dls = np.mean([out[rank][True][2][k] for rank in range(world)])
+        assert abs(mean_dls - r.dlogit_scale) <= 1e-2 * abs(r.dlogit_scale)
+    for rank in range(world):
+        assert abs(out[rank][True][0] - world * want_loss) <= 1e-3 * world * want_loss
+        assert rel(out[rank][True][1][0] / world, grads[0][rank * b:(rank + 1) * b]) <= 1e-2

@@ -5,11 +5,12 @@ Tolerances: the golden vectors are fp32 reference outputs, the closed form runs 
 loss, 2e-4 relative (Frobenius) on gradients (fp32 rounding of a 2048-term softmax/matmul chain).
 """
 import math
+import os
 
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import GOLDEN, load_golden
 from oracle import infonce_oracle as io
 from oracle import retrieval_oracle as ro
 from oracle.make_golden import (INFONCE_CASES, checksum, infonce_inputs, retrieval_inputs_1v5, retrieval_inputs_nn,

@@ -38,9 +38,11 @@ __device__ __forceinline__ void normalize_row(const void* x, int64_t ld, int64_t
   inv_out = 1.0f / nrm;
   if (lane == 0 && inv_norm) inv_norm[row] = inv_out;
   const int64_t obase = row * (int64_t)D;
+  const bool rcp = y_f32 == nullptr;      // bf16 operands only: multiply by 1/||x|| (see normalize_pair_kernel)
   auto emit = [&](int c, float4 q) {
-    if (!already) {  // true division, as the reference does (x / norm)
-      q.x = q.x / nrm; q.y = q.y / nrm; q.z = q.z / nrm; q.w = q.w / nrm;
+    if (!already) {
+      if (rcp) { q.x *= inv_out; q.y *= inv_out; q.z *= inv_out; q.w *= inv_out; }
+      else { q.x = q.x / nrm; q.y = q.y / nrm; q.z = q.z / nrm; q.w = q.w / nrm; }      // true division, as the reference does
     }
     if (y_f32) store4<VPA_F32>(y_f32, obase + 4 * c, q);
     if (y_bf16) store4<VPA_BF16>(y_bf16, obase + 4 * c, q);
@@ -73,7 +75,10 @@ normalize_cast_kernel(const void* __restrict__ x, int64_t rows, int D, int64_t l
 // Both modalities + the diagonal cosine <a_i, t_i> in one launch (training path).  NV = float4 chunks per lane
 // (D <= 128*NV): all 2*NV 16-byte loads of a row pair are issued before anything depends on them, and the small
 // register footprint keeps >= 32 warps per SM resident -- the kernel is pure HBM streaming.
-template <int DTYPE, int NV>
+// RCP: the outputs are bf16 operands only (tensor-core mode) -> multiply by 1/||x|| instead of the reference's true
+// division: the quotient is rounded to 8 mantissa bits anyway, and 2*D IEEE divisions per row pair made the kernel
+// instruction-bound (ncu r01: issue slots 70 %, MUFU 67 %, 66 % of the HBM copy peak).  fp32 outputs keep `x / norm`.
+template <int DTYPE, int NV, bool RCP>
 __global__ void __launch_bounds__(kNormWarps * 32, NV <= 4 ? 4 : 2)
 normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, int64_t rows, int D,
                       int64_t ld1, int64_t ld2, int already,
@@ -104,9 +109,10 @@ normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, 
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
   const float n1 = already ? 1.0f : sqrtf(s1), n2 = already ? 1.0f : sqrtf(s2);
+  const float r1 = 1.0f / n1, r2 = 1.0f / n2;
   if (lane == 0) {
-    if (inv1) inv1[row] = 1.0f / n1;
-    if (inv2) inv2[row] = 1.0f / n2;
+    if (inv1) inv1[row] = r1;
+    if (inv2) inv2[row] = r2;
   }
   float dot = 0.f;
   const int64_t obase = row * (int64_t)D;
@@ -115,9 +121,14 @@ normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, 
     const int c = lane + 32 * v;
     if (c < nvec) {
       float4 p = ka[v], q = kt[v];
-      if (!already) {   // true division, as the reference does (x / norm)
-        p.x = p.x / n1; p.y = p.y / n1; p.z = p.z / n1; p.w = p.w / n1;
-        q.x = q.x / n2; q.y = q.y / n2; q.z = q.z / n2; q.w = q.w / n2;
+      if (!already) {
+        if constexpr (RCP) {
+          p.x *= r1; p.y *= r1; p.z *= r1; p.w *= r1;
+          q.x *= r2; q.y *= r2; q.z *= r2; q.w *= r2;
+        } else {        // true division, as the reference does (x / norm)
+          p.x = p.x / n1; p.y = p.y / n1; p.z = p.z / n1; p.w = p.w / n1;
+          q.x = q.x / n2; q.y = q.y / n2; q.z = q.z / n2; q.w = q.w / n2;
+        }
       }
       if (a_f32) store4<VPA_F32>(a_f32, obase + 4 * c, p);
       if (t_f32) store4<VPA_F32>(t_f32, obase + 4 * c, q);
@@ -198,19 +209,20 @@ int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t 
   if (int e = check_rows(x1, rows, D, ld1, in_dtype)) return e;
   if (int e = check_rows(x2, rows, D, ld2, in_dtype)) return e;
   if (rows == 0) return 0;
-  if (D > 128 * kMaxVec) {  // rows too long for the register-resident pair kernel: three launches
-    if (int e = normalize_cast_launch(x1, in_dtype, rows, D, ld1, already, a_bf16, a_f32, inv1, st)) return e;
-    if (int e = normalize_cast_launch(x2, in_dtype, rows, D, ld2, already, t_bf16, t_f32, inv2, st)) return e;
-    return set_error(VPA_E_UNSUPPORTED, "normalize_pair: D=%d > %d needs the diag kernel (not built)", D, 128 * kMaxVec);
-  }
+  if (D > 128 * kMaxVec)      // rows too long for the register-resident pair kernel: rejected BEFORE any work is enqueued
+    return set_error(VPA_E_UNSUPPORTED, "normalize_pair: D=%d > %d is not supported (use vpa_normalize_cast per matrix)", D,
+                     128 * kMaxVec);
   dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps)), block(kNormWarps * 32);
   auto* ab = reinterpret_cast<__nv_bfloat16*>(a_bf16);
   auto* tb = reinterpret_cast<__nv_bfloat16*>(t_bf16);
   const int nv = D <= 128 ? 1 : (D <= 256 ? 2 : (D <= 512 ? 4 : 8));
   prof_begin(PROF_NORMALIZE, st);
-#define VPA_PAIR(DT, NV)                                                                                               \
-  normalize_pair_kernel<DT, NV><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, t_f32, inv1, \
-                                                        inv2, diag_cos, diag_from_bf16)
+  const bool rcp = a_f32 == nullptr && t_f32 == nullptr;      // bf16 operands only
+#define VPA_PAIR(DT, NV)                                                                                                 \
+  if (rcp) normalize_pair_kernel<DT, NV, true><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, \
+                                                                       t_f32, inv1, inv2, diag_cos, diag_from_bf16);      \
+  else normalize_pair_kernel<DT, NV, false><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32,    \
+                                                                    t_f32, inv1, inv2, diag_cos, diag_from_bf16)
 #define VPA_PAIR_NV(DT)                 \
   switch (nv) {                         \
     case 1: VPA_PAIR(DT, 1); break;     \

@@ -34,6 +34,7 @@ extern "C" {
 #define VPA_F32 0
 #define VPA_BF16 1
 #define VPA_F16 2
+#define VPA_U8 3 /* label matrices only */
 
 /* arithmetic of the similarity contraction */
 #define VPA_PREC_BF16_TC 0   /* bf16 operands, fp32 accumulate, tcgen05 tensor cores (TMA + TMEM)   */
@@ -171,6 +172,37 @@ int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int 
                       int64_t ldq, int64_t ldk, const int32_t* gt_idx, int g, int k,
                       int64_t* topk_idx, float* topk_val, int32_t* ranks,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same scoring with the similarity tile consumed in registers -- S is never written -- and BOTH directions from one pass:
+ * ranks_q[i,c] = position of key gt_q[i,c] in row i of S = Q.K^T (as above), ranks_k[j,c] = position of query gt_k[j,c] in
+ * COLUMN j of S, i.e. in row j of the other direction's similarity K.Q^T (fp32 fmaf is commutative in its factors: the same
+ * values bit for bit).  One call therefore serves both halves of LossHead.report / retrieval_eval (loss_head.py:115-117 and
+ * :128-130; :139-142 and :156-158; :81-91 and :95-103) for 2*N*M*D flops.  top1_*: the best key per query / best query per
+ * key (index int64 + value), "larger value, then lower index" -- the k = 1 of `ind[:, :1]` (:182, :381-385); NaN similarities
+ * sort FIRST, as torch.argsort(descending=True) places them.  Any output group may be omitted (g = 0 / NULL pointers).
+ * Ground-truth indices outside [0, M) / [0, N) yield rank 0 (never counted); g_q, g_k <= 8; k > 1 needs vpa_sim_rank_topk. */
+size_t vpa_sim_fused_workspace_bytes(int64_t N, int64_t M, int g_q, int g_k);
+int vpa_sim_rank_fused(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
+                       const int32_t* gt_q, int g_q, const int32_t* gt_k, int g_k, int32_t* ranks_q, int32_t* ranks_k,
+                       int64_t* top1_q, float* top1_val_q, int64_t* top1_k, float* top1_val_k, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-label ranking metrics of the AudioSet zero-shot / tagging evaluation.  Replaces the per-class scikit-learn calls of
+ *   /root/reference/cvap/module/decoder/loss_more.py:92-123 (BCELossHead.report, reached from BCELossHead.zero_shot :77-84 and
+ *   cvap/monitor/audioset_clf.py:377-404): average_precision_score, roc_auc_score and the middle point of
+ *   precision_recall_curve for every class, plus the micro-averaged AP over all (sample, class) pairs.
+ * S (N, C) fp32 scores, Y (N, C) labels (VPA_F32 or VPA_U8; positive == 1), row-major with leading dimensions.
+ * per_class[c] = { AP, ROC-AUC, precision_mid, recall_mid } (double; AP / AUC are NaN where scikit-learn has none);
+ * flags[c] bit 0: class without a positive, bit 1: without a negative; support[c] = positives; micro_ap (may be NULL).
+ * truncate_pr != 0: scikit-learn 1.0.1's precision_recall_curve (the release the reference pins), which stops the curve
+ * at full recall; 0: the un-truncated curve of releases >= 1.1.  N <= 32768 samples per call (one CTA sorts a class in
+ * shared memory).  All sums are fixed-order fp64: results are deterministic.
+ * ------------------------------------------------------------------------------------------ */
+size_t vpa_multilabel_workspace_bytes(int64_t N, int C);
+int vpa_multilabel_scores(const float* S, int64_t ld_s, const void* Y, int y_dtype, int64_t ld_y, int64_t N, int C,
+                          int truncate_pr, double* per_class, int32_t* flags, int32_t* support, double* micro_ap,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row-sharded training step, orchestrated inside the library: TWO calls per step (forward, backward) instead of a

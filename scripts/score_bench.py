@@ -42,6 +42,16 @@ ms21, _ = timed(lambda: vb.sim_rank_topk(tn, an, gt21))
 sim_us, _ = prof(3); rank_us, _ = prof(4)
 out["c4_t2a"] = {"call_ms": ms21, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us,
                  "rank_gbs": (4 * N * M + 4 * M) / (rank_us * 1e-6) / 1e9}
+# fused path: the similarity tile is consumed in registers (vpa_sim_rank_fused); kernel time = reference + tile kernels
+from vipant_b200 import functional as F_
+ms_a2t, _ = timed(lambda: F_.sim_rank_fused(an, tn, gt_q=gt12))
+fa2t_us, _ = prof(3)
+ms_both, _ = timed(lambda: F_.sim_rank_fused(an, tn, gt_q=gt12, gt_k=gt21))
+fboth_us, _ = prof(3)
+out["c4_fused"] = {"a2t_call_ms": ms_a2t, "a2t_kernels_us": fa2t_us, "both_directions_call_ms": ms_both,
+                   "both_directions_kernels_us": fboth_us, "flops": 2 * N * M * 512,
+                   "both_tflops_fp32": 2 * N * M * 512 / (fboth_us * 1e-6) / 1e12,
+                   "algorithmic_bytes_4(N+M)D": 4 * (N + M) * 512}
 lib.vpa_profile_enable(0)
 
 def full_report():

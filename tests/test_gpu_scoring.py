@@ -153,3 +153,95 @@ def test_report_with_gold_file(strings, tmp_path):
         for i in range(0, len(ids), 50):
             head(torch.from_numpy(a[i:i + 50]).cuda(), torch.from_numpy(t[i:i + 50]).cuda(), normalized=False, names=ids[i:i + 50])
     assert head.report(gold_file=str(path)) == strings["retrieval_nn_goldfile"]
+
+
+@pytest.mark.parametrize("N,M,D,gq,gk", [(975, 4875, 512, 5, 1), (130, 70, 36, 2, 3), (1, 1, 4, 1, 1), (64, 5000, 128, 0, 1),
+                                         (300, 300, 512, 1, 1), (2000, 50, 512, 0, 0)])
+def test_fused_both_directions(N, M, D, gq, gk):
+    """vpa_sim_rank_fused: ranks of both directions and both nearest neighbours from one pass over the similarity (never
+    written).  Checker 1: the materialising kernels of the same library -- the similarities are the same fp32 sums, so the
+    integer results must be IDENTICAL, no margin.  Checker 2: the fp64 oracle on entries whose margin is >= 1e-6."""
+    import vipant_b200 as vb
+    from vipant_b200 import functional as F_
+    gen = torch.Generator().manual_seed(1000 + N + M)
+    q = torch.randn(N, D, generator=gen)
+    k = 0.5 * q[torch.arange(M) % N] + torch.randn(M, D, generator=gen)
+    qn, kn = vb.l2_normalize(q.cuda()), vb.l2_normalize(k.cuda())
+    gt_q = torch.randint(0, M, (N, gq), generator=gen) if gq else None
+    gt_k = torch.randint(0, N, (M, gk), generator=gen) if gk else None
+    res = F_.sim_rank_fused(qn, kn, gt_q=None if gt_q is None else gt_q.cuda(), gt_k=None if gt_k is None else gt_k.cuda(),
+                            top1_q=True, top1_k=True)
+    # the same values through the materialised path (top-2 forces it)
+    r_q, top_q, val_q = vb.sim_rank_topk(qn, kn, None if gt_q is None else gt_q.cuda(), topk=min(2, M))
+    r_k, top_k, val_k = vb.sim_rank_topk(kn, qn, None if gt_k is None else gt_k.cuda(), topk=min(2, N))
+    if gq:
+        assert torch.equal(res["ranks_q"], r_q)
+    if gk:
+        assert torch.equal(res["ranks_k"], r_k)
+    assert torch.equal(res["top1_q"][0], top_q[:, 0]) and torch.equal(res["top1_q"][1], val_q[:, 0])
+    assert torch.equal(res["top1_k"][0], top_k[:, 0]) and torch.equal(res["top1_k"][1], val_k[:, 0])
+    # fp64 oracle
+    S = qn.double().cpu().numpy() @ kn.double().cpu().numpy().T
+
+    def margins(S64, gt):          # per (row, gt): smallest |S[i,k] - S[i,gt]| over k != gt (SURVEY 8c(ii))
+        out = np.empty(gt.shape)
+        rows = np.arange(S64.shape[0])
+        for c in range(gt.shape[1]):
+            d = np.abs(S64 - S64[rows, gt[:, c]][:, None])
+            d[rows, gt[:, c]] = np.inf
+            out[:, c] = d.min(1) if S64.shape[1] > 1 else np.inf
+        return out
+    if gq:
+        want = ro.rank_of(S, gt_q.numpy())
+        ok = margins(S, gt_q.numpy()) >= 1e-6
+        assert np.array_equal(res["ranks_q"].cpu().numpy()[ok], want[ok]) and ok.mean() > 0.99
+    if gk:
+        want = ro.rank_of(S.T, gt_k.numpy())
+        ok = margins(S.T, gt_k.numpy()) >= 1e-6
+        assert np.array_equal(res["ranks_k"].cpu().numpy()[ok], want[ok]) and ok.mean() > 0.99
+    srt = np.sort(S, axis=1)
+    clear = (srt[:, -1] - srt[:, -2] >= 1e-6) if M > 1 else np.ones(N, bool)
+    assert np.array_equal(res["top1_q"][0].cpu().numpy()[clear], S.argmax(1)[clear])
+
+
+def test_fused_ties_nan_and_bad_indices():
+    import vipant_b200 as vb
+    from vipant_b200 import functional as F_
+    q = torch.zeros(2, 8, device="cuda"); q[0, 0] = 1; q[1, 1] = 1
+    k = torch.zeros(6, 8, device="cuda")
+    k[0, 0] = 1; k[1, 0] = 3; k[2, 0] = 3; k[3, 0] = 2; k[4, 0] = 3; k[5, 1] = 5
+    res = F_.sim_rank_fused(q, k, gt_q=torch.tensor([[3, 2], [5, 0]], device="cuda"), gt_k=torch.tensor([1, 0, 0, 1, 0, 1], device="cuda"),
+                            top1_q=True, top1_k=True)
+    assert res["ranks_q"].tolist() == [[3, 1], [0, 1]]            # stable descending position: ties -> lower index first
+    assert res["top1_q"][0].tolist() == [1, 5] and res["top1_q"][1].tolist() == [3.0, 5.0]
+    # columns: keys 0-4 see (q0: k[j,0], q1: 0); key 5 sees (0, 5).  Rank of the designated query within each key's row:
+    assert res["ranks_k"][:, 0].tolist() == [1, 0, 0, 1, 0, 0]
+    assert res["top1_k"][0].tolist() == [0, 0, 0, 0, 0, 1]
+    # out-of-range ground truth: rank 0 from the fused kernel (documented), a ValueError from the materialising path
+    bad = torch.tensor([[6, 0], [0, -1]], device="cuda")
+    r = F_.sim_rank_fused(q, k, gt_q=bad)["ranks_q"]
+    assert r[0, 0].item() == 0 and r[1, 1].item() == 0
+    with pytest.raises(ValueError):
+        vb.sim_rank_topk(q, k, bad, topk=3)
+    with pytest.raises(ValueError):
+        F_.sim_rank_fused(q, k, gt_q=torch.zeros(2, 9, dtype=torch.long, device="cuda"))
+    # NaN similarities sort first, as torch.argsort(descending=True) places them
+    kn = k.clone(); kn[4, 0] = float("nan")
+    res = F_.sim_rank_fused(q[:1], kn, top1_q=True)
+    assert res["top1_q"][0].tolist() == [4]
+    assert torch.argsort(q[:1] @ kn.T, descending=True)[0, 0].item() == 4
+
+
+def test_retrieval_eval_static_and_mixed_normalisation(strings):
+    """`retrieval_eval` on its own (reference :79-107) and a stash whose batches arrive partly pre-normalised."""
+    import vipant_b200 as vb
+    g = load_golden("retrieval_1v5_small")
+    a, t = retrieval_inputs_1v5(n=150, seed=int(g["seed"]))
+    an, tn = vb.l2_normalize(torch.from_numpy(a).cuda()), vb.l2_normalize(torch.from_numpy(t).cuda())
+    want = strings["retrieval_1v5_small"].split("REFERENCE\n")[1]
+    assert vb.LossHead.retrieval_eval(an, tn, k=5) == want
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None)).cuda().eval()
+    with torch.no_grad():
+        head(torch.from_numpy(a[:64]).cuda(), torch.from_numpy(t[:320]).cuda(), normalized=False)
+        head(an[64:], tn[320:], normalized=True)
+    assert head.report() == strings["retrieval_1v5_small"]

@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 
 from . import build as _build
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, U8 = 0, 1, 2, 3
 PREC_BF16_TC, PREC_FP32_SIMT = 0, 1
 
 # name -> (restype, argtypes); mirrors include/vipant_b200.h one to one
@@ -62,6 +62,12 @@ _SIGNATURES = {
     "vpa_sim_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vpa_sim_rank_topk": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vpa_sim_fused_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "vpa_sim_rank_fused": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vpa_multilabel_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "vpa_multilabel_scores": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vpa_infonce_host_scratch_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "vpa_infonce_step_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_int,
                                       c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -88,6 +88,17 @@ int sim_rank_topk_launch(const float* Q, const float* K, int64_t N, int64_t M, i
                          const int32_t* gt_idx, int g, int k, int64_t* topk_idx, float* topk_val,
                          int32_t* ranks, float* S, cudaStream_t st);
 
+size_t sim_fused_workspace_bytes(int64_t N, int64_t M, int g_q, int g_k);
+int sim_rank_fused_launch(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
+                          const int32_t* gt_q, int g_q, const int32_t* gt_k, int g_k, int32_t* ranks_q, int32_t* ranks_k,
+                          int64_t* top1_q, float* top1_val_q, int64_t* top1_k, float* top1_val_k, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st);
+
+size_t multilabel_workspace_bytes(int64_t N, int C);
+int multilabel_scores_launch(const float* S, int64_t ld_s, const void* Y, int y_dtype, int64_t ld_y, int64_t N, int C,
+                             int truncate_pr, double* per_class, int32_t* flags, int32_t* support, double* micro_ap,
+                             void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 static int sm_count() {      // of the CURRENT device (a process may drive several)
   static int cached[64] = {};
   int dev = 0, v = 0;
@@ -480,6 +491,25 @@ int vpa_sim_rank_topk(const float* Q, const float* K, int64_t N, int64_t M, int 
     return set_error(VPA_E_WORKSPACE, "sim_rank_topk: workspace %zu < %zu", workspace_bytes, vpa_sim_workspace_bytes(N, M));
   return sim_rank_topk_launch(Q, K, N, M, D, ldq, ldk, gt_idx, g, k, topk_idx, topk_val, ranks,
                               static_cast<float*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+size_t vpa_sim_fused_workspace_bytes(int64_t N, int64_t M, int g_q, int g_k) { return sim_fused_workspace_bytes(N, M, g_q, g_k); }
+
+int vpa_sim_rank_fused(const float* Q, const float* K, int64_t N, int64_t M, int D, int64_t ldq, int64_t ldk,
+                       const int32_t* gt_q, int g_q, const int32_t* gt_k, int g_k, int32_t* ranks_q, int32_t* ranks_k,
+                       int64_t* top1_q, float* top1_val_q, int64_t* top1_k, float* top1_val_k, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return sim_rank_fused_launch(Q, K, N, M, D, ldq, ldk, gt_q, g_q, gt_k, g_k, ranks_q, ranks_k, top1_q, top1_val_q, top1_k,
+                               top1_val_k, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t vpa_multilabel_workspace_bytes(int64_t N, int C) { return multilabel_workspace_bytes(N, C); }
+
+int vpa_multilabel_scores(const float* S, int64_t ld_s, const void* Y, int y_dtype, int64_t ld_y, int64_t N, int C,
+                          int truncate_pr, double* per_class, int32_t* flags, int32_t* support, double* micro_ap,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  return multilabel_scores_launch(S, ld_s, Y, y_dtype, ld_y, N, C, truncate_pr, per_class, flags, support, micro_ap, workspace,
+                                  workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 // ---- row-sharded step orchestrated in the library (two calls per training step) ------------------------------------

@@ -399,6 +399,7 @@ def _share_fd_from_rank0(rank, world, fd, name, group):
         srv.listen(world)
     dist.barrier(group=group)                      # the socket exists
     if rank == 0:
+        srv.settimeout(30.0)
         for _ in range(world - 1):
             conn, _ = srv.accept()
             if fd is not None:
@@ -409,11 +410,14 @@ def _share_fd_from_rank0(rank, world, fd, name, group):
         srv.close()
         return fd
     cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    for _ in range(200):
+    cli.settimeout(30.0)
+    for attempt in range(200):
         try:
             cli.connect(name)
             break
         except OSError:
+            if attempt == 199:
+                raise
             time.sleep(0.05)
     _, fds, _, _ = socket.recv_fds(cli, 16, 1)
     cli.close()
@@ -427,8 +431,9 @@ def _nvls_setup(lib, handle, rank, world, pid0, group):
         return (lib.vpa_last_error_string() or b"").decode()
     fd = ctypes.c_int(-1)
     rc = lib.vpa_p2p_nvls_export(handle, ctypes.byref(fd)) if rank == 0 else 0
+    # (the socket name must be the same string in every process: rank 0's pid + the number of segments set up so far)
     got = _share_fd_from_rank0(rank, world, fd.value if (rank == 0 and rc == 0) else None,
-                               f"\0vipant-b200-nvls-{pid0}-{id(group) & 0xffff}", group)
+                               f"\0vipant-b200-nvls-{pid0}-{len(_P2P)}", group)
     if rank == 0:
         if rc == 0:
             os.close(fd.value)
@@ -565,13 +570,89 @@ def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, 
     return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group, logit_scale_grad == "sum", segment_key)
 
 
+def _gt_matrix(gt, rows, upper, dev, what):
+    """(rows,) or (rows, g <= 8) integer ground-truth indices -> int32 (rows, g), validated on the host side of the call:
+    an index outside [0, upper) would make the kernel compare against another row's memory."""
+    if gt is None:
+        return None, 0
+    gt2 = gt[:, None] if gt.dim() == 1 else gt           # rows may be 0
+    if gt2.dim() != 2 or gt2.shape[0] != rows:
+        raise ValueError(f"{what} must have shape (N,) or (N, g) with N={rows}, got {tuple(gt.shape)}")
+    if gt2.shape[1] > 8:
+        raise ValueError(f"{what}: at most 8 ground-truth indices per row, got {gt2.shape[1]}")
+    g32 = gt2.to(device=dev, dtype=torch.int32).contiguous()
+    return g32, g32.shape[1]
+
+
+def check_gt_range(gt: torch.Tensor, upper: int, what: str = "gt") -> None:
+    """Raise if an index lies outside [0, upper).  One device->host sync: call it once per evaluation, not per batch."""
+    if gt is not None and gt.numel() and (int(gt.min()) < 0 or int(gt.max()) >= upper):
+        raise ValueError(f"{what}: indices must lie in [0, {upper})")
+
+
+def sim_rank_fused(q: torch.Tensor, k: torch.Tensor, gt_q: Optional[torch.Tensor] = None,
+                   gt_k: Optional[torch.Tensor] = None, top1_q: bool = False, top1_k: bool = False):
+    """Both directions of the monitors' scoring from ONE pass over the similarity ``q @ k.T`` (never written to memory).
+
+    q (N, D), k (M, D): CUDA, converted to fp32.  gt_q: (N,) / (N, g<=8) key indices whose rank within each query's row
+    is wanted; gt_k: (M,) / (M, g<=8) query indices whose rank within each key's row of ``k @ q.T`` is wanted.
+    Returns a dict: ranks_q (N, g) int64, ranks_k (M, g) int64, top1_q / top1_k (idx int64, val fp32) -- entries only for
+    what was asked.  rank = 0-based position in a stable descending sort; NaN similarities sort first (as torch.argsort
+    does); out-of-range ground-truth indices give rank 0 -- validate with check_gt_range when they come from outside.
+    """
+    _require_cuda(q, k, gt_q, gt_k)
+    q = _rows2d(q.float())
+    k = _rows2d(k.float())
+    N, D = q.shape
+    M = k.shape[0]
+    if k.shape[1] != D:
+        raise ValueError(f"feature dims differ: {D} vs {k.shape[1]}")
+    dev = q.device
+    gq, ng_q = _gt_matrix(gt_q, N, M, dev, "gt_q")
+    gk, ng_k = _gt_matrix(gt_k, M, N, dev, "gt_k")
+    out = {}
+    rq = torch.zeros((N, ng_q), dtype=torch.int32, device=dev) if ng_q else None
+    rk = torch.zeros((M, ng_k), dtype=torch.int32, device=dev) if ng_k else None
+    iq = torch.full((N,), -1, dtype=torch.int64, device=dev) if top1_q else None
+    vq = torch.empty((N,), dtype=torch.float32, device=dev) if top1_q else None
+    ik = torch.full((M,), -1, dtype=torch.int64, device=dev) if top1_k else None
+    vk = torch.empty((M,), dtype=torch.float32, device=dev) if top1_k else None
+    if N and M:
+        lib = _cabi.lib()
+        with torch.cuda.device(dev):
+            ws_bytes = lib.vpa_sim_fused_workspace_bytes(N, M, ng_q, ng_k)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.vpa_sim_rank_fused(_ptr(q), _ptr(k), N, M, D, q.stride(0), k.stride(0), _ptr(gq), ng_q, _ptr(gk),
+                                               ng_k, _ptr(rq), _ptr(rk), _ptr(iq), _ptr(vq), _ptr(ik), _ptr(vk), _ptr(ws),
+                                               ws_bytes, _stream()), "vpa_sim_rank_fused")
+    if rq is not None:
+        out["ranks_q"] = rq.long()
+    if rk is not None:
+        out["ranks_k"] = rk.long()
+    if top1_q:
+        out["top1_q"] = (iq, vq)
+    if top1_k:
+        out["top1_k"] = (ik, vk)
+    return out
+
+
 def sim_rank_topk(q: torch.Tensor, k: torch.Tensor, gt: Optional[torch.Tensor] = None, topk: int = 0):
     """Similarity ``q @ k.T`` (fp32) reduced on the fly to ranks of ground-truth columns and the top-k keys.
 
     q (N, D), k (M, D): CUDA, converted to fp32.  gt: (N,) or (N, g<=8) integer column indices.
     Returns (ranks int64 (N, g) or None, topk_idx int64 (N, topk) or None, topk_val fp32 or None);
     rank = 0-based position of the column in a stable descending sort of the row.
+    topk <= 1 runs the fused kernel (the similarity is consumed in registers); topk > 1 materialises S in a workspace.
+    NaN similarities: the fused path sorts them first (like torch.argsort(descending=True)), the topk > 1 path last.
     """
+    if topk <= 1:
+        if q.dim() == 2 and k.dim() == 2 and topk > k.shape[0]:
+            raise ValueError("topk exceeds the number of keys")
+        res = sim_rank_fused(q, k, gt_q=gt, top1_q=topk == 1)
+        idx = val = None
+        if topk == 1:
+            idx, val = res["top1_q"][0][:, None], res["top1_q"][1][:, None]
+        return res.get("ranks_q"), idx, val
     _require_cuda(q, k, gt)
     q = _rows2d(q.float())
     k = _rows2d(k.float())
@@ -580,14 +661,9 @@ def sim_rank_topk(q: torch.Tensor, k: torch.Tensor, gt: Optional[torch.Tensor] =
     if k.shape[1] != D:
         raise ValueError(f"feature dims differ: {D} vs {k.shape[1]}")
     dev = q.device
-    g = 0
-    gt32 = None
-    if gt is not None:
-        gt2 = gt[:, None] if gt.dim() == 1 else gt           # (N,) or (N, g); N may be 0
-        if gt2.dim() != 2 or gt2.shape[0] != N:
-            raise ValueError(f"gt must have shape (N,) or (N, g) with N={N}, got {tuple(gt.shape)}")
-        gt32 = gt2.to(device=dev, dtype=torch.int32).contiguous()
-        g = gt32.shape[1]
+    gt32, g = _gt_matrix(gt, N, M, dev, "gt")
+    if gt32 is not None:
+        check_gt_range(gt32, M)          # this kernel reads S[gt] unchecked
     ranks = torch.empty((N, g), dtype=torch.int32, device=dev) if g else None
     idx = torch.empty((N, topk), dtype=torch.int64, device=dev) if topk else None
     val = torch.empty((N, topk), dtype=torch.float32, device=dev) if topk else None

@@ -68,6 +68,15 @@ def _is_primary():
     return not dist.is_initialized() or dist.get_rank() == 0
 
 
+def _compact(x):
+    """The batch as the stash keeps it: the tensor itself when it owns its storage (an encoder output), a copy when it is a
+    view into something larger (`hidden[:, 0, :]` would keep the whole hidden state alive for the rest of the evaluation)."""
+    x = x.detach()
+    if x.is_contiguous() and x.untyped_storage().nbytes() <= 2 * x.numel() * x.element_size() + 512:
+        return x
+    return x.clone(memory_format=torch.contiguous_format)
+
+
 def _cfg_get(cfg, key, default=None):
     try:
         v = getattr(cfg, key)
@@ -89,22 +98,36 @@ class LossHead(nn.Module):
 
     # -- accumulate ------------------------------------------------------------------------------
     def infer(self, x1, x2, *args, **kwargs):
+        """Stash the batch (reference :34-46).  The L2 normalisation of :38-40 is applied when the stash is read (`_stash`):
+        one fused kernel launch over the concatenated features instead of two launches per batch."""
         if not (hasattr(self, "x1s") and hasattr(self, "x2s") and hasattr(self, "ids")):
             self.x1s, self.x2s, self.ids = [], [], []
-        already = bool(kwargs.get("normalized", False))
-        self.x1s.append(F_.l2_normalize(x1, already_normalized=already))     # fused normalise kernel
-        self.x2s.append(F_.l2_normalize(x2, already_normalized=already))
+            self._stash_normalized = []
+        F_._require_cuda(x1, x2)
+        self.x1s.append(_compact(x1))
+        self.x2s.append(_compact(x2))
+        self._stash_normalized.append(bool(kwargs.get("normalized", False)))
         names = kwargs.get("names", None)
         if names is not None:
             self.ids.extend(names)
         return None
+
+    def _stash(self):
+        """(x1s, x2s): the stashed features as two fp32 matrices of unit-norm rows."""
+        flags = getattr(self, "_stash_normalized", [True] * len(self.x1s))
+        if len(set(flags)) <= 1:
+            already = bool(flags[0]) if flags else True
+            return (F_.l2_normalize(torch.cat(self.x1s), already_normalized=already),
+                    F_.l2_normalize(torch.cat(self.x2s), already_normalized=already))
+        return (torch.cat([F_.l2_normalize(x, already_normalized=f) for x, f in zip(self.x1s, flags)]),
+                torch.cat([F_.l2_normalize(x, already_normalized=f) for x, f in zip(self.x2s, flags)]))
 
     # -- metrics ---------------------------------------------------------------------------------
     @staticmethod
     def retrieval_metrics(ranks, nsample=None, msg=""):
         """R@1/5/10/50, median and mean rank (+1) of a float32 rank vector (reference :67-77)."""
         nsample = nsample or ranks.shape[0]
-        hits = {k: int((ranks < k).sum().item()) / nsample * 100. for k in (1, 5, 10, 50)}
+        hits = {k: int((ranks < k).sum()) / nsample * 100. for k in (1, 5, 10, 50)}
         med = ranks.median() + 1
         avg = ranks.mean() + 1
         return (f"{msg}: R@1 {hits[1]:2.2f} R5 {hits[5]:2.2f} R10 {hits[10]:2.2f} R50 {hits[50]:2.2f} "
@@ -123,9 +146,8 @@ class LossHead(nn.Module):
         n = x1s.shape[0]
         gt12 = torch.arange(n * k, device=x1s.device).view(n, k)
         gt21 = torch.arange(n * k, device=x1s.device) // k
-        r12, _, _ = F_.sim_rank_topk(x1s, x2s, gt12)
-        r21, _, _ = F_.sim_rank_topk(x2s, x1s, gt21)
-        return LossHead._retrieval_eval_from_ranks(r12, r21[:, 0])
+        res = F_.sim_rank_fused(x1s, x2s, gt_q=gt12, gt_k=gt21)          # both directions, one pass over the similarity
+        return LossHead._retrieval_eval_from_ranks(res["ranks_q"].cpu(), res["ranks_k"][:, 0].cpu())
 
     def _gold_cluster(self, gold_file, nsample, verbose=False):
         by_class, by_sample = defaultdict(list), defaultdict(str)
@@ -147,7 +169,7 @@ class LossHead(nn.Module):
         """Per-class P@1 / R@1 / mAP / mAR from each row's nearest neighbour (reference :182-238, k = 1)."""
         k = 1
         per_class = defaultdict(dict)
-        for idx, nb in enumerate(top1.tolist()):
+        for idx, nb in enumerate(top1.flatten().tolist()):
             sample = self.ids[idx]
             cname = by_sample[sample]
             hit = 1 if self.ids[nb] in by_class[cname] else 0
@@ -169,47 +191,48 @@ class LossHead(nn.Module):
         return f"{msg}: P@{k} {p:2.2f} R@{k} {r:2.2f} mAP {p_cls:2.2f} mAR {r_cls:2.2f}"
 
     def report(self, gold_file=None):
-        x1s = torch.cat(self.x1s)
-        x2s = torch.cat(self.x2s)
+        """Reference :109-244.  ONE fused kernel pass over the similarity yields the ranks (and nearest neighbours) of both
+        directions; they come to the host in one copy each and the reference's own expressions run on them there."""
+        x1s, x2s = self._stash()
         n1, n2 = x1s.shape[0], x2s.shape[0]
         dev = x1s.device
         msg_12 = msg_21 = ""
         ref_metric = ""
         if n1 == n2:
             gt = torch.arange(n1, device=dev)
-            want_top = 1 if gold_file is not None else 0
-            r12, top12, _ = F_.sim_rank_topk(x1s, x2s, gt, topk=want_top)
-            r21, top21, _ = F_.sim_rank_topk(x2s, x1s, gt, topk=want_top)
-            r12, r21 = r12[:, 0], r21[:, 0]
-            t12_1 = int((r12 < 1).sum().item()) / n1 * 100.
-            t12_5 = int((r12 < 5).sum().item()) / n1 * 100.
-            t21_1 = int((r21 < 1).sum().item()) / n1 * 100.
-            t21_5 = int((r21 < 5).sum().item()) / n1 * 100.
+            want_top = gold_file is not None
+            res = F_.sim_rank_fused(x1s, x2s, gt_q=gt, gt_k=gt, top1_q=want_top, top1_k=want_top)
+            r12, r21 = res["ranks_q"][:, 0].cpu(), res["ranks_k"][:, 0].cpu()
+            t12_1 = int((r12 < 1).sum()) / n1 * 100.
+            t12_5 = int((r12 < 5).sum()) / n1 * 100.
+            t21_1 = int((r21 < 1).sum()) / n1 * 100.
+            t21_5 = int((r21 < 5).sum()) / n1 * 100.
             p_12 = f"I->A: t1 = {t12_1:2.2f} t5 = {t12_5:2.2f}"
             p_21 = f"A->I: t1 = {t21_1:2.2f} t5 = {t21_5:2.2f}"
             if gold_file is not None:
                 by_class, by_sample = self._gold_cluster(gold_file, n1)
-                msg_12 = self._class_stats(top12[:, 0], by_class, by_sample, n1, "I->A")
-                msg_21 = self._class_stats(top21[:, 0], by_class, by_sample, n1, "A->I")
+                msg_12 = self._class_stats(res["top1_q"][0].cpu(), by_class, by_sample, n1, "I->A")
+                msg_21 = self._class_stats(res["top1_k"][0].cpu(), by_class, by_sample, n1, "A->I")
         elif n1 * 5 == n2:
             # 1 clip vs 5 captions: caption c belongs to clip c // 5 (collator order)
             gt12 = torch.arange(n2, device=dev).view(n1, 5)
             gt21 = torch.arange(n2, device=dev) // 5
-            r12, _, _ = F_.sim_rank_topk(x1s, x2s, gt12)               # (n1, 5)
-            r21, _, _ = F_.sim_rank_topk(x2s, x1s, gt21)
-            r21 = r21[:, 0]
+            res = F_.sim_rank_fused(x1s, x2s, gt_q=gt12, gt_k=gt21)
+            r12, r21 = res["ranks_q"].cpu(), res["ranks_k"][:, 0].cpu()        # (n1, 5), (n2,)
             t12_1 = (r12 < 1).sum(-1).sum() / (1 * r12.shape[0]) * 100.    # P@1   (0-d tensors, as in :143-146)
             t12_5 = (r12 < 5).sum(-1).sum() / (5 * r12.shape[0]) * 100.    # R@5
             mean12 = r12.min(-1)[0].float().mean() + 1
             p_12 = f"A->T: t1 = {t12_1:2.2f} t5 = {t12_5:2.2f} mR = {mean12:2.2f}"
-            t21_1 = int((r21 < 1).sum().item()) / r21.shape[0] * 100.
-            t21_5 = int((r21 < 5).sum().item()) / r21.shape[0] * 100.
+            t21_1 = int((r21 < 1).sum()) / r21.shape[0] * 100.
+            t21_5 = int((r21 < 5).sum()) / r21.shape[0] * 100.
             mean21 = r21.float().mean() + 1
             p_21 = f"T->A: t1 = {t21_1:2.2f} t5 = {t21_5:2.2f} mR = {mean21:2.2f}"
             ref_metric = self._retrieval_eval_from_ranks(r12, r21)      # no second similarity pass
         else:
             p_12, p_21 = f"{x1s.shape}x{x2s.shape}", "-"
         del self.x1s, self.x2s, self.ids
+        if hasattr(self, "_stash_normalized"):
+            del self._stash_normalized
         msg = "" if msg_12 == msg_21 == "" else f"\n{msg_12} {msg_21}\n"
         ref = "" if ref_metric == "" else f"\nREFERENCE\n{ref_metric}"
         return f"{msg}{p_12} {p_21} @ {n1}{ref}"

@@ -243,12 +243,14 @@ int vpa_infonce_bwd_sharded(void* comm, const void* x1, const void* x2, int in_d
 
 /* ------------------------------------------------------------------------------------------
  * The same row-sharded step over NVLink PEER MEMORY instead of NCCL.  The all-gather of the normalised operands is FUSED INTO
- * the forward kernel: the first CTAs of its grid are relays that pull the peers' rows with TMA bulk copies through a shared-
- * memory ring (x2 operands first, 256-row chunks) and raise one arrival flag per chunk; the sweep CTAs of the same grid start
- * on the local block and consume the peers' tiles as their flags flip.  The statistics exchange is one kernel (message into
- * every peer, wait for R messages, merge, loss) and the d logit_scale exchange rides in the backward's finalize kernel: six
- * launches per step, no collective library call on the data path; results are bitwise identical on every rank and to the
- * NCCL transport.
+ * the sweep kernels: the first CTAs of a grid are relays that pull the peers' rows with TMA bulk copies through a shared-
+ * memory ring (256-row chunks) and raise one arrival flag per chunk; the sweep CTAs of the same grid start on the local block
+ * and consume the peers' tiles as their flags flip.  The forward kernel gathers the x2 operands (all it reads), the backward
+ * kernel the x1 operands (which only its second problem reads) while its first problem already runs.  The statistics exchange
+ * is one kernel (message into every peer, wait for R messages, merge, loss) and the d logit_scale exchange rides in the
+ * backward's finalize kernel: six launches per step, no collective library call on the data path.  Loss and d logit_scale are
+ * bitwise identical on every rank and to the NCCL transport; the feature gradients agree with it to fp32 rounding (the
+ * backward visits its tiles in another order).
  *
  * Setup (once per (rows_local, world, D, precision) and call site): every rank calls vpa_p2p_create -- the library
  * cudaMalloc's its symmetric segment (gathered operands x 2 steps, messages, flags, workspace) and returns a 64-byte CUDA IPC
@@ -273,10 +275,11 @@ int vpa_p2p_destroy(void* p2p);
  * vpa_p2p_nvls_attach (fd < 0 on rank 0); after a host barrier every rank calls vpa_p2p_nvls_bind, then
  * vpa_p2p_connect(p2p, NULL-able). */
 int vpa_p2p_mode(void* p2p);
-/* Diagnostics / tests (host only): the relay CTAs' work-item map.  out5 = matrix (0: x2 operands, 1: x1), source rank, chunk
- * index, first row within the source's block, row count.  Items 0 .. 2 * chunks_per_rank * (world-1) - 1; relay CTA k of n
- * takes items k, k + n, ... */
-int vpa_debug_relay_item(int item, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5);
+/* Diagnostics / tests (host only): the relay CTAs' work-item map for matrices [m0, 2).  out5 = matrix (0: x2 operands, 1: x1),
+ * source rank, chunk index, first row within the source's block, row count.  Items 0 .. (2 - m0) * chunks_per_rank *
+ * (world-1) - 1; relay CTA k of n takes items k, k + n, ...  source_major: 0 = chunk k of every peer before chunk k+1 (the
+ * forward's order), 1 = peer after peer starting at me+1 (the backward's order). */
+int vpa_debug_relay_item(int item, int m0, int source_major, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5);
 int vpa_p2p_nvls_export(void* p2p, int* fd_out);
 int vpa_p2p_nvls_attach(void* p2p, int fd);
 int vpa_p2p_nvls_bind(void* p2p);

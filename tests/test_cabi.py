@@ -153,28 +153,31 @@ def test_transport_selection(monkeypatch):
     assert F_._transport(object()) == "host"
 
 
+@pytest.mark.parametrize("source_major", [0, 1])
 @pytest.mark.parametrize("world,b", [(8, 4096), (4, 8192), (2, 16384), (3, 384), (2, 300), (4, 512), (2, 64), (5, 1000)])
-def test_relay_items_cover_every_peer_row_once(lib, world, b):
+def test_relay_items_cover_every_peer_row_once(lib, world, b, source_major):
     """The relay CTAs' item map (the compiled relay_item_decode, evaluated on the host): every row of every peer block is
-    pulled exactly once per matrix, one item per 256-row chunk (what its arrival flag stands for), the x2 operands come
-    first and chunk k of all peers comes before chunk k+1 of any; out-of-range items are rejected."""
+    pulled exactly once per matrix, one item per 256-row chunk (what its arrival flag stands for).  Chunk-major (forward):
+    the x2 operands come first and chunk k of all peers before chunk k+1 of any.  Source-major (backward, x1 operands only):
+    peer me+1 completely, then me+2, ...  Out-of-range items are rejected."""
     cpr = -(-b // 256)
     out = (ctypes.c_int * 5)()
     for me in (0, world - 1):
-        total = 2 * cpr * (world - 1)
-        seen = np.zeros((2, world, b), dtype=np.int32)
-        chunks = set()
-        order = []
-        for item in range(total):
-            assert lib.vpa_debug_relay_item(item, world, me, cpr, b, out) == 0
-            m, src, c, row0, rows = list(out)
-            assert 0 <= m < 2 and 0 <= src < world and src != me and 0 <= c < cpr and rows >= 1
-            assert row0 == c * 256 and row0 + rows == min(b, (c + 1) * 256)
-            seen[m, src, row0:row0 + rows] += 1
-            chunks.add((m, src, c))
-            order.append((m, c))
-        peers = [q for q in range(world) if q != me]
-        assert np.all(seen[:, peers, :] == 1) and np.all(seen[:, me, :] == 0)
-        assert len(chunks) == total
-        assert order == sorted(order)                       # matrix-major, then chunk-major
-        assert lib.vpa_debug_relay_item(total, world, me, cpr, b, out) == -1
+        for m0 in (0, 1):
+            total = (2 - m0) * cpr * (world - 1)
+            seen = np.zeros((2, world, b), dtype=np.int32)
+            chunks = set()
+            order = []
+            for item in range(total):
+                assert lib.vpa_debug_relay_item(item, m0, source_major, world, me, cpr, b, out) == 0
+                m, src, c, row0, rows = list(out)
+                assert m0 <= m < 2 and 0 <= src < world and src != me and 0 <= c < cpr and rows >= 1
+                assert row0 == c * 256 and row0 + rows == min(b, (c + 1) * 256)
+                seen[m, src, row0:row0 + rows] += 1
+                chunks.add((m, src, c))
+                order.append((m, (src - me) % world, c) if source_major else (m, c))
+            peers = [q for q in range(world) if q != me]
+            assert np.all(seen[m0:, peers, :] == 1) and np.all(seen[:, me, :] == 0) and np.all(seen[:m0] == 0)
+            assert len(chunks) == total
+            assert order == sorted(order)             # matrix-major, then chunk-major / peer-major starting at me+1
+            assert lib.vpa_debug_relay_item(total, m0, source_major, world, me, cpr, b, out) == -1

@@ -51,7 +51,7 @@ _SIGNATURES = {
     "vpa_p2p_connect": (c_int, [c_void_p, c_void_p]),
     "vpa_p2p_destroy": (c_int, [c_void_p]),
     "vpa_p2p_mode": (c_int, [c_void_p]),
-    "vpa_debug_relay_item": (c_int, [c_int, c_int, c_int, c_int, c_int64, POINTER(c_int)]),
+    "vpa_debug_relay_item": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, POINTER(c_int)]),
     "vpa_p2p_nvls_export": (c_int, [c_void_p, POINTER(c_int)]),
     "vpa_p2p_nvls_attach": (c_int, [c_void_p, c_int]),
     "vpa_p2p_nvls_bind": (c_int, [c_void_p]),

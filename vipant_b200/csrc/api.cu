@@ -144,8 +144,10 @@ static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int
 // SM pairs is minimal.  The grid lists all big units first, then the tails, and the hardware hands the next unit to the
 // first free slot: simulated here exactly (in-order list scheduling).  `fixed` = per-unit cost in tile equivalents.
 // Equal chunking alone wastes up to a whole wave when units do not divide the slots (64 backward units on 74 slots).
-static void pick_split(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int* small_tiles) {
-  const int slots = sm_count() / 2;
+static void pick_split(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int* small_tiles,
+                       int reserved_sms = 0) {
+  int slots = (sm_count() - reserved_sms) / 2;
+  if (slots < 1) slots = 1;
   long best = -1;
   int best_k = 1, best_small = 0;
   const int kmax = n_tiles < 16 ? n_tiles : 16;
@@ -178,23 +180,23 @@ static void pick_split(int base_units, int n_tiles, int fixed, int* chunks, int*
   *small_tiles = best_small;
 }
 
-static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, int D, int precision);
+static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, int D, int precision, int reserved_sms);
 
 // The split search costs milliseconds: plans are computed once per shape.
-SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision) {
+SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision, int reserved_sms) {
   static std::mutex mu;
-  static std::map<std::tuple<int64_t, int64_t, int, int, int>, SweepPlan> cache;
-  const auto key = std::make_tuple(rows_local, rows_global, D, precision, sm_count());
+  static std::map<std::tuple<int64_t, int64_t, int, int, int, int>, SweepPlan> cache;
+  const auto key = std::make_tuple(rows_local, rows_global, D, precision, sm_count(), reserved_sms);
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
-  const SweepPlan p = plan_sweep_uncached(rows_local, rows_global, D, precision);
+  const SweepPlan p = plan_sweep_uncached(rows_local, rows_global, D, precision, reserved_sms);
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, p);
   return p;
 }
 
-static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, int D, int precision) {
+static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, int D, int precision, int reserved_sms) {
   SweepPlan p{};
   if (precision == VPA_PREC_FP32_SIMT) {
     p.rows_per_blk = 8;
@@ -217,15 +219,15 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
     p.n_tiles = (int)((rows_global + 255) / 256);
     pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
     // per-unit fixed cost (prologue, X load, pipeline fill, dX drain) measured at ~3.5 tiles of 256 columns (b=4096 sweep)
-    pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small);
+    pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small, reserved_sms);
     p.fast_fwd = 1;
     // A row-sharded forward consumes operand rows while they arrive from the peers: it is gated by the transfer, not by
     // the tensor cores, and a second wave of tail units (which the LPT split adds) only starts when the first wave ends --
     // measured at N = 8: forward sweep 0.178 ms with equal chunks in one wave, 0.193 ms with the split.  Equal chunks there,
-    // planned on the SM pairs the relay CTAs leave free.
+    // planned on the SM pairs the relay CTAs of the peer-memory transport leave free (reserved_sms).
     const bool sharded = rows_local < rows_global;
     if (!sharded) pick_split(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, &p.fwd1_small);
-    else pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2, relay_ctas_default());
+    else pick_chunks(p.pair_fwd_iblk, p.n_tiles, 2, &p.fwd1_chunks, &p.fwd1_tiles_per_chunk, 2, reserved_sms);
     p.n_rowgroups = p.pair_fwd_iblk * 8;
     auto force = [&](const char* name, int* chunks, int* tpc, int* small) {     // tuning knobs for measurements
       if (const char* e = getenv(name)) {
@@ -287,6 +289,12 @@ static int check_infonce_shape(int64_t rows_local, int64_t rows_global, int D, i
   return 0;
 }
 
+size_t infonce_workspace_bytes(int64_t rows_local, int64_t rows_global, int D, int precision, int reserved_sms) {
+  if (rows_local <= 0 || rows_global < rows_local || D <= 0) return 0;
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision, reserved_sms);
+  return carve_workspace(nullptr, rows_local, rows_global, D, plan).bytes;
+}
+
 }  // namespace vpa
 
 using namespace vpa;
@@ -345,9 +353,7 @@ int vpa_normalize_pair(const void* x1, const void* x2, int in_dtype, int64_t row
 }
 
 size_t vpa_infonce_workspace_bytes(int64_t rows_local, int64_t rows_global, int D, int precision) {
-  if (rows_local <= 0 || rows_global < rows_local || D <= 0) return 0;
-  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
-  return carve_workspace(nullptr, rows_local, rows_global, D, plan).bytes;
+  return vpa::infonce_workspace_bytes(rows_local, rows_global, D, precision, 0);
 }
 
 size_t vpa_infonce_colsum_floats(int64_t rows_global) { return rows_global > 0 ? (size_t)kColSumSplit * (size_t)rows_global : 0; }
@@ -356,11 +362,11 @@ static int fwd_sweep_impl(const void* a_loc, const void* t_loc, const void* a_al
                           int64_t rows_local, int64_t rows_global, int D, int64_t row_offset, const float* logit_scale,
                           float scale_max, void* workspace, size_t workspace_bytes, float* col_sum, bool allow_fast,
                           int parts, cudaStream_t st, const P2PRowFlags* yflags = nullptr, bool reduce_cols = true,
-                          const RelayArgs* relay = nullptr) {
+                          const RelayArgs* relay = nullptr, int reserved_sms = 0) {
   // reduce_cols == false: the caller reduces the single-pass column partials itself (pack_stats); col_sum is not touched
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && logit_scale && workspace, "infonce_fwd_sweep: null pointer");
-  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision, reserved_sms);
   const Workspace ws = carve_workspace(workspace, rows_local, rows_global, D, plan);
   if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_fwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
   SweepArgs a{};
@@ -444,14 +450,15 @@ static int bwd_impl(const void* a_loc, const void* t_loc, const void* a_all, con
                     const float* row_lse_all, const float* col_lse_all, const float* grad_out, const void* x1,
                     const void* x2, int in_dtype, int64_t ld1, int64_t ld2, const float* inv_norm1,
                     const float* inv_norm2, int already_normalized, void* workspace, size_t workspace_bytes,
-                    void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, int dls_sum, void* stream) {
+                    void* dx1, void* dx2, float* dlogit_scale, const P2PStep* p2p, int dls_sum, void* stream,
+                    const RelayArgs* relay = nullptr, int reserved_sms = 0) {
   if (int e = check_infonce_shape(rows_local, rows_global, D, row_offset, precision)) return e;
   VPA_CHECK_ARG(a_loc && t_loc && a_all && t_all && scale && row_lse_all && col_lse_all && grad_out && dx1 && dx2 && workspace,
                 "infonce_bwd: null pointer");
   VPA_CHECK_ARG(already_normalized || (x1 && x2 && inv_norm1 && inv_norm2), "infonce_bwd: x / inv_norm required");
   VPA_CHECK_ARG(in_dtype == VPA_F32 || in_dtype == VPA_BF16 || in_dtype == VPA_F16, "infonce_bwd: bad dtype");
   VPA_CHECK_ARG(ld1 >= D && ld2 >= D && ld1 % 4 == 0 && ld2 % 4 == 0, "infonce_bwd: bad leading dimension");
-  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision);
+  const SweepPlan plan = plan_sweep(rows_local, rows_global, D, precision, reserved_sms);
   const Workspace ws = carve_workspace(workspace, rows_local, rows_global, D, plan);
   if (ws.bytes > workspace_bytes) return set_error(VPA_E_WORKSPACE, "infonce_bwd: workspace %zu < %zu", workspace_bytes, ws.bytes);
   SweepArgs a{};
@@ -460,6 +467,10 @@ static int bwd_impl(const void* a_loc, const void* t_loc, const void* a_all, con
   a.scale = scale;
   a.lse_x[0] = row_lse_all; a.lse_y[0] = col_lse_all;   // problem 0: rows of S
   a.lse_x[1] = col_lse_all; a.lse_y[1] = row_lse_all;   // problem 1: columns of S
+  if (relay) {                                          // peer-memory transport: the x1 operands arrive while the sweep runs
+    a.relay = relay;
+    a.aflags = p2p->aflags;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int e = (precision == VPA_PREC_BF16_TC) ? (plan.impl == 1 ? pair_infonce_bwd(a, ws, plan, st) : tc_infonce_bwd(a, ws, plan, st))
                                               : simt_infonce_bwd(a, ws, plan, st)) return e;
@@ -668,10 +679,10 @@ int vpa_p2p_connect(void* p2p, const void* all_ipc_handles) { return p2p_connect
 int vpa_p2p_destroy(void* p2p) { return p2p_destroy(p2p); }
 int vpa_p2p_mode(void* p2p) { return p2p_mode(p2p); }
 // the relay CTAs' item -> (matrix, source rank, chunk, first row, rows) map, evaluated on the host (tests)
-int vpa_debug_relay_item(int item, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5) {
+int vpa_debug_relay_item(int item, int m0, int source_major, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5) {
   VPA_CHECK_ARG(out5 && world >= 2 && me >= 0 && me < world && chunks_per_rank >= 1 && rows_local >= 1 && item >= 0 &&
-                item < 2 * chunks_per_rank * (world - 1), "debug_relay_item: bad argument");
-  const RelayItem it = relay_item_decode(item, world, me, chunks_per_rank, rows_local);
+                (m0 == 0 || m0 == 1) && item < (2 - m0) * chunks_per_rank * (world - 1), "debug_relay_item: bad argument");
+  const RelayItem it = relay_item_decode(item, m0, source_major, world, me, chunks_per_rank, rows_local);
   out5[0] = it.m; out5[1] = it.src; out5[2] = it.c; out5[3] = it.row0; out5[4] = it.rows;
   return 0;
 }
@@ -697,22 +708,32 @@ int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype,
   if (int e = normalize_pair_launch(x1, x2, in_dtype, b, D, ld1, ld2, already_normalized, tcp ? a_loc : nullptr,
                                     tcp ? t_loc : nullptr, tcp ? nullptr : (float*)a_loc, tcp ? nullptr : (float*)t_loc,
                                     h.inv1, h.inv2, h.dcos, tcp ? 1 : 0, st)) return e;
-  const SweepPlan plan = plan_sweep(b, B, D, precision);
+  const int reserved = p2p_relay_ctas(p2p);
+  const SweepPlan plan = plan_sweep(b, B, D, precision, reserved);
   const Workspace ws = carve_workspace(h.ws, b, B, D, plan);
   const bool from_colpart = pack_reduces_columns(plan, precision);
   const bool single_pass = tcp && plan.impl == 1 && plan.fast_fwd;
+  // The x1 operands of the previous step travel in its backward's grid.  If that backward has not been called (two forwards
+  // in a row), fetch them now: once this step's message is out, the peers may move on and reuse those buffers.
+  if (const uint32_t pend = p2p_a_pending(p2p)) {
+    if (int e = p2p_relay_standalone(p2p, pend, 1, false, st)) return e;
+    p2p_set_a_pending(p2p, 0);
+  }
   if (single_pass) {
-    // ONE kernel is the all-gather and the contraction: its first CTAs relay the peers' rows (x2 operands first, then the
-    // x1 operands the backward needs), its sweep CTAs start on the local block and consume remote tiles as their flags flip.
-    // When it has finished, every operand of the step has landed.
+    // ONE kernel is the all-gather and the contraction: its first CTAs relay the peers' x2 operand rows, its sweep CTAs
+    // start on the local block and consume remote tiles as their flags flip.  (Exact temperature regime, decided on the
+    // device: the relays fetch the x1 operands too, which the two-sweep kernel below reads.)
+    RelayArgs fr = h.relay;
+    fr.m0 = 0; fr.m1 = 1; fr.source_major = 0; fr.signal_ready = 1;
     if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                               h.colsum8, true, 1, st, &h.yflags, !from_colpart, &h.relay)) return e;
+                               h.colsum8, true, 1, st, &h.yflags, !from_colpart, &fr, reserved)) return e;
+    p2p_set_a_pending(p2p, epoch);
   } else {
-    if (int e = p2p_relay_standalone(p2p, epoch, st)) return e;
+    if (int e = p2p_relay_standalone(p2p, epoch, 0, true, st)) return e;
   }
   // the exact two-sweep kernel (other temperature regime / other shapes); device-gated when the single-pass kernel exists
   if (int e = fwd_sweep_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, logit_scale, scale_max, h.ws, h.ws_bytes,
-                             h.colsum8, true, single_pass ? 2 : 3, st, nullptr, !from_colpart)) return e;
+                             h.colsum8, true, single_pass ? 2 : 3, st, nullptr, !from_colpart, nullptr, reserved)) return e;
   const float cap = (scale_max > 0.f) ? scale_max : INFINITY;
   // message out, every rank's message in, statistics of all rows + the global loss
   return exchange_stats_launch(ws, plan, b, B, logit_scale, cap, h.dcos, single_pass ? 1 : 0, h.colsum8, from_colpart, h, loss_out, st);
@@ -731,10 +752,15 @@ int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x
   const size_t es = precision == VPA_PREC_BF16_TC ? 2 : 4;
   const char* a_loc = static_cast<const char*>(h.a_all) + (size_t)off * D * es;
   const char* t_loc = static_cast<const char*>(h.t_all) + (size_t)off * D * es;
-  // (the forward's kernels on this stream have gathered every operand; finalize_bwd exchanges the d logit_scale partials)
+  // The peers' x1 operands (read by the second problem only) arrive through relay CTAs in front of the backward's own grid
+  // while its first problem runs; finalize_bwd exchanges the d logit_scale partials.
+  RelayArgs br = h.relay;
+  br.m0 = 1; br.m1 = 2; br.source_major = 1; br.signal_ready = 0;
+  const bool fetch = p2p_a_pending(p2p) == epoch;
+  if (fetch) p2p_set_a_pending(p2p, 0);
   return bwd_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B, grad_out, x1, x2,
                   in_dtype, ld1, ld2, h.inv1, h.inv2, already_normalized, h.ws, h.ws_bytes, dx1, dx2, dlogit_scale, &h,
-                  dls_reduce ? 1 : 0, stream);
+                  dls_reduce ? 1 : 0, stream, fetch ? &br : nullptr, p2p_relay_ctas(p2p));
 }
 
 // ---- host-buffer end-to-end step ---------------------------------------------------------------------

@@ -152,7 +152,9 @@ struct SweepPlan {
   int n_rowgroups;          // single-pass forward: 32-row groups of column partial sums (8 per 256-row block)
 };
 constexpr int kColSumSplit = 8;   // column sums are reduced to [kColSumSplit][rows_global] (fixed order) before any all-reduce
-SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision);
+// reserved_sms: SMs the sweeps must leave to the relay CTAs of the peer-memory transport (0 on every other path)
+SweepPlan plan_sweep(int64_t rows_local, int64_t rows_global, int D, int precision, int reserved_sms = 0);
+size_t infonce_workspace_bytes(int64_t rows_local, int64_t rows_global, int D, int precision, int reserved_sms);
 int relay_ctas_default();      // relay CTAs of the peer-memory transport (api.cu)
 
 // Scratch layout shared by both precisions.
@@ -186,7 +188,8 @@ struct SweepArgs {
   const float* lse_x[2];       // backward: lse of the X rows' direction, GLOBAL vector (rows_global)
   const float* lse_y[2];       // backward: lse of the other direction, GLOBAL vector
   P2PRowFlags yflags;          // single-pass forward over peer memory: arrival flags of y[0]'s rows (zero: none)
-  const struct RelayArgs* relay;   // single-pass forward over peer memory: relay CTAs in front of the grid (p2p.cuh; nullptr: none)
+  P2PRowFlags aflags;          // backward over peer memory: arrival flags of y[1]'s rows, the peers' x1 operands (zero: none)
+  const struct RelayArgs* relay;   // single-pass forward / backward over peer memory: relay CTAs in front of the grid (p2p.cuh)
 };
 
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);

@@ -64,7 +64,10 @@ struct Params {
   int gate;                 // 0: always run; 1: run only if s*log2e <= kFastS2Limit; 2: run only if it is larger
   float* colpart;           // FWD1: float[n_iblk*8][n_y] column sums of exp2(S*s2 - s2) per 32-row group
   P2PRowFlags yflags;       // FWD1 over peer memory: arrival flags of the Y rows (nullptr: everything is already there)
-  RelayArgs relay;          // FWD1 over peer memory: the first relay.n_ctas CTAs of the grid are the operand all-gather (p2p.cuh)
+  P2PRowFlags aflags;       // BWD over peer memory: arrival flags of problem 1's Y rows (the x1 operands of the peers)
+  int rot;                  // BWD: every unit visits tile (t + rot) mod n_tiles -- the local rank block first, then the peers'
+                            // blocks in the order the relay CTAs fetch them
+  RelayArgs relay;          // FWD1 / BWD over peer memory: the first relay.n_ctas CTAs of the grid are the operand all-gather
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -233,13 +236,17 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
-  if (MODE == MODE_FWD1 && (int)blockIdx.x < P.relay.n_ctas) {
+  if ((MODE == MODE_FWD1 || MODE == MODE_BWD) && (int)blockIdx.x < P.relay.n_ctas) {
     // Relay CTAs: the all-gather of the operand rows over NVLink, in the same grid as the sweep that consumes them.  They
-    // come first in blockIdx order, i.e. they are resident before any sweep CTA that polls their flags, and they run in
-    // both temperature regimes (the exact forward and the backward read the gathered rows too).
+    // come first in blockIdx order, i.e. they are resident before any sweep CTA that polls their flags.  The forward
+    // fetches the x2 operands (all it reads); the x1 operands, which only the backward's second problem reads, travel in
+    // the backward's grid while its first problem already runs -- except in the exact temperature regime, whose two-sweep
+    // forward kernel reads them: then the forward's relays fetch them as well and the backward's find them in place.
     if (blockIdx.x == 0) relay_signal_ready(P.relay);
-    if (P.relay.multicast) relay_multicast(P.relay, blockIdx.x);
-    else relay_pull(P.relay, blockIdx.x, sptr);
+    int m1 = P.relay.m1;
+    if (MODE == MODE_FWD1 && fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e > kFastS2Limit) m1 = 2;
+    if (P.relay.multicast) relay_multicast(P.relay, m1, blockIdx.x);
+    else relay_pull(P.relay, m1, blockIdx.x, sptr);
     return;
   }
   if (P.gate != 0) {       // regime gate on the DEVICE value of the temperature (no host sync): uniform over the grid
@@ -250,7 +257,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
   const bool is_leader = crank == 0;
 
-  int u = ((int)blockIdx.x - (MODE == MODE_FWD1 ? P.relay.n_ctas : 0)) >> 1;      // pair index (after the relay CTAs)
+  int u = ((int)blockIdx.x - ((MODE == MODE_FWD1 || MODE == MODE_BWD) ? P.relay.n_ctas : 0)) >> 1;   // pair index (after the relay CTAs)
   int prob_, chunk_, iblk_, tile0_, nt_;
   {
     const int per = P.n_iblk * P.n_big, big_units = P.n_prob * per;
@@ -304,6 +311,11 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       if (b1 > b0) { o.cpr = cpr; o.blk0 = b0; o.blk1 = b1; }
     }
     return o;
+  };
+  // BWD: the j-th tile of this unit (rotated start, see Params::rot)
+  auto tile_at = [&](int j) {
+    const int t = tile0 + j + P.rot;
+    return t >= P.n_tiles ? t - P.n_tiles : t;
   };
   const uint32_t bar0 = sbase + L.bars;
   auto bar = [&](int i) { return bar0 + 8u * i; };
@@ -360,18 +372,19 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       for (int jh = 0; jh < 2; ++jh)
         for (int nb = 0; nb < P.nblk; ++nb) {
           const int d0 = nb * 256 + (int)crank * 128;
-          push(d0, d0 + 64, (tile0 + t) * kBN + jh * 128);
+          push(d0, d0 + 64, tile_at(t) * kBN + jh * 128);
         }
     };
     TileOrder order = make_order();
     int tcur = order.first();
     for (int j = 0; j < nt; ++j, tcur = (j < nt) ? order.next() : tcur) {
+      if (MODE == MODE_BWD) tcur = tile_at(j);
       const int r = tcur * kBN + (int)crank * 128;             // this CTA's half of the tile's Y rows
-      if (MODE == MODE_FWD1 && P.yflags.flags != nullptr) {
-        // peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cu).  Poll the
+      if ((MODE == MODE_FWD1 && P.yflags.flags != nullptr) || (MODE == MODE_BWD && prob == 1 && P.aflags.flags != nullptr)) {
+        // peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cuh).  Poll the
         // chunk flags (system-scope acquire), then order the TMA (async proxy) reads after the observation.
         if (elected) {
-          p2p_wait_rows(P.yflags, r, min(r + 128, pb.n_y));
+          p2p_wait_rows(MODE == MODE_BWD ? P.aflags : P.yflags, r, min(r + 128, pb.n_y));
           asm volatile("fence.proxy.async;" ::: "memory");
         }
         __syncwarp();
@@ -573,13 +586,13 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       float dsc = 0.f;
       const int etb = threadIdx.x - 64;               // 0..255
       auto load_cl = [&](int t) {                     // raw column lse of tile t for shared-memory slot etb; +inf masks columns past n_y
-        const int cj = (tile0 + t) * kBN + etb;
+        const int cj = tile_at(t) * kBN + etb;
         return (cj < pb.n_y) ? __ldg(pb.lse_y + cj) : INFINITY;
       };
       float cl_raw = load_cl(0);
       for (int j = 0; j < nt; ++j) {
         const int b = j & 1;
-        const int col0 = (tile0 + j) * kBN;
+        const int col0 = tile_at(j) * kBN;
         float* clb = cl_s + b * 256;                  // double-buffered: one barrier per tile
         clb[etb] = (cl_raw + lb) * kLog2e;            // base-2, + log2 B
         if (j + 1 < nt) cl_raw = load_cl(j + 1);      // prefetch (raw: nothing depends on it until the next tile)
@@ -755,7 +768,12 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.gate = gate;
   P.colpart = ws.colpart;
   if (fwd1) P.yflags = a.yflags;
-  if (fwd1 && a.relay) P.relay = *a.relay;
+  if (bwd) {
+    P.aflags = a.aflags;
+    // (any rotation covers every tile once; this one starts every unit on the local rank block)
+    if (a.relay || a.aflags.flags) P.rot = (int)((a.row_offset / kBN) % (P.n_tiles > 0 ? P.n_tiles : 1));
+  }
+  if ((fwd1 || bwd) && a.relay) P.relay = *a.relay;
   static_assert(kRelaySmemBytes + 1024 <= kSmemLimit, "the relay ring must fit into the forward kernel's shared memory");
   for (int p = 0; p < 2; ++p) {
     P.p[p].n_x = (int)a.rows_local;

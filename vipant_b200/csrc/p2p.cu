@@ -72,7 +72,7 @@ static SegLayout seg_layout(int64_t b, int world, int D, int precision) {
     L.dcos[p] = take(b * 4);
   }
   L.colsum8 = take((size_t)kColSumSplit * B * 4);
-  L.ws_bytes = vpa_infonce_workspace_bytes(b, B, D, precision);
+  L.ws_bytes = infonce_workspace_bytes(b, B, D, precision, relay_ctas_default());
   L.ws = take(L.ws_bytes);
   L.total = o;
   return L;
@@ -87,7 +87,8 @@ struct P2PHandle {
   SegLayout L{};
   uint32_t epoch = 0;
   int nvls = 0;             // 1: segment allocated with the VMM API and bound into an NVSwitch multicast object (see below)
-  int relay_ctas = 20;      // relay CTAs in front of the forward grid (whole CTA pairs; VPA_P2P_RELAY_CTAS)
+  int relay_ctas = 20;      // relay CTAs in front of the forward / backward grids (whole CTA pairs; VPA_P2P_RELAY_CTAS)
+  uint32_t a_pending = 0;   // step whose x1 operands are still to be gathered (by its backward, or by the next forward)
   CUmemGenericAllocationHandle vmm_mem = 0, vmm_mc = 0;
   CUdeviceptr uc_va = 0, mc_va = 0;
   size_t vmm_size = 0;
@@ -101,11 +102,11 @@ __global__ void __launch_bounds__(256) p2p_relay_kernel(const RelayArgs A) {
   extern __shared__ uint8_t relay_smem[];
   if (blockIdx.x == 0) relay_signal_ready(A);
   if (A.multicast) {
-    relay_multicast(A, blockIdx.x);
+    relay_multicast(A, A.m1, blockIdx.x);
     return;
   }
   const uint32_t base = relay_smem_u32(relay_smem);
-  relay_pull(A, blockIdx.x, relay_smem + (((base + 1023u) & ~1023u) - base));
+  relay_pull(A, A.m1, blockIdx.x, relay_smem + (((base + 1023u) & ~1023u) - base));
 }
 
 // ---------------------------------------------------------------- host side
@@ -392,6 +393,7 @@ static RelayArgs relay_args(const P2PHandle* h, uint32_t epoch) {
   A.cpr = L.cpr;
   A.n_ctas = h->relay_ctas;
   A.multicast = h->nvls;
+  A.m0 = 0; A.m1 = 2; A.source_major = 0; A.signal_ready = 1;      // (callers narrow this down)
   return A;
 }
 
@@ -426,17 +428,25 @@ P2PStep p2p_step(void* handle, uint32_t epoch) {
   s.yflags.chunks_per_rank = L.cpr;
   s.yflags.me = h->rank;
   s.yflags.epoch = epoch;
+  s.aflags = s.yflags;
+  s.aflags.flags = reinterpret_cast<const uint32_t*>(base + L.flags[1]);
   s.relay = relay_args(h, epoch);
   return s;
 }
 
 int p2p_relay_ctas(void* handle) { return static_cast<P2PHandle*>(handle)->relay_ctas; }
+// step whose x1 operands (read by the backward only) have not been gathered yet; 0: none
+uint32_t p2p_a_pending(void* handle) { return static_cast<P2PHandle*>(handle)->a_pending; }
+void p2p_set_a_pending(void* handle, uint32_t epoch) { static_cast<P2PHandle*>(handle)->a_pending = epoch; }
 
-// the operand all-gather as a kernel of its own on `st` (shapes without the fused forward): everything has landed when it ends
-int p2p_relay_standalone(void* handle, uint32_t epoch, cudaStream_t st) {
+// the operand all-gather as a kernel of its own on `st` (shapes without the fused kernels; the x1 operands of a step whose
+// backward has not been called when the next forward starts): matrices [m0, 2), everything has landed when it ends
+int p2p_relay_standalone(void* handle, uint32_t epoch, int m0, bool signal_ready, cudaStream_t st) {
   P2PHandle* h = static_cast<P2PHandle*>(handle);
   RelayArgs A = relay_args(h, epoch);
-  const int items = A.multicast ? 2 * A.cpr : 2 * A.cpr * (h->world - 1);
+  A.m0 = m0;
+  A.signal_ready = signal_ready ? 1 : 0;
+  const int items = (2 - m0) * (A.multicast ? A.cpr : A.cpr * (h->world - 1));
   A.n_ctas = items < 32 ? items : 32;
   static SmemAttrCache attr_cache;
   if (int e = ensure_dynamic_smem(attr_cache, p2p_relay_kernel, (int)kRelaySmemBytes + 1024)) return e;

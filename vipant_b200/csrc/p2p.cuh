@@ -111,21 +111,33 @@ struct RelayArgs {
   int row_bytes, cpr;                              // bytes per operand row; 256-row chunks per rank block
   int n_ctas;                                      // relay CTAs (0: no relay)
   int multicast;                                   // 1: NVLS stores of the own block instead of pulls
+  int m0, m1;                                      // matrices [m0, m1) to move
+  int source_major;                                // item order: 0 chunk-major over the peers, 1 peer after peer (me+1, me+2, ...)
+  int signal_ready;                                // 1: this launch announces "my rows of this step are complete" to the peers
 };
 constexpr int kRelaySlots = 6;
 constexpr int kRelayPieceBytes = 32768;
 constexpr uint32_t kRelaySmemBytes = kRelaySlots * kRelayPieceBytes + 64;      // ring + mbarriers (1024-byte aligned base)
 
 struct RelayItem { int m, src, c, row0, rows; };
-// item -> (matrix, source rank, chunk): shared by the device code and, host side, vpa_debug_relay_item (CPU test)
-__host__ __device__ inline RelayItem relay_item_decode(int item, int world, int me, int cpr, int64_t b) {
+// item -> (matrix, source rank, chunk): shared by the device code and, host side, vpa_debug_relay_item (CPU test).
+// chunk-major: chunk k of every peer before chunk k+1 of any (the forward sweep visits its tiles in that order);
+// source-major: all chunks of peer me+1, then me+2, ... (the backward sweep starts on the local block and walks the rank
+// blocks in that order).  Either way the ranks start on different peers: nobody's egress is a hot spot.
+__host__ __device__ inline RelayItem relay_item_decode(int item, int m0, int source_major, int world, int me, int cpr, int64_t b) {
   const int per_m = cpr * (world - 1);
   RelayItem it;
-  it.m = item / per_m;
-  const int r = item - it.m * per_m;
-  it.c = r / (world - 1);
-  const int q = r - it.c * (world - 1) + 1;
-  it.src = (me + q) % world;                       // rotate: the ranks do not all read the same peer at the same time
+  it.m = m0 + item / per_m;
+  const int r = item % per_m;
+  int q;
+  if (source_major) {
+    q = r / cpr + 1;
+    it.c = r - (q - 1) * cpr;
+  } else {
+    it.c = r / (world - 1);
+    q = r - it.c * (world - 1) + 1;
+  }
+  it.src = (me + q) % world;
   const int64_t row0 = (int64_t)it.c * kPushRows;
   const int64_t left = b - row0;
   it.row0 = (int)row0;
@@ -153,16 +165,18 @@ static __device__ __noinline__ void relay_timeout(int what, int a, int b) {
 // the rows finished before this kernel started: stream order)
 __device__ __forceinline__ void relay_signal_ready(const RelayArgs& A) {
   const int q = threadIdx.x;
-  if (q < A.v.world && q != A.v.rank) {
+  if (A.signal_ready && q < A.v.world && q != A.v.rank) {
     __threadfence_system();
     if (A.multicast) return;                       // multicast mode: nobody pulls
     st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[q] + A.off_ready) + A.v.rank, A.v.epoch);
   }
 }
 
-// Pull role of relay CTA `cta` of `A.n_ctas`.  `ring` = 1024-byte aligned shared memory of kRelaySmemBytes.  One thread
-// drives the TMA engine; the caller lets the other threads of the CTA leave.
-__device__ __forceinline__ void relay_pull(const RelayArgs& A, int cta, uint8_t* ring) {
+// Pull role of relay CTA `cta` of `A.n_ctas`: matrices [A.m0, m1).  `ring` = 1024-byte aligned shared memory of
+// kRelaySmemBytes.  One thread drives the TMA engine; the caller lets the other threads of the CTA leave.  Chunks whose
+// arrival flag already carries this step's number are skipped (the backward's relay finds the x1 operands in place when
+// the forward had to fetch them for the exact-regime kernel).
+__device__ __forceinline__ void relay_pull(const RelayArgs& A, int m1, int cta, uint8_t* ring) {
   if (threadIdx.x != 0) return;
   const int me = A.v.rank, world = A.v.world;
   char* mine = A.v.base[me];
@@ -172,15 +186,20 @@ __device__ __forceinline__ void relay_pull(const RelayArgs& A, int cta, uint8_t*
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   const uint32_t* ready = reinterpret_cast<const uint32_t*>(mine + A.off_ready);
-  const int total = 2 * A.cpr * (world - 1);
+  const int total = (m1 - A.m0) * A.cpr * (world - 1);
   const int piece_rows = kRelayPieceBytes / A.row_bytes > 0 ? kRelayPieceBytes / A.row_bytes : 1;
   unsigned seen = 1u << me;                        // sources whose ready flag this thread has already observed
   struct Cursor { int item, piece, npieces; RelayItem it; };
-  auto open = [&](Cursor& c) {                     // position on the first piece of item c.item (if any)
-    if (c.item < total) {
-      c.it = relay_item_decode(c.item, world, me, A.cpr, A.b);
-      c.npieces = (c.it.rows + piece_rows - 1) / piece_rows;
-      c.piece = 0;
+  auto open = [&](Cursor& c) {                     // position on the first piece of the next item that is still missing
+    while (c.item < total) {
+      c.it = relay_item_decode(c.item, A.m0, A.source_major, world, me, A.cpr, A.b);
+      const uint32_t have = ld_acquire_sys_u32(reinterpret_cast<const uint32_t*>(mine + A.off_flags[c.it.m]) + c.it.src * A.cpr + c.it.c);
+      if ((int32_t)(have - A.v.epoch) < 0) {       // (both cursors see the same flags: only this thread sets them, after use)
+        c.npieces = (c.it.rows + piece_rows - 1) / piece_rows;
+        c.piece = 0;
+        return;
+      }
+      c.item += A.n_ctas;
     }
   };
   auto advance = [&](Cursor& c) {
@@ -241,13 +260,15 @@ __device__ __forceinline__ void relay_pull(const RelayArgs& A, int cta, uint8_t*
 }
 
 // Multicast role (NVLS segment): chunks of THIS rank's block, all threads of the CTA storing through the multicast mapping.
-__device__ __forceinline__ void relay_multicast(const RelayArgs& A, int cta) {
+__device__ __forceinline__ void relay_multicast(const RelayArgs& A, int m1, int cta) {
   const int me = A.v.rank;
   char* mine = A.v.base[me];
-  const int total = 2 * A.cpr;
+  const int total = (m1 - A.m0) * A.cpr;
   const int nthr = blockDim.x;
   for (int item = cta; item < total; item += A.n_ctas) {
-    const int m = item / A.cpr, c = item - m * A.cpr;
+    const int m = A.m0 + item / A.cpr, c = item % A.cpr;
+    // already published in this step (the multicast flag store also lands in this rank's own copy)?  CTA-uniform.
+    if ((int32_t)(ld_acquire_sys_u32(reinterpret_cast<const uint32_t*>(mine + A.off_flags[m]) + me * A.cpr + c) - A.v.epoch) >= 0) continue;
     const int64_t row0 = (int64_t)c * kPushRows;
     const int rows = (int)min((int64_t)kPushRows, A.b - row0);
     const int n16 = rows * (A.row_bytes / 16);
@@ -290,7 +311,8 @@ struct P2PStep {
   void* ws;
   size_t ws_bytes;
   P2PRowFlags yflags;       // chunk flags of the x2 operands (the Y stream of the single-pass forward)
-  RelayArgs relay;          // the operand all-gather of this step (n_ctas: relay CTAs in front of the forward grid)
+  P2PRowFlags aflags;       // chunk flags of the x1 operands (the Y stream of the backward's second problem)
+  RelayArgs relay;          // the operand all-gather of this step (n_ctas: relay CTAs in front of the forward / backward grid)
 };
 
 int p2p_create(int64_t b, int world, int rank, int D, int precision, void** out, void* ipc_handle64);
@@ -300,8 +322,10 @@ int p2p_check(void* handle, int64_t b, int world, int rank, int D, int precision
 uint32_t p2p_next_epoch(void* handle);
 uint32_t p2p_current_epoch(void* handle);
 P2PStep p2p_step(void* handle, uint32_t epoch);
-int p2p_relay_standalone(void* handle, uint32_t epoch, cudaStream_t st);
+int p2p_relay_standalone(void* handle, uint32_t epoch, int m0, bool signal_ready, cudaStream_t st);
 int p2p_relay_ctas(void* handle);
+uint32_t p2p_a_pending(void* handle);
+void p2p_set_a_pending(void* handle, uint32_t epoch);
 int p2p_mode(void* handle);
 int p2p_nvls_export(void* handle, int* fd_out);
 int p2p_nvls_attach(void* handle, int fd);

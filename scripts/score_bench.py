@@ -38,7 +38,7 @@ N, M, g, k = 975, 4875, 5, 10
 out["c4_a2t"] = {"call_ms": ms12, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us,
                  "rank_bytes": 4 * N * M + 12 * N * k + 4 * N * g, "rank_gbs": (4 * N * M + 12 * N * k + 4 * N * g) / (rank_us * 1e-6) / 1e9,
                  "sim_gflops": 2 * N * M * 512 / (sim_us * 1e-6) / 1e9}
-ms21, _ = timed(lambda: vb.sim_rank_topk(tn, an, gt21))
+ms21, _ = timed(lambda: vb.sim_rank_topk(tn, an, gt21, topk=2))          # (topk > 1: the materialising kernels)
 sim_us, _ = prof(3); rank_us, _ = prof(4)
 out["c4_t2a"] = {"call_ms": ms21, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us,
                  "rank_gbs": (4 * N * M + 4 * M) / (rank_us * 1e-6) / 1e9}
@@ -69,11 +69,11 @@ out["c4_report"] = {"gpu_ms_incl_infer_batches": ms_rep, "cpu_oracle_numpy_ms": 
 audios, text, labels = zero_shot_inputs(c=50, seed=1213)
 au, tx = torch.from_numpy(audios).cuda(), torch.from_numpy(text).cuda()
 lib.vpa_profile_enable(1)
-ms_zs, _ = timed(lambda: vb.sim_rank_topk(au, tx, None, topk=1))
-sim_us, _ = prof(3); rank_us, _ = prof(4)
+ms_zs, _ = timed(lambda: vb.sim_rank_topk(au, tx, None, topk=1))          # fused kernel: similarity + argmax
+sim_us, _ = prof(3)
 lib.vpa_profile_enable(0)
 t0 = time.perf_counter(); ro.zero_shot_report(audios, text, labels); cpu_zs = (time.perf_counter() - t0) * 1e3
-out["c5_zero_shot"] = {"call_ms": ms_zs, "sim_kernel_us": sim_us, "rank_topk_kernel_us": rank_us, "cpu_oracle_numpy_ms": cpu_zs}
+out["c5_zero_shot"] = {"call_ms": ms_zs, "fused_kernels_us": sim_us, "cpu_oracle_numpy_ms": cpu_zs}
 
 # ---- normalise kernel alone at the training shape (HBM roofline row)
 x = torch.randn(32768, 512, device="cuda")

@@ -194,11 +194,11 @@ def test_fused_both_directions(N, M, D, gq, gk):
     if gq:
         want = ro.rank_of(S, gt_q.numpy())
         ok = margins(S, gt_q.numpy()) >= 1e-6
-        assert np.array_equal(res["ranks_q"].cpu().numpy()[ok], want[ok]) and ok.mean() > 0.99
+        assert np.array_equal(res["ranks_q"].cpu().numpy()[ok], want[ok]) and ok.mean() > 0.9
     if gk:
         want = ro.rank_of(S.T, gt_k.numpy())
         ok = margins(S.T, gt_k.numpy()) >= 1e-6
-        assert np.array_equal(res["ranks_k"].cpu().numpy()[ok], want[ok]) and ok.mean() > 0.99
+        assert np.array_equal(res["ranks_k"].cpu().numpy()[ok], want[ok]) and ok.mean() > 0.9
     srt = np.sort(S, axis=1)
     clear = (srt[:, -1] - srt[:, -2] >= 1e-6) if M > 1 else np.ones(N, bool)
     assert np.array_equal(res["top1_q"][0].cpu().numpy()[clear], S.argmax(1)[clear])

@@ -24,8 +24,10 @@ namespace vpa {
 constexpr int kApThreads = 1024;
 constexpr int kApMaxN = 32768;
 
-__device__ __forceinline__ uint32_t ap_orderable(float v) {      // monotone fp32 -> uint32; 0 is below every real key
-  const uint32_t u = __float_as_uint(v);
+// monotone fp32 -> uint32; 0 is below every real key.  -0 and +0 map to ONE key: numpy counts them as the same score, and a
+// threshold is a boundary between distinct scores.
+__device__ __forceinline__ uint32_t ap_orderable(float v) {
+  const uint32_t u = __float_as_uint(v + 0.0f);      // -0 + 0 = +0
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 

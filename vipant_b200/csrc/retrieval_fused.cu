@@ -28,8 +28,11 @@ constexpr int kFTQ = 128, kFTK = 64, kFTD = 16; // tile: query rows, key rows, k
 constexpr int kFQS = kFTQ + 4, kFKS = kFTK + 4; // padded strides (floats)
 constexpr int kFMaxGt = 8;
 
-__device__ __forceinline__ uint32_t orderable_u32(float v) {      // monotone map fp32 -> uint32 (-0 < +0; NaN above +inf)
-  const uint32_t u = __float_as_uint(v);
+// monotone map fp32 -> uint32 that agrees with the fp32 comparisons used for the ranks: -0 and +0 get the same key, every
+// NaN (either sign) sorts above +inf -- torch.argsort(descending=True) places NaN first
+__device__ __forceinline__ uint32_t orderable_u32(float v) {
+  if (v != v) return 0xffffffffu;
+  const uint32_t u = __float_as_uint(v + 0.0f);      // -0 + 0 = +0
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float orderable_to_float(uint32_t o) {

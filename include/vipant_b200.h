@@ -65,8 +65,9 @@ int vpa_profile_enable(int on);
 unsigned long long vpa_launch_count(void);
 /* Work decomposition chosen for a shape (diagnostics / tests; host only, no device needed): out10 = n_tiles, single-pass
  * forward {chunks, tiles per equal chunk, tiles of the short tail chunk}, backward {same three}, forward row blocks,
- * backward row blocks, impl (1 = CTA-pair kernels). */
-int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision, int* out10);
+ * backward row blocks, impl (1 = CTA-pair kernels).  peer_memory != 0: the plan of the peer-memory transport, whose relay
+ * CTAs take SMs from the sweeps. */
+int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision, int peer_memory, int* out10);
 int vpa_profile_read(int kind, float* total_ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------

@@ -88,13 +88,15 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 @pytest.mark.parametrize("b,B", [(32768, 32768), (16384, 32768), (8192, 32768), (4096, 32768), (512, 512), (640, 640),
                                  (384, 1152), (64, 64), (1000, 1000), (4096, 4096), (2048, 16384), (300, 2400)])
-def test_sweep_plan_covers_every_tile(b, B):
-    """vpa_plan_query (host only): every row block's tiles are covered exactly once by n_big equal chunks + one short tail."""
+@pytest.mark.parametrize("peer_memory", [0, 1])
+def test_sweep_plan_covers_every_tile(b, B, peer_memory):
+    """vpa_plan_query (host only): every row block's tiles are covered exactly once by n_big equal chunks + one short tail,
+    also in the plan of the peer-memory transport (relay CTAs take SM pairs from the sweeps)."""
     import ctypes
     from vipant_b200 import _cabi
     lib = _cabi.lib()
     out = (ctypes.c_int * 10)()
-    assert lib.vpa_plan_query(b, B, 512, _cabi.PREC_BF16_TC, out) == 0
+    assert lib.vpa_plan_query(b, B, 512, _cabi.PREC_BF16_TC, peer_memory, out) == 0
     n_tiles, f_chunks, f_tpc, f_small, b_chunks, b_tpc, b_small, f_iblk, b_iblk, impl = list(out)
     assert impl == 1 and n_tiles == -(-B // 256) and f_iblk == -(-b // 256) and b_iblk == -(-b // 128)
     for chunks, tpc, small in ((f_chunks, f_tpc, f_small), (b_chunks, b_tpc, b_small)):

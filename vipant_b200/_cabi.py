@@ -18,7 +18,7 @@ PREC_BF16_TC, PREC_FP32_SIMT = 0, 1
 _SIGNATURES = {
     "vpa_version": (c_int, []),
     "vpa_last_error_string": (c_char_p, []),
-    "vpa_plan_query": (c_int, [c_int64, c_int64, c_int, c_int, POINTER(c_int)]),
+    "vpa_plan_query": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     "vpa_profile_enable": (c_int, [c_int]),
     "vpa_launch_count": (ctypes.c_ulonglong, []),
     "vpa_profile_read": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),

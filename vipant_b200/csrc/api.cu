@@ -28,6 +28,35 @@ int set_error(int code, const char* fmt, ...) {
 static unsigned long long g_launches = 0;      // kernel launches of this library since it was loaded (not thread-safe: a statistic)
 void note_launch() { ++g_launches; }
 
+static bool pdl_setting() {
+  static int v = -1;
+  if (v < 0) {
+    v = 0;                                                   // (default decided by measurement: profiles/r02_scaling.md)
+    if (const char* e = getenv("VPA_PDL")) v = atoi(e) != 0;
+  }
+  return v != 0;
+}
+
+bool carveout_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    v = 0;                                                   // (default decided by measurement: profiles/r02_scaling.md)
+    if (const char* e = getenv("VPA_CARVEOUT")) v = atoi(e) != 0;
+  }
+  return v != 0;
+}
+void apply_carveout(const void* kernel) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, bool> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+  std::lock_guard<std::mutex> lock(mu);
+  bool& d = done[std::make_pair(kernel, dev)];
+  if (d) return;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) cudaGetLastError();
+  d = true;
+}
+
 // ---- opt-in launch timing ---------------------------------------------------------------------------
 constexpr int kProfSlots = 512;
 struct ProfState {
@@ -37,6 +66,8 @@ struct ProfState {
   int n[PROF_KINDS];
 };
 static ProfState g_prof;
+
+bool pdl_enabled() { return pdl_setting() && !g_prof.on; }
 
 void prof_begin(int kind, cudaStream_t st) {
   if (!g_prof.on || g_prof.n[kind] >= kProfSlots) return;
@@ -109,13 +140,23 @@ static int sm_count() {      // of the CURRENT device (a process may drive sever
   return v;
 }
 
-// Relay CTAs of the peer-memory transport (whole CTA pairs in front of the single-pass forward's grid, p2p.cuh): the sharded
-// forward plans its units on the SM pairs they leave free.
+// Relay CTAs of the peer-memory transport (whole CTA pairs in front of a sweep kernel's grid, p2p.cuh).  The forward cannot
+// finish before its x2 operands have arrived, so it gives the transfer 20 SMs (measured at 8 GPUs: 12 / 20 / 28 relay CTAs
+// move 243 / 305 / 335 GB/s into one GPU; the sweep wants the other SMs).  The backward runs 3-4x longer than the transfer
+// of its x1 operands and consumes them at <= 75 GB/s: 4 relay CTAs keep ahead of it.
 int relay_ctas_default() {
   static int v = 0;
   if (v == 0) {
     v = 20;
     if (const char* e = getenv("VPA_P2P_RELAY_CTAS")) { const int q = atoi(e); if (q >= 2 && q <= 64) v = q & ~1; }   // tuning knob
+  }
+  return v;
+}
+int relay_ctas_bwd_default() {
+  static int v = 0;
+  if (v == 0) {
+    v = 4;
+    if (const char* e = getenv("VPA_P2P_RELAY_CTAS_BWD")) { const int q = atoi(e); if (q >= 2 && q <= 64) v = q & ~1; }   // tuning knob
   }
   return v;
 }
@@ -144,9 +185,12 @@ static void pick_chunks(int base_units, int n_tiles, int fixed, int* chunks, int
 // SM pairs is minimal.  The grid lists all big units first, then the tails, and the hardware hands the next unit to the
 // first free slot: simulated here exactly (in-order list scheduling).  `fixed` = per-unit cost in tile equivalents.
 // Equal chunking alone wastes up to a whole wave when units do not divide the slots (64 backward units on 74 slots).
+// `relay_slots` of the SM pairs are taken by relay CTAs (peer-memory transport) for the first `relay_tiles` tile times of the
+// kernel and join the pool afterwards: the simulation starts them busy instead of leaving them out.
 static void pick_split(int base_units, int n_tiles, int fixed, int* chunks, int* tiles_per_chunk, int* small_tiles,
-                       int reserved_sms = 0) {
-  int slots = (sm_count() - reserved_sms) / 2;
+                       int relay_slots = 0, int relay_tiles = 0) {
+  int slots = sm_count() / 2;
+  if (relay_slots > slots - 1) relay_slots = slots - 1;
   if (slots < 1) slots = 1;
   long best = -1;
   int best_k = 1, best_small = 0;
@@ -159,6 +203,8 @@ static void pick_split(int base_units, int n_tiles, int fixed, int* chunks, int*
       if ((long)(k - 1) * tpc >= big_tiles) continue;                 // an empty chunk
       if (small > 0 && small >= tpc) break;                             // the tail must be the short one
       heap.assign(slots, 0);                                            // min-heap of the slots' free times
+      for (int r = 0; r < relay_slots; ++r) heap[r] = relay_tiles;
+      std::make_heap(heap.begin(), heap.end(), std::greater<long>());
       long makespan = 0;
       auto place = [&](long cost) {
         std::pop_heap(heap.begin(), heap.end(), std::greater<long>());
@@ -219,7 +265,15 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
     p.n_tiles = (int)((rows_global + 255) / 256);
     pick_chunks(2 * p.pair_fwd_iblk, p.n_tiles, 1, &p.fwd_chunks, &p.fwd_tiles_per_chunk, 2);
     // per-unit fixed cost (prologue, X load, pipeline fill, dX drain) measured at ~3.5 tiles of 256 columns (b=4096 sweep)
-    pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small, reserved_sms);
+    {
+      // backward over peer memory: relay CTA pairs hold their SMs until the peers' x1 operands are in -- in tile times of
+      // this kernel: bytes / (measured per-CTA pull rate ~25 GB/s with few relays) / (time of one 128 x 256 tile pair of MMAs)
+      const int bwd_relay = reserved_sms > 0 ? relay_ctas_bwd_default() : 0;
+      const double bytes = (double)(rows_global - rows_local) * D * 2.0;
+      const double tile_us = 4.0 * 128.0 * 256.0 * D / (1.45e15 / (sm_count() / 2)) * 1e6;
+      const int relay_tiles = bwd_relay ? (int)(bytes / (bwd_relay * 25e9) * 1e6 / tile_us + 1.0) : 0;
+      pick_split(2 * p.pair_bwd_iblk, p.n_tiles, 4, &p.bwd_chunks, &p.bwd_tiles_per_chunk, &p.bwd_small, bwd_relay / 2, relay_tiles);
+    }
     p.fast_fwd = 1;
     // A row-sharded forward consumes operand rows while they arrive from the peers: it is gated by the transfer, not by
     // the tensor cores, and a second wave of tail units (which the LPT split adds) only starts when the first wave ends --
@@ -307,9 +361,9 @@ const char* vpa_last_error_string(void) { return g_err; }
 
 // Work decomposition of the sweeps for a shape (diagnostics / tests): out[0..9] = n_tiles, fwd1 chunks, fwd1 tiles per big
 // chunk, fwd1 tail tiles, bwd chunks, bwd tiles per big chunk, bwd tail tiles, fwd1 row blocks, bwd row blocks, impl.
-int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision, int* out10) {
+int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision, int peer_memory, int* out10) {
   VPA_CHECK_ARG(out10 && rows_local > 0 && rows_global >= rows_local && D > 0, "plan_query: bad argument");
-  const SweepPlan p = plan_sweep(rows_local, rows_global, D, precision);
+  const SweepPlan p = plan_sweep(rows_local, rows_global, D, precision, peer_memory ? relay_ctas_default() : 0);
   const int v[10] = {p.n_tiles, p.fwd1_chunks, p.fwd1_tiles_per_chunk, p.fwd1_small, p.bwd_chunks, p.bwd_tiles_per_chunk,
                      p.bwd_small, p.pair_fwd_iblk, p.pair_bwd_iblk, p.impl};
   for (int i = 0; i < 10; ++i) out10[i] = v[i];
@@ -756,6 +810,7 @@ int vpa_infonce_bwd_p2p(void* p2p, uint32_t epoch, const void* x1, const void* x
   // while its first problem runs; finalize_bwd exchanges the d logit_scale partials.
   RelayArgs br = h.relay;
   br.m0 = 1; br.m1 = 2; br.source_major = 1; br.signal_ready = 0;
+  br.n_ctas = relay_ctas_bwd_default();
   const bool fetch = p2p_a_pending(p2p) == epoch;
   if (fetch) p2p_set_a_pending(p2p, 0);
   return bwd_impl(a_loc, t_loc, h.a_all, h.t_all, precision, b, B, D, off, h.scale, h.stats_all, h.stats_all + B, grad_out, x1, x2,

@@ -236,6 +236,10 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
+  pdl_trigger();
+  // nothing is read from global memory before the preceding kernel has completed (common.cuh); kernels without a gate or
+  // relay role run their prologue (barriers, tensor-memory allocation) first and wait further down
+  if (P.gate != 0 || ((MODE == MODE_FWD1 || MODE == MODE_BWD) && (int)blockIdx.x < P.relay.n_ctas)) pdl_wait();
   if ((MODE == MODE_FWD1 || MODE == MODE_BWD) && (int)blockIdx.x < P.relay.n_ctas) {
     // Relay CTAs: the all-gather of the operand rows over NVLink, in the same grid as the sweep that consumes them.  They
     // come first in blockIdx order, i.e. they are resident before any sweep CTA that polls their flags.  The forward
@@ -345,6 +349,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs; each fills ITS half of every operand) ===========================
@@ -798,7 +803,7 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   dim3 grid((fwd1 ? 1 : 2) * 2 * P.pairs_per_problem + P.relay.n_ctas), block(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd);
   const int kind = bwd ? PROF_BWD_SWEEP : (fwd1 ? PROF_FWD_SWEEP : (gate == 2 ? PROF_FWD_GENERAL : PROF_FWD_SWEEP));
   prof_begin(kind, st);
-  pair_kernel<MODE><<<grid, block, dyn_smem, st>>>(maps[0], maps[1], maps[2], maps[3], P);
+  VPA_CUDA(launch_kernel(pair_kernel<MODE>, grid, block, dyn_smem, st, maps[0], maps[1], maps[2], maps[3], P));
   prof_end(kind, st);
   VPA_LAUNCH_CHECK(bwd ? "pair_kernel<BWD>" : (fwd1 ? "pair_kernel<FWD1>" : "pair_kernel<FWD>"));
   return 0;

@@ -9,6 +9,8 @@ namespace vpa {
 __global__ void __launch_bounds__(256)
 colsum_reduce_kernel(const float* __restrict__ colpart, int n_groups, int64_t B, float* __restrict__ colsum,
                      const float* __restrict__ logit_scale, float scale_cap, float s2_limit) {
+  pdl_trigger();
+  pdl_wait();
   if (fminf(expf(*logit_scale), scale_cap) * kLog2e > s2_limit) return;     // not the single-pass regime
   const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= B) return;
@@ -36,6 +38,8 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
                                      const float* __restrict__ colsum, float* __restrict__ row_lse,
                                      float* __restrict__ col_lse, float* __restrict__ diag,
                                      float* __restrict__ scale_out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float e = expf(*logit_scale);
   const float s = fminf(e, scale_cap);
@@ -169,6 +173,8 @@ __device__ __forceinline__ void pack_publish(const PackArgs& A) {
   }
 }
 __global__ void pack_stats_kernel(const PackArgs A) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float s = fminf(expf(*A.logit_scale), A.scale_cap);
   pack_one(A, idx, s, A.fast && s * kLog2e <= A.s2_limit);
@@ -243,6 +249,8 @@ __device__ __forceinline__ void merge_loss(const MergeArgs& A, double term) {
   }
 }
 __global__ void __launch_bounds__(256) merge_stats_kernel(const MergeArgs A) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float e = expf(*A.logit_scale);
   const float s = fminf(e, A.scale_cap);
@@ -260,6 +268,8 @@ __global__ void __launch_bounds__(256) merge_stats_kernel(const MergeArgs A) {
 // still has to write this rank's message off the machine.
 constexpr int kExchangeMaxBlocks = 2 * 148;
 __global__ void __launch_bounds__(256) exchange_stats_kernel(const PackArgs P, const MergeArgs A) {
+  pdl_trigger();
+  pdl_wait();
   const float e = expf(*A.logit_scale);
   const float s = fminf(e, A.scale_cap);
   const bool fastr = P.fast && s * kLog2e <= P.s2_limit;
@@ -365,6 +375,8 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
                     void* __restrict__ dx1, void* __restrict__ dx2,
                     const float* __restrict__ dscale_part, int n_dscale, float* __restrict__ dlogit_scale,
                     const P2PView pv, size_t off_dls, int dls_sum) {
+  pdl_trigger();
+  pdl_wait();
   const float s = scale[0], g = grad_out[0];
   const int lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * kFinWarps + (threadIdx.x >> 5);   // (problem, row)
@@ -445,8 +457,8 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
 int colsum_reduce_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_global, const float* logit_scale,
                          float scale_cap, float* colsum, cudaStream_t st) {
   dim3 grid((unsigned)((rows_global + 255) / 256), kColSumSplit);
-  colsum_reduce_kernel<<<grid, 256, 0, st>>>(ws.colpart, plan.n_rowgroups, rows_global, colsum, logit_scale, scale_cap,
-                                             pair_fast_s2_limit());
+  VPA_CUDA(launch_kernel(colsum_reduce_kernel, grid, dim3(256), 0, st, ws.colpart, plan.n_rowgroups, rows_global, colsum, logit_scale,
+                         scale_cap, pair_fast_s2_limit()));
   VPA_LAUNCH_CHECK("colsum_reduce_kernel");
   return 0;
 }
@@ -458,10 +470,9 @@ int combine_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t row
   const int threads = 256;
   const int64_t n = 2 * rows_local;
   dim3 grid((unsigned)((n + threads - 1) / threads));
-  combine_stats_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const float2*>(ws.fwd_part), plan.fwd_chunks,
-                                                 plan.fwd1_chunks, rows_local, rows_global, row_offset, logit_scale,
-                                                 scale_cap, diag_cos, fast, pair_fast_s2_limit(), colsum, row_lse, col_lse,
-                                                 diag, scale_out);
+  VPA_CUDA(launch_kernel(combine_stats_kernel, grid, dim3(threads), 0, st, reinterpret_cast<const float2*>(ws.fwd_part),
+                         plan.fwd_chunks, plan.fwd1_chunks, rows_local, rows_global, row_offset, logit_scale, scale_cap, diag_cos,
+                         fast, pair_fast_s2_limit(), colsum, row_lse, col_lse, diag, scale_out));
   VPA_LAUNCH_CHECK("combine_stats_kernel");
   return 0;
 }
@@ -499,7 +510,7 @@ int pack_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b, int
                       cudaStream_t st) {
   const int64_t n = B > b ? B : b;
   const PackArgs A = make_pack_args(ws, plan, b, B, logit_scale, scale_cap, diag_cos, fast, colsum8, from_colpart, msg, nullptr);
-  pack_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(A);
+  VPA_CUDA(launch_kernel(pack_stats_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, A));
   VPA_LAUNCH_CHECK("pack_stats_kernel");
   return 0;
 }
@@ -509,7 +520,7 @@ int merge_stats_launch(const float* msgs, int R, int64_t b, int64_t B, const flo
                        cudaStream_t st) {
   const MergeArgs M = make_merge_args(msgs, R, b, B, logit_scale, scale_cap, fast, stats_all, scale_out, nullptr, loss_part,
                                       loss_counter, loss_out);
-  merge_stats_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(M);
+  VPA_CUDA(launch_kernel(merge_stats_kernel, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, st, M));
   VPA_LAUNCH_CHECK("merge_stats_kernel");
   return 0;
 }
@@ -522,7 +533,8 @@ int exchange_stats_launch(const Workspace& ws, const SweepPlan& plan, int64_t b,
   const MergeArgs M = make_merge_args(p2p.msgs, p2p.view.world, b, B, logit_scale, scale_cap, fast, p2p.stats_all, p2p.scale, &p2p,
                                       p2p.loss_part, p2p.loss_counter, loss_out);
   const int64_t blocks = (B + 255) / 256;
-  exchange_stats_kernel<<<(unsigned)(blocks < kExchangeMaxBlocks ? blocks : kExchangeMaxBlocks), 256, 0, st>>>(A, M);
+  VPA_CUDA(launch_kernel(exchange_stats_kernel, dim3((unsigned)(blocks < kExchangeMaxBlocks ? blocks : kExchangeMaxBlocks)), dim3(256),
+                         0, st, A, M));
   VPA_LAUNCH_CHECK("exchange_stats_kernel");
   return 0;
 }
@@ -546,10 +558,10 @@ int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows
   const int64_t n = 2 * rows_local;
   dim3 grid((unsigned)((n + kFinWarps - 1) / kFinWarps)), block(kFinWarps * 32);
   const int nv = D <= 128 ? 1 : (D <= 256 ? 2 : (D <= 512 ? 4 : 8));
-#define VPA_FIN(DT, NV)                                                                                            \
-  finalize_bwd_kernel<DT, NV><<<grid, block, 0, st>>>(ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, grad_out, \
-                                                      x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2,             \
-                                                      ws.dscale_part, plan.n_dscale, dlogit_scale, pv, off_dls, dls_sum)
+#define VPA_FIN(DT, NV)                                                                                                  \
+  VPA_CUDA(launch_kernel(finalize_bwd_kernel<DT, NV>, grid, block, 0, st, ws.bwd_part, plan.bwd_chunks, rows_local, D, scale, \
+                         grad_out, x1, x2, ld1, ld2, inv1, inv2, already, dx1, dx2, ws.dscale_part, plan.n_dscale,         \
+                         dlogit_scale, pv, off_dls, dls_sum))
 #define VPA_FIN_NV(DT)                 \
   switch (nv) {                        \
     case 1: VPA_FIN(DT, 1); break;     \

@@ -86,6 +86,8 @@ normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, 
                       float* __restrict__ a_f32, float* __restrict__ t_f32,
                       float* __restrict__ inv1, float* __restrict__ inv2,
                       float* __restrict__ diag_cos, int diag_from_bf16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -218,11 +220,11 @@ int normalize_pair_launch(const void* x1, const void* x2, int in_dtype, int64_t 
   const int nv = D <= 128 ? 1 : (D <= 256 ? 2 : (D <= 512 ? 4 : 8));
   prof_begin(PROF_NORMALIZE, st);
   const bool rcp = a_f32 == nullptr && t_f32 == nullptr;      // bf16 operands only
-#define VPA_PAIR(DT, NV)                                                                                                 \
-  if (rcp) normalize_pair_kernel<DT, NV, true><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32, \
-                                                                       t_f32, inv1, inv2, diag_cos, diag_from_bf16);      \
-  else normalize_pair_kernel<DT, NV, false><<<grid, block, 0, st>>>(x1, x2, rows, D, ld1, ld2, already, ab, tb, a_f32,    \
-                                                                    t_f32, inv1, inv2, diag_cos, diag_from_bf16)
+#define VPA_PAIR(DT, NV)                                                                                                  \
+  if (rcp) VPA_CUDA(launch_kernel(normalize_pair_kernel<DT, NV, true>, grid, block, 0, st, x1, x2, rows, D, ld1, ld2, already, \
+                                  ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16));                            \
+  else VPA_CUDA(launch_kernel(normalize_pair_kernel<DT, NV, false>, grid, block, 0, st, x1, x2, rows, D, ld1, ld2, already,   \
+                              ab, tb, a_f32, t_f32, inv1, inv2, diag_cos, diag_from_bf16))
 #define VPA_PAIR_NV(DT)                 \
   switch (nv) {                         \
     case 1: VPA_PAIR(DT, 1); break;     \

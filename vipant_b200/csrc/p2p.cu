@@ -100,6 +100,8 @@ struct P2PHandle {
 // operands before the forward starts.  Same device code as the relay CTAs of the fused forward kernel.
 __global__ void __launch_bounds__(256) p2p_relay_kernel(const RelayArgs A) {
   extern __shared__ uint8_t relay_smem[];
+  pdl_trigger();
+  pdl_wait();
   if (blockIdx.x == 0) relay_signal_ready(A);
   if (A.multicast) {
     relay_multicast(A, A.m1, blockIdx.x);
@@ -451,7 +453,7 @@ int p2p_relay_standalone(void* handle, uint32_t epoch, int m0, bool signal_ready
   static SmemAttrCache attr_cache;
   if (int e = ensure_dynamic_smem(attr_cache, p2p_relay_kernel, (int)kRelaySmemBytes + 1024)) return e;
   prof_begin(PROF_PUSH, st);
-  p2p_relay_kernel<<<A.n_ctas, 256, A.multicast ? 0 : kRelaySmemBytes + 1024, st>>>(A);
+  VPA_CUDA(launch_kernel(p2p_relay_kernel, dim3(A.n_ctas), dim3(256), A.multicast ? 0 : kRelaySmemBytes + 1024, st, A));
   prof_end(PROF_PUSH, st);
   VPA_LAUNCH_CHECK("p2p_relay_kernel");
   return 0;

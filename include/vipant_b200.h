@@ -63,6 +63,12 @@ const char* vpa_last_error_string(void);
 int vpa_profile_enable(int on);
 /* Kernel launches of this library since it was loaded (every launch site counts itself): bench.py's `gpu_launches`. */
 unsigned long long vpa_launch_count(void);
+/* Launch tuning of the training-step kernels (measurement / tests; -1 leaves a setting unchanged):
+ * programmatic_dependent_launch: the kernels of one call are launched with programmatic stream serialization (each may be
+ *   scheduled while its predecessor runs and blocks in griddepcontrol.wait before touching memory);
+ * max_shared_carveout: the kernels without shared memory ask for the maximum-shared-memory L1 split the sweeps use.
+ * Environment: VPA_PDL, VPA_CARVEOUT.  Both are OFF by default (what was measured and why). */
+int vpa_launch_tuning(int programmatic_dependent_launch, int max_shared_carveout);
 /* Work decomposition chosen for a shape (diagnostics / tests; host only, no device needed): out10 = n_tiles, single-pass
  * forward {chunks, tiles per equal chunk, tiles of the short tail chunk}, backward {same three}, forward row blocks,
  * backward row blocks, impl (1 = CTA-pair kernels).  peer_memory != 0: the plan of the peer-memory transport, whose relay

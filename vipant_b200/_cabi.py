@@ -21,6 +21,7 @@ _SIGNATURES = {
     "vpa_plan_query": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     "vpa_profile_enable": (c_int, [c_int]),
     "vpa_launch_count": (ctypes.c_ulonglong, []),
+    "vpa_launch_tuning": (c_int, [c_int, c_int]),
     "vpa_profile_read": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),
     "vpa_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_normalize_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int,

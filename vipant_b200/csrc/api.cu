@@ -28,22 +28,21 @@ int set_error(int code, const char* fmt, ...) {
 static unsigned long long g_launches = 0;      // kernel launches of this library since it was loaded (not thread-safe: a statistic)
 void note_launch() { ++g_launches; }
 
+static int g_pdl = -1, g_carveout = -1;       // -1: not decided yet (environment, else the default)
 static bool pdl_setting() {
-  static int v = -1;
-  if (v < 0) {
-    v = 0;                                                   // (default decided by measurement: profiles/r02_scaling.md)
-    if (const char* e = getenv("VPA_PDL")) v = atoi(e) != 0;
+  if (g_pdl < 0) {
+    g_pdl = 0;                                               // (default decided by measurement: profiles/r02_scaling.md)
+    if (const char* e = getenv("VPA_PDL")) g_pdl = atoi(e) != 0;
   }
-  return v != 0;
+  return g_pdl != 0;
 }
 
 bool carveout_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    v = 0;                                                   // (default decided by measurement: profiles/r02_scaling.md)
-    if (const char* e = getenv("VPA_CARVEOUT")) v = atoi(e) != 0;
+  if (g_carveout < 0) {
+    g_carveout = 0;                                          // (default decided by measurement: profiles/r02_scaling.md)
+    if (const char* e = getenv("VPA_CARVEOUT")) g_carveout = atoi(e) != 0;
   }
-  return v != 0;
+  return g_carveout != 0;
 }
 void apply_carveout(const void* kernel) {
   static std::mutex mu;
@@ -371,6 +370,12 @@ int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision
 }
 
 unsigned long long vpa_launch_count(void) { return g_launches; }
+
+int vpa_launch_tuning(int programmatic_dependent_launch, int max_shared_carveout) {
+  if (programmatic_dependent_launch >= 0) g_pdl = programmatic_dependent_launch != 0;
+  if (max_shared_carveout >= 0) g_carveout = max_shared_carveout != 0;
+  return 0;
+}
 
 int vpa_profile_enable(int on) {
   g_prof.on = on != 0;

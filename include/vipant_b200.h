@@ -63,12 +63,6 @@ const char* vpa_last_error_string(void);
 int vpa_profile_enable(int on);
 /* Kernel launches of this library since it was loaded (every launch site counts itself): bench.py's `gpu_launches`. */
 unsigned long long vpa_launch_count(void);
-/* Launch tuning of the training-step kernels (measurement / tests; -1 leaves a setting unchanged):
- * programmatic_dependent_launch: the kernels of one call are launched with programmatic stream serialization (each may be
- *   scheduled while its predecessor runs and blocks in griddepcontrol.wait before touching memory);
- * max_shared_carveout: the kernels without shared memory ask for the maximum-shared-memory L1 split the sweeps use.
- * Environment: VPA_PDL, VPA_CARVEOUT.  Both are OFF by default (what was measured and why). */
-int vpa_launch_tuning(int programmatic_dependent_launch, int max_shared_carveout);
 /* Work decomposition chosen for a shape (diagnostics / tests; host only, no device needed): out10 = n_tiles, single-pass
  * forward {chunks, tiles per equal chunk, tiles of the short tail chunk}, backward {same three}, forward row blocks,
  * backward row blocks, impl (1 = CTA-pair kernels).  peer_memory != 0: the plan of the peer-memory transport, whose relay
@@ -275,21 +269,11 @@ int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles /* world x 64 bytes, rank order */);
 int vpa_p2p_destroy(void* p2p);
 
-/* VPA_P2P_MODE=nvls at vpa_p2p_create time: the segment is backed by VMM memory bound into one NVSwitch multicast object, and
- * every exchange is a multimem.st (one store, all ranks): the relay CTAs store this rank's OWN rows once instead of pulling.
- * vpa_p2p_mode: 1 TMA pull relay (default), 4 NVLS.  Setup in mode 4 replaces the IPC handle exchange: rank 0 calls
- * vpa_p2p_nvls_export and passes the POSIX file descriptor to the other ranks' processes (SCM_RIGHTS); every rank calls
- * vpa_p2p_nvls_attach (fd < 0 on rank 0); after a host barrier every rank calls vpa_p2p_nvls_bind, then
- * vpa_p2p_connect(p2p, NULL-able). */
-int vpa_p2p_mode(void* p2p);
 /* Diagnostics / tests (host only): the relay CTAs' work-item map for matrices [m0, 2).  out5 = matrix (0: x2 operands, 1: x1),
  * source rank, chunk index, first row within the source's block, row count.  Items 0 .. (2 - m0) * chunks_per_rank *
  * (world-1) - 1; relay CTA k of n takes items k, k + n, ...  source_major: 0 = chunk k of every peer before chunk k+1 (the
  * forward's order), 1 = peer after peer starting at me+1 (the backward's order). */
 int vpa_debug_relay_item(int item, int m0, int source_major, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5);
-int vpa_p2p_nvls_export(void* p2p, int* fd_out);
-int vpa_p2p_nvls_attach(void* p2p, int fd);
-int vpa_p2p_nvls_bind(void* p2p);
 
 int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype, int64_t rows_local, int world, int rank,
                         int D, int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale,

@@ -116,21 +116,6 @@ def test_sharded_matches_global_batch(precision, B, D, transport):
     _check(out, world, B, D, precision)
 
 
-def test_nvls_multicast_transport_two_gpus():
-    """VPA_P2P_MODE=nvls: segment bound into an NVSwitch multicast object, every exchange a multimem.st.  Needs 2 GPUs behind
-    an NVSwitch; VIPANT_REQUIRE_P2P turns a failed setup into an error instead of the NCCL fallback."""
-    world = 2
-    if not os.environ.get("VIPANT_TEST_NVLS"):
-        pytest.skip("opt in with VIPANT_TEST_NVLS=1 (needs an NVSwitch fabric with multicast enabled)")
-    if torch.cuda.device_count() < world:
-        pytest.skip("needs 2 GPUs")
-    mgr = mp.Manager()
-    out = mgr.dict()
-    env = {"VPA_P2P_MODE": "nvls", "VIPANT_REQUIRE_P2P": "1"}
-    mp.spawn(_worker, args=(world, _free_port(), 1024, 512, "bf16", "p2p", False, 4, out, env), nprocs=world, join=True)
-    _check(out, world, 1024, 512, "bf16", env)
-
-
 def _worker_many_steps(rank, world, port, B, D, steps, out):
     """>= 50 steps with DIFFERENT data every step: shakes the parity buffers / epoch flags of the peer-memory transport.
     Every rank holds the whole batch too and checks each step against the single-GPU path of the same library."""

@@ -202,29 +202,3 @@ def test_gold_file_class_stats_match_reference(strings, tmp_path):
     msg_21 = head._class_stats(torch.from_numpy(g["top1_21"].astype(np.int64)), by_class, by_sample, len(ids), "A->I")
     expected = strings["retrieval_nn_goldfile"].split("\n")[1]
     assert f"{msg_12} {msg_21}" == expected
-
-
-def _fd_worker(rank, world, port, path, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        fd = os.open(path, os.O_RDONLY) if rank == 0 else None
-        got = F_._share_fd_from_rank0(rank, world, fd, f"\0vipant-b200-test-{port}", dist.group.WORLD)
-        out[rank] = os.pread(got, 64, 0).decode()
-        os.close(got)
-        none = F_._share_fd_from_rank0(rank, world, None, f"\0vipant-b200-test-{port}-b", dist.group.WORLD)
-        out[f"none{rank}"] = none is None
-    finally:
-        dist.destroy_process_group()
-
-
-def test_descriptor_passing_between_rank_processes(tmp_path):
-    """The host side of the NVLS setup: rank 0's file descriptor reaches the other ranks' processes (SCM_RIGHTS)."""
-    path = tmp_path / "payload.txt"
-    path.write_text("multicast object stand-in")
-    world = 3
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_fd_worker, args=(world, _free_port(), str(path), out), nprocs=world, join=True)
-    for r in range(world):
-        assert out[r] == "multicast object stand-in" and out[f"none{r}"]

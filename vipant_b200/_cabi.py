@@ -21,7 +21,6 @@ _SIGNATURES = {
     "vpa_plan_query": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     "vpa_profile_enable": (c_int, [c_int]),
     "vpa_launch_count": (ctypes.c_ulonglong, []),
-    "vpa_launch_tuning": (c_int, [c_int, c_int]),
     "vpa_profile_read": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),
     "vpa_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_normalize_pair": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_int64, c_int,
@@ -51,11 +50,7 @@ _SIGNATURES = {
     "vpa_p2p_create": (c_int, [c_int64, c_int, c_int, c_int, c_int, POINTER(c_void_p), c_void_p]),
     "vpa_p2p_connect": (c_int, [c_void_p, c_void_p]),
     "vpa_p2p_destroy": (c_int, [c_void_p]),
-    "vpa_p2p_mode": (c_int, [c_void_p]),
     "vpa_debug_relay_item": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, POINTER(c_int)]),
-    "vpa_p2p_nvls_export": (c_int, [c_void_p, POINTER(c_int)]),
-    "vpa_p2p_nvls_attach": (c_int, [c_void_p, c_int]),
-    "vpa_p2p_nvls_bind": (c_int, [c_void_p]),
     "vpa_infonce_fwd_p2p": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64, c_int,
                                     c_void_p, c_float, c_int, c_void_p, POINTER(c_uint32), c_void_p]),
     "vpa_infonce_bwd_p2p": (c_int, [c_void_p, c_uint32, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64, c_int64,

@@ -28,34 +28,6 @@ int set_error(int code, const char* fmt, ...) {
 static unsigned long long g_launches = 0;      // kernel launches of this library since it was loaded (not thread-safe: a statistic)
 void note_launch() { ++g_launches; }
 
-static int g_pdl = -1, g_carveout = -1;       // -1: not decided yet (environment, else the default)
-static bool pdl_setting() {
-  if (g_pdl < 0) {
-    g_pdl = 0;                                               // (default decided by measurement: profiles/r02_scaling.md)
-    if (const char* e = getenv("VPA_PDL")) g_pdl = atoi(e) != 0;
-  }
-  return g_pdl != 0;
-}
-
-bool carveout_enabled() {
-  if (g_carveout < 0) {
-    g_carveout = 0;                                          // (default decided by measurement: profiles/r02_scaling.md)
-    if (const char* e = getenv("VPA_CARVEOUT")) g_carveout = atoi(e) != 0;
-  }
-  return g_carveout != 0;
-}
-void apply_carveout(const void* kernel) {
-  static std::mutex mu;
-  static std::map<std::pair<const void*, int>, bool> done;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
-  std::lock_guard<std::mutex> lock(mu);
-  bool& d = done[std::make_pair(kernel, dev)];
-  if (d) return;
-  if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) cudaGetLastError();
-  d = true;
-}
-
 // ---- opt-in launch timing ---------------------------------------------------------------------------
 constexpr int kProfSlots = 512;
 struct ProfState {
@@ -65,8 +37,6 @@ struct ProfState {
   int n[PROF_KINDS];
 };
 static ProfState g_prof;
-
-bool pdl_enabled() { return pdl_setting() && !g_prof.on; }
 
 void prof_begin(int kind, cudaStream_t st) {
   if (!g_prof.on || g_prof.n[kind] >= kProfSlots) return;
@@ -370,12 +340,6 @@ int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision
 }
 
 unsigned long long vpa_launch_count(void) { return g_launches; }
-
-int vpa_launch_tuning(int programmatic_dependent_launch, int max_shared_carveout) {
-  if (programmatic_dependent_launch >= 0) g_pdl = programmatic_dependent_launch != 0;
-  if (max_shared_carveout >= 0) g_carveout = max_shared_carveout != 0;
-  return 0;
-}
 
 int vpa_profile_enable(int on) {
   g_prof.on = on != 0;
@@ -736,7 +700,6 @@ int vpa_p2p_create(int64_t rows_local, int world, int rank, int D, int precision
 }
 int vpa_p2p_connect(void* p2p, const void* all_ipc_handles) { return p2p_connect(p2p, all_ipc_handles); }
 int vpa_p2p_destroy(void* p2p) { return p2p_destroy(p2p); }
-int vpa_p2p_mode(void* p2p) { return p2p_mode(p2p); }
 // the relay CTAs' item -> (matrix, source rank, chunk, first row, rows) map, evaluated on the host (tests)
 int vpa_debug_relay_item(int item, int m0, int source_major, int world, int me, int chunks_per_rank, int64_t rows_local, int* out5) {
   VPA_CHECK_ARG(out5 && world >= 2 && me >= 0 && me < world && chunks_per_rank >= 1 && rows_local >= 1 && item >= 0 &&
@@ -745,9 +708,6 @@ int vpa_debug_relay_item(int item, int m0, int source_major, int world, int me, 
   out5[0] = it.m; out5[1] = it.src; out5[2] = it.c; out5[3] = it.row0; out5[4] = it.rows;
   return 0;
 }
-int vpa_p2p_nvls_export(void* p2p, int* fd_out) { return p2p_nvls_export(p2p, fd_out); }
-int vpa_p2p_nvls_attach(void* p2p, int fd) { return p2p_nvls_attach(p2p, fd); }
-int vpa_p2p_nvls_bind(void* p2p) { return p2p_nvls_bind(p2p); }
 
 int vpa_infonce_fwd_p2p(void* p2p, const void* x1, const void* x2, int in_dtype, int64_t b, int world, int rank, int D,
                         int64_t ld1, int64_t ld2, int already_normalized, const float* logit_scale, float scale_max,

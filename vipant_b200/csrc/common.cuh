@@ -42,39 +42,16 @@ enum { PROF_NORMALIZE = 0, PROF_FWD_SWEEP = 1, PROF_BWD_SWEEP = 2, PROF_SIM = 3,
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(int kind, cudaStream_t st);
 
-// ---- programmatic dependent launch ---------------------------------------------------------------
-// The kernels of one step run back to back on a stream; at 8 GPUs a step is ~0.6 ms of six kernels, so the few microseconds
-// between the end of one kernel and the first instruction of the next count.  With the launch attribute below a kernel may
-// be SCHEDULED while its predecessor still runs (as soon as every CTA of the predecessor has executed pdl_trigger());
-// its threads then block in pdl_wait() until the predecessor has completed and flushed its memory.  Every kernel of the
-// library calls pdl_wait() before it touches global memory, so the semantics stay those of plain stream order; only the
-// launch latency and the kernel prologue (barrier init, TMEM allocation, descriptor prefetch) overlap.
-bool pdl_enabled();      // api.cu (VPA_PDL=0 disables; also off while the launch-timing hooks record events between kernels)
-// The sweep kernels configure the SM for ~227 KB of shared memory; a kernel without shared memory that follows makes the SM
-// switch its L1 / shared-memory split back, and the next sweep switches it again.  With VPA_CARVEOUT=1 the small streaming
-// kernels ask for the same (maximum shared memory) split: they have no reuse for L1 to exploit.
-bool carveout_enabled();
-void apply_carveout(const void* kernel);
+// ---- kernel launch with a typed argument list (cudaLaunchKernelEx; cluster dimensions come from __cluster_dims__) ----------
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  if (smem == 0 && carveout_enabled()) apply_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  const bool pdl = pdl_enabled();
-  cfg.attrs = pdl ? attr : nullptr;
-  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-#ifdef __CUDACC__
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#endif
 
 // ---- device helpers ----------------------------------------------------------------------
 constexpr float kLog2e = 1.4426950408889634f;

@@ -236,10 +236,6 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const SmemLayout L = smem_layout<MODE>(P.kboxes);
   if (sbase - smem_u32(smem_raw) + L.total > kSmemLimit) asm volatile("trap;");     // alignment pad does not fit
-  pdl_trigger();
-  // nothing is read from global memory before the preceding kernel has completed (common.cuh); kernels without a gate or
-  // relay role run their prologue (barriers, tensor-memory allocation) first and wait further down
-  if (P.gate != 0 || ((MODE == MODE_FWD1 || MODE == MODE_BWD) && (int)blockIdx.x < P.relay.n_ctas)) pdl_wait();
   if ((MODE == MODE_FWD1 || MODE == MODE_BWD) && (int)blockIdx.x < P.relay.n_ctas) {
     // Relay CTAs: the all-gather of the operand rows over NVLink, in the same grid as the sweep that consumes them.  They
     // come first in blockIdx order, i.e. they are resident before any sweep CTA that polls their flags.  The forward
@@ -249,8 +245,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     if (blockIdx.x == 0) relay_signal_ready(P.relay);
     int m1 = P.relay.m1;
     if (MODE == MODE_FWD1 && fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e > kFastS2Limit) m1 = 2;
-    if (P.relay.multicast) relay_multicast(P.relay, m1, blockIdx.x);
-    else relay_pull(P.relay, m1, blockIdx.x, sptr);
+    relay_pull(P.relay, m1, blockIdx.x, sptr);
     return;
   }
   if (P.gate != 0) {       // regime gate on the DEVICE value of the temperature (no host sync): uniform over the grid
@@ -349,7 +344,6 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
 
   if (warp == 0) {
     // =========================== TMA producer (both CTAs; each fills ITS half of every operand) ===========================
@@ -382,17 +376,39 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     };
     TileOrder order = make_order();
     int tcur = order.first();
+    const bool polling = (MODE == MODE_FWD1 && P.yflags.flags != nullptr) || (MODE == MODE_BWD && prob == 1 && P.aflags.flags != nullptr);
+    int verified = 0;               // tiles, from the current one on, whose rows are known to have arrived
     for (int j = 0; j < nt; ++j, tcur = (j < nt) ? order.next() : tcur) {
       if (MODE == MODE_BWD) tcur = tile_at(j);
       const int r = tcur * kBN + (int)crank * 128;             // this CTA's half of the tile's Y rows
-      if ((MODE == MODE_FWD1 && P.yflags.flags != nullptr) || (MODE == MODE_BWD && prob == 1 && P.aflags.flags != nullptr)) {
-        // peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cuh).  Poll the
-        // chunk flags (system-scope acquire), then order the TMA (async proxy) reads after the observation.
-        if (elected) {
-          p2p_wait_rows(MODE == MODE_BWD ? P.aflags : P.yflags, r, min(r + 128, pb.n_y));
-          asm volatile("fence.proxy.async;" ::: "memory");
+      if (polling) {
+        // Peer-memory all-gather in flight: these rows may still be on their way from another GPU (p2p.cuh).  One poll
+        // (a system-scope acquire load: an L2 round trip) per tile would add ~0.5 us to every tile of the sweep, so the
+        // whole warp looks ahead: lane L tests the L-th upcoming tile, lane 0 waits for the current one, and the sweep does
+        // not poll again until it has used up the tiles found complete (the transfer normally runs well ahead of it).
+        if (verified == 0) {
+          const P2PRowFlags& fl = MODE == MODE_BWD ? P.aflags : P.yflags;
+          bool ok = false;
+          if (j + lane < nt) {
+            int t = tcur;
+            if (MODE == MODE_BWD) {
+              t = tile_at(j + lane);
+            } else {
+              TileOrder ahead = order;
+              for (int k = 0; k < lane; ++k) t = ahead.next();
+            }
+            const int rl = t * kBN + (int)crank * 128;
+            if (lane == 0) { p2p_wait_rows(fl, rl, min(rl + 128, pb.n_y)); ok = true; }
+            else ok = p2p_rows_ready(fl, rl, min(rl + 128, pb.n_y));
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, ok);
+          verified = __ffs(~mask) - 1;                          // consecutive complete tiles from the current one (>= 1)
+          if (verified < 0) verified = 32;
+          __syncwarp();                                         // the lanes' observations are ordered before ...
+          if (elected) asm volatile("fence.acq_rel.sys;\n\tfence.proxy.async;" ::: "memory");   // ... the TMA (async proxy) reads
+          __syncwarp();
         }
-        __syncwarp();
+        --verified;
       }
       for (int kb = 0; kb < P.kboxes; kb += 2) push(kb * kBoxK, (kb + 1) * kBoxK, r);
       if (MODE == MODE_BWD && j >= 1) push_dx(j - 1);

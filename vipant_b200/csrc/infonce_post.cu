@@ -9,8 +9,6 @@ namespace vpa {
 __global__ void __launch_bounds__(256)
 colsum_reduce_kernel(const float* __restrict__ colpart, int n_groups, int64_t B, float* __restrict__ colsum,
                      const float* __restrict__ logit_scale, float scale_cap, float s2_limit) {
-  pdl_trigger();
-  pdl_wait();
   if (fminf(expf(*logit_scale), scale_cap) * kLog2e > s2_limit) return;     // not the single-pass regime
   const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= B) return;
@@ -38,8 +36,6 @@ __global__ void combine_stats_kernel(const float2* __restrict__ part, int n_chun
                                      const float* __restrict__ colsum, float* __restrict__ row_lse,
                                      float* __restrict__ col_lse, float* __restrict__ diag,
                                      float* __restrict__ scale_out) {
-  pdl_trigger();
-  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float e = expf(*logit_scale);
   const float s = fminf(e, scale_cap);
@@ -105,7 +101,6 @@ __device__ __forceinline__ void pack_one(const PackArgs& A, int64_t idx, float s
   const int64_t slot = (int64_t)A.pv.rank * (B + 3 * b);
   auto put = [&](int64_t pos, float v) {
     if (!p2p) { A.msg[pos] = v; return; }
-    if (A.pv.mc) { mc_st_f32(reinterpret_cast<float*>(A.pv.mc + A.off_msgs) + slot + pos, v); return; }      // NVLS: one store, all ranks
     for (int q = 0; q < A.pv.world; ++q) reinterpret_cast<float*>(A.pv.base[q] + A.off_msgs)[slot + pos] = v;
   };
   if (idx < B) {
@@ -166,15 +161,11 @@ __device__ __forceinline__ void pack_publish(const PackArgs& A) {
     __threadfence();
   }
   __syncthreads();
-  if (last && A.pv.mc) {
-    if (threadIdx.x == 0) mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(A.pv.mc + A.off_msg_flags) + A.pv.rank, A.pv.epoch);
-  } else if (last && (int)threadIdx.x < A.pv.world) {      // one thread per destination: the release stores travel in parallel
+  if (last && (int)threadIdx.x < A.pv.world) {      // one thread per destination: the release stores travel in parallel
     st_release_sys_u32(reinterpret_cast<uint32_t*>(A.pv.base[threadIdx.x] + A.off_msg_flags) + A.pv.rank, A.pv.epoch);
   }
 }
 __global__ void pack_stats_kernel(const PackArgs A) {
-  pdl_trigger();
-  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float s = fminf(expf(*A.logit_scale), A.scale_cap);
   pack_one(A, idx, s, A.fast && s * kLog2e <= A.s2_limit);
@@ -249,8 +240,6 @@ __device__ __forceinline__ void merge_loss(const MergeArgs& A, double term) {
   }
 }
 __global__ void __launch_bounds__(256) merge_stats_kernel(const MergeArgs A) {
-  pdl_trigger();
-  pdl_wait();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float e = expf(*A.logit_scale);
   const float s = fminf(e, A.scale_cap);
@@ -268,8 +257,6 @@ __global__ void __launch_bounds__(256) merge_stats_kernel(const MergeArgs A) {
 // still has to write this rank's message off the machine.
 constexpr int kExchangeMaxBlocks = 2 * 148;
 __global__ void __launch_bounds__(256) exchange_stats_kernel(const PackArgs P, const MergeArgs A) {
-  pdl_trigger();
-  pdl_wait();
   const float e = expf(*A.logit_scale);
   const float s = fminf(e, A.scale_cap);
   const bool fastr = P.fast && s * kLog2e <= P.s2_limit;
@@ -339,9 +326,7 @@ loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse
 // of the R partials in rank order (bitwise identical on every rank).  Every rank's block stores before it waits: no cycle.
 static __device__ __noinline__ void dls_exchange(const P2PView& pv, size_t off_dls, float part_dls, float* dlogit_scale) {
   const unsigned long long w = ((unsigned long long)pv.epoch << 32) | (unsigned long long)__float_as_uint(part_dls);
-  if (pv.mc) {
-    if (threadIdx.x == 0) mc_st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.mc + off_dls) + pv.rank, w);
-  } else if ((int)threadIdx.x < pv.world) {    // one thread per destination
+  if ((int)threadIdx.x < pv.world) {           // one thread per destination
     st_release_sys_u64(reinterpret_cast<unsigned long long*>(pv.base[threadIdx.x] + off_dls) + pv.rank, w);
   }
   if (threadIdx.x < 32) {
@@ -375,8 +360,6 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
                     void* __restrict__ dx1, void* __restrict__ dx2,
                     const float* __restrict__ dscale_part, int n_dscale, float* __restrict__ dlogit_scale,
                     const P2PView pv, size_t off_dls, int dls_sum) {
-  pdl_trigger();
-  pdl_wait();
   const float s = scale[0], g = grad_out[0];
   const int lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * kFinWarps + (threadIdx.x >> 5);   // (problem, row)

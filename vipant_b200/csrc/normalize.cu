@@ -86,8 +86,6 @@ normalize_pair_kernel(const void* __restrict__ x1, const void* __restrict__ x2, 
                       float* __restrict__ a_f32, float* __restrict__ t_f32,
                       float* __restrict__ inv1, float* __restrict__ inv2,
                       float* __restrict__ diag_cos, int diag_from_bf16) {
-  pdl_trigger();
-  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
   if (row >= rows) return;

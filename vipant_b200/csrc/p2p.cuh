@@ -14,26 +14,9 @@ constexpr int kPushRows = 256;        // flag granularity of the operand push ==
 
 struct P2PView {
   char* base[kMaxPeers];              // base[rank] is the local segment
-  char* mc;                           // NVLS transport: multicast mapping of the segment (a store lands in EVERY rank's
-                                      // copy at the same offset, replicated by the NVSwitch); nullptr otherwise
   int rank, world;
   uint32_t epoch;                     // step number (monotonic, starts at 1); flags carry the epoch of the data they publish
 };
-
-// stores to a multicast address (multimem.st: one store, every replica)
-__device__ __forceinline__ void mc_st_f32(float* p, float v) {
-  asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-__device__ __forceinline__ void mc_st_v4(uint4* p, uint4 v) {
-  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)),
-               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
-}
-__device__ __forceinline__ void mc_st_release_sys_u32(uint32_t* p, uint32_t v) {
-  asm volatile("multimem.st.release.sys.global.f32 [%0], %1;" ::"l"(p), "f"(__uint_as_float(v)) : "memory");
-}
-__device__ __forceinline__ void mc_st_release_sys_u64(unsigned long long* p, unsigned long long v) {      // one 8-byte element
-  asm volatile("multimem.st.release.sys.global.f64 [%0], %1;" ::"l"(p), "d"(__longlong_as_double((long long)v)) : "memory");
-}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
@@ -92,16 +75,29 @@ __device__ __forceinline__ void p2p_wait_rows(const P2PRowFlags& f, int r0, int 
   }
 }
 
+// the same test without waiting: are global rows [r0, r1) of the gathered matrix complete?
+__device__ __forceinline__ bool p2p_rows_ready(const P2PRowFlags& f, int r0, int r1) {
+  int row = r0;
+  while (row < r1) {
+    const int src = row / f.rows_per_rank;
+    const int off = row - src * f.rows_per_rank;
+    const int c = off / kPushRows;
+    if (src != f.me && (int32_t)(ld_acquire_sys_u32(f.flags + src * f.chunks_per_rank + c) - f.epoch) < 0) return false;
+    row = src * f.rows_per_rank + min(f.rows_per_rank, (c + 1) * kPushRows);
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------- operand relay (the all-gather of the row-sharded step)
 // The gathered operand matrices are filled by RELAY CTAs: whole CTAs that do nothing but move rows, driven by one thread
 // and the TMA engine.  They run as the first CTAs of the single-pass forward's grid (infonce_pair.cu: one kernel does the
 // all-gather and the contraction; CTAs are dispatched in blockIdx order, so the relays are resident before any sweep CTA
 // that polls their flags) or as a kernel of their own for the shapes the CTA-pair sweeps do not cover.
-//   pull (default)  cp.async.bulk peer-global -> shared-memory ring -> cp.async.bulk local-global: up to kRelaySlots x 32 KB
-//                   of NVLink reads in flight per CTA (an LDG copy loop holds ~32 KB per CTA and measured 260-360 GB/s at
-//                   8 GPUs); one local arrival flag per 256-row chunk once its stores have completed.
-//   multicast       (NVLS segment) every rank stores its OWN rows once through the multicast mapping; the NVSwitch
-//                   replicates them to all ranks: 1/(R-1) of the egress.  Flags travel the same way.
+// A relay pulls: cp.async.bulk peer-global -> shared-memory ring -> cp.async.bulk local-global, up to kRelaySlots x 32 KB of
+// NVLink reads in flight per CTA; one local arrival flag per 256-row chunk once its stores have completed.  (Measured at
+// 8 GPUs, all pulling from all: 12 / 20 / 28 relay CTAs move 243 / 305 / 335 GB/s into one GPU.  An NVSwitch-multicast
+// variant -- every rank storing its own rows once with multimem.st -- was brought up and measured the same or slower
+// (profiles/r02_scaling.md) and was removed, as were the LDG pull / push kernels and the copy-engine variant of round 1.)
 // Items are ordered matrix-major (x2 operands first: the forward needs only them), then chunk-major over the peers, so
 // the early chunks of every peer block land first -- the order in which the sweep visits its tiles.
 struct RelayArgs {
@@ -110,7 +106,6 @@ struct RelayArgs {
   int64_t b;                                       // rows per rank
   int row_bytes, cpr;                              // bytes per operand row; 256-row chunks per rank block
   int n_ctas;                                      // relay CTAs (0: no relay)
-  int multicast;                                   // 1: NVLS stores of the own block instead of pulls
   int m0, m1;                                      // matrices [m0, m1) to move
   int source_major;                                // item order: 0 chunk-major over the peers, 1 peer after peer (me+1, me+2, ...)
   int signal_ready;                                // 1: this launch announces "my rows of this step are complete" to the peers
@@ -167,7 +162,6 @@ __device__ __forceinline__ void relay_signal_ready(const RelayArgs& A) {
   const int q = threadIdx.x;
   if (A.signal_ready && q < A.v.world && q != A.v.rank) {
     __threadfence_system();
-    if (A.multicast) return;                       // multicast mode: nobody pulls
     st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.base[q] + A.off_ready) + A.v.rank, A.v.epoch);
   }
 }
@@ -259,42 +253,6 @@ __device__ __forceinline__ void relay_pull(const RelayArgs& A, int m1, int cta, 
   }
 }
 
-// Multicast role (NVLS segment): chunks of THIS rank's block, all threads of the CTA storing through the multicast mapping.
-__device__ __forceinline__ void relay_multicast(const RelayArgs& A, int m1, int cta) {
-  const int me = A.v.rank;
-  char* mine = A.v.base[me];
-  const int total = (m1 - A.m0) * A.cpr;
-  const int nthr = blockDim.x;
-  for (int item = cta; item < total; item += A.n_ctas) {
-    const int m = A.m0 + item / A.cpr, c = item % A.cpr;
-    // already published in this step (the multicast flag store also lands in this rank's own copy)?  CTA-uniform.
-    if ((int32_t)(ld_acquire_sys_u32(reinterpret_cast<const uint32_t*>(mine + A.off_flags[m]) + me * A.cpr + c) - A.v.epoch) >= 0) continue;
-    const int64_t row0 = (int64_t)c * kPushRows;
-    const int rows = (int)min((int64_t)kPushRows, A.b - row0);
-    const int n16 = rows * (A.row_bytes / 16);
-    const size_t off = A.off_mat[m] + ((size_t)me * A.b + row0) * A.row_bytes;
-    const uint4* from = reinterpret_cast<const uint4*>(mine + off);
-    uint4* to = reinterpret_cast<uint4*>(A.v.mc + off);
-    constexpr int kU = 8;
-    for (int i = threadIdx.x; i < n16; i += nthr * kU) {
-      uint4 val[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int idx = i + u * nthr;
-        if (idx < n16) val[u] = __ldg(from + idx);
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int idx = i + u * nthr;
-        if (idx < n16) mc_st_v4(to + idx, val[u]);
-      }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0)
-      mc_st_release_sys_u32(reinterpret_cast<uint32_t*>(A.v.mc + A.off_flags[m]) + me * A.cpr + c, A.v.epoch);
-  }
-}
 #endif  // __CUDACC__
 
 // Host-side description of one step's buffers inside the local segment (p2p.cu::p2p_step) + what kernels need to reach
@@ -326,9 +284,5 @@ int p2p_relay_standalone(void* handle, uint32_t epoch, int m0, bool signal_ready
 int p2p_relay_ctas(void* handle);
 uint32_t p2p_a_pending(void* handle);
 void p2p_set_a_pending(void* handle, uint32_t epoch);
-int p2p_mode(void* handle);
-int p2p_nvls_export(void* handle, int* fd_out);
-int p2p_nvls_attach(void* handle, int fd);
-int p2p_nvls_bind(void* handle);
 
 }  // namespace vpa

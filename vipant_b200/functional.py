@@ -361,9 +361,7 @@ def _get_p2p(group, b, D, precision, dev, seg_key=None):
     everyone = [None] * world
     dist.all_gather_object(everyone, (rc, bytes(mine.raw), os.getpid()), group=group)
     ok = all(r == 0 for r, _, _ in everyone)
-    if ok and lib.vpa_p2p_mode(handle) == 4:
-        rc, err = _nvls_setup(lib, handle, rank, world, everyone[0][2], group)
-    elif ok:
+    if ok:
         rc = lib.vpa_p2p_connect(handle, b"".join(h for _, h, _ in everyone))
         err = "" if rc == 0 else (lib.vpa_last_error_string() or b"").decode()
     status = [None] * world
@@ -386,68 +384,6 @@ def _get_p2p(group, b, D, precision, dev, seg_key=None):
 
 
 _P2P_ATEXIT = []
-
-
-def _share_fd_from_rank0(rank, world, fd, name, group):
-    """Rank 0 hands the open file descriptor `fd` (or None: "nothing to share") to every other rank's process over an abstract
-    UNIX socket `name` (SCM_RIGHTS).  Returns the received descriptor on the other ranks (None if rank 0 had none), `fd` on 0."""
-    import socket
-    import time
-    if rank == 0:
-        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        srv.bind(name)
-        srv.listen(world)
-    dist.barrier(group=group)                      # the socket exists
-    if rank == 0:
-        srv.settimeout(30.0)
-        for _ in range(world - 1):
-            conn, _ = srv.accept()
-            if fd is not None:
-                socket.send_fds(conn, [b"fd"], [fd])
-            else:
-                conn.sendall(b"no")
-            conn.close()
-        srv.close()
-        return fd
-    cli = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    cli.settimeout(30.0)
-    for attempt in range(200):
-        try:
-            cli.connect(name)
-            break
-        except OSError:
-            if attempt == 199:
-                raise
-            time.sleep(0.05)
-    _, fds, _, _ = socket.recv_fds(cli, 16, 1)
-    cli.close()
-    return fds[0] if fds else None
-
-
-def _nvls_setup(lib, handle, rank, world, pid0, group):
-    """EXPERIMENTAL NVLS transport: rank 0 creates the multicast object and passes its file descriptor to every other rank's
-    process; all attach their device, agree, then bind their memory and map the multicast view."""
-    def err():
-        return (lib.vpa_last_error_string() or b"").decode()
-    fd = ctypes.c_int(-1)
-    rc = lib.vpa_p2p_nvls_export(handle, ctypes.byref(fd)) if rank == 0 else 0
-    # (the socket name must be the same string in every process: rank 0's pid + the number of segments set up so far)
-    got = _share_fd_from_rank0(rank, world, fd.value if (rank == 0 and rc == 0) else None,
-                               f"\0vipant-b200-nvls-{pid0}-{len(_P2P)}", group)
-    if rank == 0:
-        if rc == 0:
-            os.close(fd.value)
-            rc = lib.vpa_p2p_nvls_attach(handle, -1)
-    else:
-        rc = lib.vpa_p2p_nvls_attach(handle, got) if got is not None else 1      # (the library closes the descriptor)
-    flags = [None] * world
-    dist.all_gather_object(flags, rc, group=group)      # every device is in the multicast team (or someone failed)
-    if any(flags):
-        return 1, err()
-    rc = lib.vpa_p2p_nvls_bind(handle)
-    if rc == 0:
-        rc = lib.vpa_p2p_connect(handle, None)
-    return rc, ("" if rc == 0 else err())
 
 
 def _destroy_p2p():

@@ -112,7 +112,8 @@ static int sm_count() {      // of the CURRENT device (a process may drive sever
 // Relay CTAs of the peer-memory transport (whole CTA pairs in front of a sweep kernel's grid, p2p.cuh).  The forward cannot
 // finish before its x2 operands have arrived, so it gives the transfer 20 SMs (measured at 8 GPUs: 12 / 20 / 28 relay CTAs
 // move 243 / 305 / 335 GB/s into one GPU; the sweep wants the other SMs).  The backward runs 3-4x longer than the transfer
-// of its x1 operands and consumes them at <= 75 GB/s: 4 relay CTAs keep ahead of it.
+// of its x1 operands and consumes them at <= 75 GB/s: 8 relay CTAs keep ahead of it (measured at 8 GPUs: backward sweep
+// 0.623 / 0.405 / 0.389 ms with 2 / 4 / 8 relay CTAs; 0.364 ms without any exchange).
 int relay_ctas_default() {
   static int v = 0;
   if (v == 0) {
@@ -124,7 +125,7 @@ int relay_ctas_default() {
 int relay_ctas_bwd_default() {
   static int v = 0;
   if (v == 0) {
-    v = 4;
+    v = 8;
     if (const char* e = getenv("VPA_P2P_RELAY_CTAS_BWD")) { const int q = atoi(e); if (q >= 2 && q <= 64) v = q & ~1; }   // tuning knob
   }
   return v;
@@ -236,7 +237,7 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
     // per-unit fixed cost (prologue, X load, pipeline fill, dX drain) measured at ~3.5 tiles of 256 columns (b=4096 sweep)
     {
       // backward over peer memory: relay CTA pairs hold their SMs until the peers' x1 operands are in -- in tile times of
-      // this kernel: bytes / (measured per-CTA pull rate ~25 GB/s with few relays) / (time of one 128 x 256 tile pair of MMAs)
+      // this kernel: bytes / (per-CTA pull rate, ~25 GB/s with few relays) / (time of one 128 x 256 tile pair of MMAs)
       const int bwd_relay = reserved_sms > 0 ? relay_ctas_bwd_default() : 0;
       const double bytes = (double)(rows_global - rows_local) * D * 2.0;
       const double tile_us = 4.0 * 128.0 * 256.0 * D / (1.45e15 / (sm_count() / 2)) * 1e6;

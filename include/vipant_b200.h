@@ -206,6 +206,30 @@ int vpa_multilabel_scores(const float* S, int64_t ld_s, const void* Y, int y_dty
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Several InfoNCE pairs over shared modalities in ONE step: the composite heads of the reference run up to five
+ * CELossHead pairs per training step on two to five feature matrices (VALCELossHead va / lv / al, loss_head.py:421-495;
+ * VACELossHead vp / ap / va / vv / aa, :497-598).  Here every modality is normalised once, the single-pass forwards of all
+ * pairs are one launch, the backward sweeps of all pairs are one launch, and the gradient of a modality that takes part in
+ * several pairs is summed before its normalisation Jacobian is applied once: 8 launches instead of 7 per pair.
+ *   x[m], ld[m]: n_mod <= 5 feature matrices (rows, D) of dtype in_dtype; pair p = (x[pair_x[p]], x[pair_y[p]]), n_pairs <= 5,
+ *   with its own temperature logit_scale[p] (device pointers) and clamp scale_max[p] (host floats; <= 0: none).
+ *   loss_out[p]: the pair's loss (loss_head.py:280-283).  grad_out[p] (device): dL/d loss_p -- the pair weights of
+ *   VACELossHead and the AMP loss scale go here.  dx[m]: gradient of modality m summed over its pairs; dlogit_scale[p].
+ * Tensor-core path only (precision VPA_PREC_BF16_TC, D in {256, 512}), rows <= 8192, one GPU; other shapes return
+ * VPA_E_UNSUPPORTED and the caller runs the pairs one by one.
+ * ------------------------------------------------------------------------------------------ */
+#define VPA_MAX_PAIRS 5
+size_t vpa_infonce_multi_state_bytes(int64_t rows, int D, int n_mod, int n_pairs, int precision);
+int vpa_infonce_multi_fwd(const void* const* x, const int64_t* ld, int in_dtype, int64_t rows, int D, int n_mod,
+                          int already_normalized, const int32_t* pair_x, const int32_t* pair_y, int n_pairs,
+                          const float* const* logit_scale, const float* scale_max, int precision, void* state,
+                          size_t state_bytes, float* loss_out, void* stream);
+int vpa_infonce_multi_bwd(const void* const* x, const int64_t* ld, int in_dtype, int64_t rows, int D, int n_mod,
+                          int already_normalized, const int32_t* pair_x, const int32_t* pair_y, int n_pairs, int precision,
+                          const float* grad_out, void* state, size_t state_bytes, void* const* dx, float* dlogit_scale,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Row-sharded training step, orchestrated inside the library: TWO calls per step (forward, backward) instead of a
  * dozen host-side launches and five framework collectives -- at 8 GPUs the step is ~0.6 ms of kernels, so host
  * enqueue time decides the scaling.  One process per GPU; rank r owns rows [r*b, (r+1)*b) of the global batch

@@ -5,7 +5,7 @@ Host side: Python mirror of the reference's loss-head API (``loss_head``), tenso
 ``embed_cache``: packed shards of pre-computed embeddings (the on-disk format either side of the path).
 """
 from . import embed_cache  # noqa: F401
-from .functional import infonce_loss, l2_normalize, sim_rank_fused, sim_rank_topk, tensor_core_supported  # noqa: F401
+from .functional import infonce_loss, infonce_multi_loss, l2_normalize, sim_rank_fused, sim_rank_topk, tensor_core_supported  # noqa: F401
 from .loss_more import BCELossHead, multilabel_scores  # noqa: F401
 from .loss_head import (  # noqa: F401
     LOSS_HEADS_REGISTRY,

@@ -38,6 +38,11 @@ _SIGNATURES = {
     "vpa_infonce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int64,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
                                 c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vpa_infonce_multi_state_bytes": (c_size_t, [c_int64, c_int, c_int, c_int, c_int]),
+    "vpa_infonce_multi_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "vpa_infonce_multi_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                      c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "vpa_comm_load": (c_int, [c_char_p]),
     "vpa_comm_unique_id": (c_int, [c_void_p]),
     "vpa_comm_init": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p)]),

@@ -547,6 +547,159 @@ int vpa_multilabel_scores(const float* S, int64_t ld_s, const void* Y, int y_dty
                                   workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+// ---- several InfoNCE pairs over shared modalities in one set of launches (composite heads) ---------------------------
+static bool pack_reduces_columns(const SweepPlan& plan, int precision);
+struct MultiState {
+  void* op[kMaxPairs];            // (rows, D) bf16 operands per modality
+  float* inv[kMaxPairs];          // (rows,)
+  float* dcos[kMaxPairs];         // per pair
+  float* msg[kMaxPairs];          // per pair (4 rows)
+  float* stats_all[kMaxPairs];    // per pair (3 rows)
+  float* scale[kMaxPairs];        // per pair {s, flows}
+  double* loss_part[kMaxPairs];
+  uint32_t* loss_counter[kMaxPairs];
+  void* ws[kMaxPairs];
+  size_t ws_bytes, bytes;
+};
+static MultiState carve_multi(void* base, int64_t rows, int D, int n_mod, int n_pairs, int precision) {
+  MultiState h{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o += align_up(bytes, 256);
+    return p;
+  };
+  for (int p = 0; p < n_pairs; ++p) h.loss_counter[p] = (uint32_t*)take(4);      // (first: one memset clears them all)
+  for (int m = 0; m < n_mod; ++m) { h.op[m] = take((size_t)rows * D * 2); h.inv[m] = (float*)take(rows * 4); }
+  h.ws_bytes = infonce_workspace_bytes(rows, rows, D, precision, 0);
+  for (int p = 0; p < n_pairs; ++p) {
+    h.dcos[p] = (float*)take(rows * 4);
+    h.msg[p] = (float*)take((size_t)4 * rows * 4);
+    h.stats_all[p] = (float*)take((size_t)3 * rows * 4);
+    h.scale[p] = (float*)take(16);
+    h.loss_part[p] = (double*)take((size_t)((rows + 255) / 256) * 8);
+    h.ws[p] = take(h.ws_bytes);
+  }
+  h.bytes = o;
+  return h;
+}
+static int check_multi(int64_t rows, int D, int n_mod, const int32_t* pair_x, const int32_t* pair_y, int n_pairs, int precision) {
+  VPA_CHECK_ARG(n_mod >= 1 && n_mod <= kMaxPairs && n_pairs >= 1 && n_pairs <= kMaxPairs && pair_x && pair_y,
+                "infonce_multi: 1..%d modalities and pairs", kMaxPairs);
+  for (int p = 0; p < n_pairs; ++p)
+    VPA_CHECK_ARG(pair_x[p] >= 0 && pair_x[p] < n_mod && pair_y[p] >= 0 && pair_y[p] < n_mod, "infonce_multi: pair %d names a modality outside [0, %d)", p, n_mod);
+  if (int e = check_infonce_shape(rows, rows, D, 0, precision)) return e;
+  if (precision != VPA_PREC_BF16_TC || !(D == 256 || D == 512))
+    return set_error(VPA_E_UNSUPPORTED, "infonce_multi: the fused multi-pair step covers the tensor-core path with D in {256, 512}");
+  const SweepPlan plan = plan_sweep(rows, rows, D, precision);
+  if (!pack_reduces_columns(plan, precision))
+    return set_error(VPA_E_UNSUPPORTED, "infonce_multi: at most 8192 rows (larger batches gain nothing from sharing launches)");
+  return 0;
+}
+
+size_t vpa_infonce_multi_state_bytes(int64_t rows, int D, int n_mod, int n_pairs, int precision) {
+  if (rows <= 0 || D <= 0 || n_mod < 1 || n_mod > kMaxPairs || n_pairs < 1 || n_pairs > kMaxPairs) return 0;
+  return carve_multi(nullptr, rows, D, n_mod, n_pairs, precision).bytes;
+}
+
+int vpa_infonce_multi_fwd(const void* const* x, const int64_t* ld, int in_dtype, int64_t rows, int D, int n_mod,
+                          int already_normalized, const int32_t* pair_x, const int32_t* pair_y, int n_pairs,
+                          const float* const* logit_scale, const float* scale_max, int precision, void* state,
+                          size_t state_bytes, float* loss_out, void* stream) {
+  if (int e = check_multi(rows, D, n_mod, pair_x, pair_y, n_pairs, precision)) return e;
+  VPA_CHECK_ARG(x && ld && logit_scale && scale_max && state && loss_out, "infonce_multi_fwd: null pointer");
+  const MultiState h = carve_multi(state, rows, D, n_mod, n_pairs, precision);
+  if (h.bytes > state_bytes) return set_error(VPA_E_WORKSPACE, "infonce_multi_fwd: state %zu < %zu", state_bytes, h.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SweepPlan plan = plan_sweep(rows, rows, D, precision);
+  // every modality is normalised once, whatever number of pairs it takes part in
+  if (int e = normalize_multi_launch(x, ld, in_dtype, rows, D, n_mod, already_normalized, h.op, h.inv, st)) return e;
+  const void* a_ptr[kMaxPairs];
+  const void* t_ptr[kMaxPairs];
+  float cap[kMaxPairs];
+  Workspace ws[kMaxPairs];
+  for (int p = 0; p < n_pairs; ++p) {
+    VPA_CHECK_ARG(logit_scale[p] != nullptr, "infonce_multi_fwd: null logit_scale of pair %d", p);
+    a_ptr[p] = h.op[pair_x[p]];
+    t_ptr[p] = h.op[pair_y[p]];
+    cap[p] = (scale_max[p] > 0.f) ? scale_max[p] : INFINITY;
+    ws[p] = carve_workspace(h.ws[p], rows, rows, D, plan);
+  }
+  if (int e = diag_cos_multi_launch(a_ptr, t_ptr, h.dcos, n_pairs, rows, D, st)) return e;
+  VPA_CUDA(cudaMemsetAsync(h.loss_counter[0], 0, (size_t)n_pairs * 256, st));
+  // single-pass forward of all pairs in one launch (each pair gates itself on the device value of ITS temperature) ...
+  PairLaunch L{};
+  L.rows_local = L.rows_global = rows; L.row_offset = 0; L.D = D;
+  L.n_prob = n_pairs;
+  for (int p = 0; p < n_pairs; ++p) {
+    L.p[p].x = a_ptr[p]; L.p[p].y = t_ptr[p];
+    L.p[p].out = ws[p].fwd_part; L.p[p].colpart = ws[p].colpart;
+    L.p[p].logit_scale = logit_scale[p]; L.p[p].scale_cap = cap[p];
+  }
+  if (int e = pair_launch_fwd1(L, plan, st)) return e;
+  // ... and the exact two-sweep kernel for the pairs in the other regime
+  PairLaunch X{};
+  X.rows_local = X.rows_global = rows; X.row_offset = 0; X.D = D;
+  X.n_prob = 2 * n_pairs;
+  for (int p = 0; p < n_pairs; ++p)
+    for (int d = 0; d < 2; ++d) {
+      PairProblem& q = X.p[2 * p + d];
+      q.x = d ? t_ptr[p] : a_ptr[p]; q.y = d ? a_ptr[p] : t_ptr[p];
+      q.out = ws[p].fwd_part + (int64_t)d * plan.fwd_chunks * rows * 2;
+      q.logit_scale = logit_scale[p]; q.scale_cap = cap[p];
+    }
+  if (int e = pair_launch_fwd(X, plan, 2, st)) return e;
+  return pack_merge_multi_launch(n_pairs, ws, plan, rows, logit_scale, cap, h.dcos, h.msg, h.stats_all, h.scale, h.loss_part,
+                                 h.loss_counter, loss_out, st);
+}
+
+int vpa_infonce_multi_bwd(const void* const* x, const int64_t* ld, int in_dtype, int64_t rows, int D, int n_mod,
+                          int already_normalized, const int32_t* pair_x, const int32_t* pair_y, int n_pairs, int precision,
+                          const float* grad_out, void* state, size_t state_bytes, void* const* dx, float* dlogit_scale,
+                          void* stream) {
+  if (int e = check_multi(rows, D, n_mod, pair_x, pair_y, n_pairs, precision)) return e;
+  VPA_CHECK_ARG(ld && grad_out && state && dx && dlogit_scale && (already_normalized || x), "infonce_multi_bwd: null pointer");
+  VPA_CHECK_ARG(in_dtype == VPA_F32 || in_dtype == VPA_BF16 || in_dtype == VPA_F16, "infonce_multi_bwd: bad dtype");
+  const MultiState h = carve_multi(state, rows, D, n_mod, n_pairs, precision);
+  if (h.bytes > state_bytes) return set_error(VPA_E_WORKSPACE, "infonce_multi_bwd: state %zu < %zu", state_bytes, h.bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SweepPlan plan = plan_sweep(rows, rows, D, precision);
+  Workspace ws[kMaxPairs];
+  PairLaunch L{};
+  L.rows_local = L.rows_global = rows; L.row_offset = 0; L.D = D;
+  L.n_prob = 2 * n_pairs;
+  FinMultiHost f{};
+  f.n_mod = n_mod; f.n_pairs = n_pairs; f.n_chunks = plan.bwd_chunks; f.D = D; f.already = already_normalized;
+  f.n_dscale = plan.n_dscale; f.in_dtype = in_dtype; f.rows = rows;
+  for (int m = 0; m < n_mod; ++m) {
+    VPA_CHECK_ARG(dx[m] != nullptr && ld[m] >= D && ld[m] % 4 == 0, "infonce_multi_bwd: bad gradient buffer / leading dimension of modality %d", m);
+    f.x[m] = x ? x[m] : nullptr; f.dx[m] = dx[m]; f.ld[m] = ld[m]; f.inv[m] = h.inv[m];
+  }
+  for (int p = 0; p < n_pairs; ++p) {
+    ws[p] = carve_workspace(h.ws[p], rows, rows, D, plan);
+    const float* row_lse = h.stats_all[p];
+    const float* col_lse = h.stats_all[p] + rows;
+    for (int d = 0; d < 2; ++d) {
+      PairProblem& q = L.p[2 * p + d];
+      const int mx = d ? pair_y[p] : pair_x[p], my = d ? pair_x[p] : pair_y[p];
+      q.x = h.op[mx]; q.y = h.op[my];
+      q.lse_x = d ? col_lse : row_lse; q.lse_y = d ? row_lse : col_lse;
+      q.out = ws[p].bwd_part + (int64_t)d * plan.bwd_chunks * rows * D;
+      q.dscale = d == 0 ? ws[p].dscale_part : nullptr;
+      q.scale = h.scale[p];
+      f.part[mx][f.n_src[mx]] = q.out;
+      f.src_pair[mx][f.n_src[mx]] = p;
+      ++f.n_src[mx];
+    }
+    f.scale[p] = h.scale[p];
+    f.dscale_part[p] = ws[p].dscale_part;
+  }
+  f.grad_out = grad_out;
+  f.dlogit_scale = dlogit_scale;
+  if (int e = pair_launch_bwd(L, plan, st)) return e;
+  return finalize_multi_launch(f, st);
+}
+
 // ---- row-sharded step orchestrated in the library (two calls per training step) ------------------------------------
 struct ShardState {
   void *a_all, *t_all;          // (B, D) operands: bf16 (tensor-core mode) or fp32; this rank's rows are written in place

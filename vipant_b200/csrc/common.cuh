@@ -204,6 +204,59 @@ struct SweepArgs {
   const struct RelayArgs* relay;   // single-pass forward / backward over peer memory: relay CTAs in front of the grid (p2p.cuh)
 };
 
+// The CTA-pair kernels sweep up to kMaxPairs InfoNCE pairs (2 * kMaxPairs problems) in ONE launch: the pairs of a composite
+// head (VALCELossHead: va / lv / al, VACELossHead: vp / ap / va / vv / aa) share their operand matrices and their launches.
+constexpr int kMaxPairs = 5;
+struct PairProblem {           // one direction of one pair: X rows (local) swept against Y rows (global), both bf16
+  const void* x;
+  const void* y;
+  const float* lse_x;          // backward: lse of the X rows' direction, GLOBAL vector
+  const float* lse_y;          // backward: lse of the other direction
+  float* out;                  // forward: float2 partials; backward: fp32 dX partials
+  float* dscale;               // backward, first direction of a pair: partial sums of G * cos (nullptr otherwise)
+  const float* logit_scale;    // forward
+  float scale_cap;
+  const float* scale;          // backward: {s, flows} of the pair
+  float* colpart;              // single-pass forward: column sums per 32-row group
+};
+struct PairLaunch {
+  PairProblem p[2 * kMaxPairs];
+  int n_prob;
+  int64_t rows_local, rows_global, row_offset;
+  int D;
+  P2PRowFlags yflags, aflags;  // peer-memory transport (single pair only)
+  const struct RelayArgs* relay;
+};
+int pair_launch_fwd1(const PairLaunch& L, const SweepPlan& plan, cudaStream_t st);              // single-pass, device-gated
+int pair_launch_fwd(const PairLaunch& L, const SweepPlan& plan, int gate, cudaStream_t st);     // exact two-sweep
+int pair_launch_bwd(const PairLaunch& L, const SweepPlan& plan, cudaStream_t st);
+
+// host-side description of the multi-pair finalisation (infonce_post.cu)
+struct FinMultiHost {
+  int n_mod, n_pairs, n_chunks, D, already, n_dscale, in_dtype;
+  int64_t rows;
+  const void* x[kMaxPairs];
+  void* dx[kMaxPairs];
+  int64_t ld[kMaxPairs];
+  const float* inv[kMaxPairs];
+  int n_src[kMaxPairs];
+  const float* part[kMaxPairs][2 * kMaxPairs];
+  int src_pair[kMaxPairs][2 * kMaxPairs];
+  const float* scale[kMaxPairs];
+  const float* grad_out;
+  const float* dscale_part[kMaxPairs];
+  float* dlogit_scale;
+};
+int finalize_multi_launch(const FinMultiHost& h, cudaStream_t st);
+int pack_merge_multi_launch(int n_pairs, const Workspace* ws, const SweepPlan& plan, int64_t rows, const float* const* logit_scale,
+                            const float* scale_cap, const float* const* diag_cos, float* const* msg, float* const* stats_all,
+                            float* const* scale_out, double* const* loss_part, uint32_t* const* loss_counter, float* loss_out,
+                            cudaStream_t st);
+int normalize_multi_launch(const void* const* x, const int64_t* ld, int in_dtype, int64_t rows, int D, int n, int already,
+                           void* const* y_bf16, float* const* inv, cudaStream_t st);
+int diag_cos_multi_launch(const void* const* a_bf16, const void* const* t_bf16, float* const* out, int n, int64_t rows, int D,
+                          cudaStream_t st);
+
 int tc_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int tc_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st);
 int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int which, cudaStream_t st);

@@ -39,30 +39,38 @@ constexpr uint32_t kSmemLimit = 232448;
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FWD1 = 2 };
 constexpr float kFastS2Limit = 62.0f;     // single-pass forward valid while 2*s*log2(e) stays inside the fp32 exponent range
 
+constexpr int kMaxProblems = 2 * kMaxPairs;   // every InfoNCE pair is swept in both directions
+constexpr int kMaxMaps = 2 * kMaxPairs;       // distinct (matrix, box height) tensor maps of one launch
+
 struct Problem {
   int n_x, n_y;
   int diag_offset;
+  int mapx, mapy;           // tensor maps of the X rows (box = rows per CTA) and the Y rows (box = 128)
   const float* lse_x;
   const float* lse_y;
   float* out;               // FWD: float2[n_chunks][n_x]; BWD: float[n_chunks][n_x][D]
-  float* dscale;            // BWD problem 0: one partial per CTA; nullptr otherwise
+  float* dscale;            // BWD, first direction of a pair: one partial per CTA; nullptr otherwise
+  const float* logit_scale; // FWD: s = min(exp(*logit_scale), scale_cap) -- every pair has its own temperature
+  float scale_cap;
+  const float* scale;       // BWD: {s, flows} as written by the forward
+  float* colpart;           // FWD1: float[n_iblk*8][n_y] column sums of exp2(S*s2 - s2) per 32-row group
+};
+
+struct TensorMaps {
+  CUtensorMap m[kMaxMaps];
 };
 
 struct Params {
-  Problem p[2];
+  Problem p[kMaxProblems];
   int pairs_per_problem;    // n_iblk * n_chunks
   int n_iblk, n_chunks, tiles_per_chunk, n_tiles;
   // Every X row block is swept by n_big equal chunks of tiles_per_chunk tiles plus (small_tiles > 0) one short tail chunk.
-  // All big units come first in the grid (both problems), the tails last: CTAs are dispatched in blockIdx order to the
+  // All big units come first in the grid (all problems), the tails last: CTAs are dispatched in blockIdx order to the
   // first free SM pair, so the tails fill the slots a single wave of big units leaves idle (LPT scheduling; api.cu).
   int n_big, small_tiles, n_prob;
   int D, kboxes, nblk;      // kboxes = D / 64; nblk = D / 256 accumulator blocks (BWD)
-  const float* logit_scale;
-  float scale_cap;
-  const float* scale;
   float inv_B, ln_B;
-  int gate;                 // 0: always run; 1: run only if s*log2e <= kFastS2Limit; 2: run only if it is larger
-  float* colpart;           // FWD1: float[n_iblk*8][n_y] column sums of exp2(S*s2 - s2) per 32-row group
+  int gate;                 // 0: always run; 1: run only if s*log2e <= kFastS2Limit; 2: run only if it is larger (per problem)
   P2PRowFlags yflags;       // FWD1 over peer memory: arrival flags of the Y rows (nullptr: everything is already there)
   P2PRowFlags aflags;       // BWD over peer memory: arrival flags of problem 1's Y rows (the x1 operands of the peers)
   int rot;                  // BWD: every unit visits tile (t + rot) mod n_tiles -- the local rank block first, then the peers'
@@ -228,8 +236,7 @@ enum { B_XFULL = 0, B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_GFULL0, B_GFULL1
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd, 1)
-pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
-            const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1, const Params P) {
+pair_kernel(const __grid_constant__ TensorMaps M, const Params P) {
   using C = Cfg<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -244,13 +251,9 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     // forward kernel reads them: then the forward's relays fetch them as well and the backward's find them in place.
     if (blockIdx.x == 0) relay_signal_ready(P.relay);
     int m1 = P.relay.m1;
-    if (MODE == MODE_FWD1 && fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e > kFastS2Limit) m1 = 2;
+    if (MODE == MODE_FWD1 && fminf(expf(*P.p[0].logit_scale), P.p[0].scale_cap) * kLog2e > kFastS2Limit) m1 = 2;
     relay_pull(P.relay, m1, blockIdx.x, sptr);
     return;
-  }
-  if (P.gate != 0) {       // regime gate on the DEVICE value of the temperature (no host sync): uniform over the grid
-    const float gs2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
-    if ((P.gate == 1) != (gs2 <= kFastS2Limit)) return;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
@@ -261,7 +264,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   {
     const int per = P.n_iblk * P.n_big, big_units = P.n_prob * per;
     if (u < big_units) {
-      prob_ = u >= per;
+      prob_ = u / per;
       u -= prob_ * per;
       chunk_ = u / P.n_iblk;
       iblk_ = u - chunk_ * P.n_iblk;
@@ -269,7 +272,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       nt_ = min(P.tiles_per_chunk, (P.n_tiles - P.small_tiles) - tile0_);
     } else {
       u -= big_units;
-      prob_ = u >= P.n_iblk;
+      prob_ = u / P.n_iblk;
       iblk_ = u - prob_ * P.n_iblk;
       chunk_ = P.n_big;
       tile0_ = P.n_tiles - P.small_tiles;
@@ -278,8 +281,12 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
   }
   const int prob = prob_, chunk = chunk_, iblk = iblk_, tile0 = tile0_, nt = nt_;
   const Problem& pb = P.p[prob];
-  const CUtensorMap* mapx = prob ? &mx1 : &mx0;
-  const CUtensorMap* mapy = prob ? &my1 : &my0;
+  if (P.gate != 0) {       // regime gate on the DEVICE value of this pair's temperature (no host sync): uniform over its CTAs
+    const float gs2 = fminf(expf(*pb.logit_scale), pb.scale_cap) * kLog2e;
+    if ((P.gate == 1) != (gs2 <= kFastS2Limit)) return;
+  }
+  const CUtensorMap* mapx = &M.m[pb.mapx];
+  const CUtensorMap* mapy = &M.m[pb.mapy];
   const int row0 = iblk * C::RP + (int)crank * C::RC;   // first local X row of this CTA
   // Order in which this CTA visits its tiles.  Over peer memory (single-pass forward) the rows of every peer block
   // arrive chunk by chunk, all blocks at the same pace: a CTA whose range touches several rank blocks visits it
@@ -489,7 +496,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
     if (MODE == MODE_FWD) {
       const int row = row0 + sub * 32 + lane;         // lane = row (128 rows per CTA)
       const bool row_ok = row < pb.n_x;
-      const float s2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
+      const float s2 = fminf(expf(*pb.logit_scale), pb.scale_cap) * kLog2e;
       float m = -INFINITY, l = 0.f;
       for (int j = 0; j < nt; ++j) {
         const int b = j & 1;
@@ -539,8 +546,8 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       const int row = row0 + sub * 32 + lane;         // lane = row (128 rows per CTA)
       const bool row_ok = row < pb.n_x;
       const bool rows_full = row0 + C::RC <= pb.n_x;
-      const float s2 = fminf(expf(*P.logit_scale), P.scale_cap) * kLog2e;
-      float* cp = P.colpart + (int64_t)(iblk * 8 + (int)crank * 4 + sub) * pb.n_y;
+      const float s2 = fminf(expf(*pb.logit_scale), pb.scale_cap) * kLog2e;
+      float* cp = pb.colpart + (int64_t)(iblk * 8 + (int)crank * 4 + sub) * pb.n_y;
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
       TileOrder order = make_order();
       int tcur = order.first();
@@ -597,7 +604,7 @@ pair_kernel(const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUt
       const int row = row0 + r_in;
       const bool row_ok = row < pb.n_x;
       const bool rows_full = row0 + C::RC <= pb.n_x;  // CTA-uniform
-      const float s2 = P.scale[0] * kLog2e;
+      const float s2 = pb.scale[0] * kLog2e;
       const float lb = P.ln_B;
       const float rl2 = row_ok ? (pb.lse_x[pb.diag_offset + row] + lb) * kLog2e : INFINITY;
       const int dcol = row + pb.diag_offset;
@@ -759,17 +766,27 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int b
 }
 
 template <int MODE>
-static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int gate, cudaStream_t st) {
-  VPA_CHECK_ARG(a.D == 256 || a.D == 512, "pair kernels need D in {256, 512} (D=%d)", a.D);
-  VPA_CHECK_ARG(a.rows_global < (1ll << 30), "rows_global too large");
-  CUtensorMap maps[4];
-  for (int p = 0; p < 2; ++p) {
-    if (int e = make_map(&maps[2 * p + 0], a.x[p], a.rows_local, a.D, Cfg<MODE>::RC)) return e;
-    if (int e = make_map(&maps[2 * p + 1], a.y[p], a.rows_global, a.D, 128)) return e;
-  }
-  Params P{};
+static int launch(const PairLaunch& L, const SweepPlan& plan, int gate, cudaStream_t st) {
+  VPA_CHECK_ARG(L.D == 256 || L.D == 512, "pair kernels need D in {256, 512} (D=%d)", L.D);
+  VPA_CHECK_ARG(L.rows_global < (1ll << 30), "rows_global too large");
+  VPA_CHECK_ARG(L.n_prob >= 1 && L.n_prob <= kMaxProblems, "pair kernels: 1..%d problems per launch (got %d)", kMaxProblems, L.n_prob);
   const bool bwd = MODE == MODE_BWD;
   const bool fwd1 = MODE == MODE_FWD1;
+  Params P{};
+  TensorMaps M{};
+  // one tensor map per distinct (matrix, rows, box height): the pairs of a composite head share their operands
+  struct Key { const void* base; int64_t rows; int box; };
+  Key keys[kMaxMaps];
+  int n_maps = 0;
+  auto map_id = [&](const void* base, int64_t rows, int box, int* id) -> int {
+    for (int i = 0; i < n_maps; ++i)
+      if (keys[i].base == base && keys[i].rows == rows && keys[i].box == box) { *id = i; return 0; }
+    if (n_maps == kMaxMaps) return set_error(VPA_E_UNSUPPORTED, "pair kernels: more than %d distinct operand maps in one launch", kMaxMaps);
+    if (int e = make_map(&M.m[n_maps], base, rows, L.D, box)) return e;
+    keys[n_maps] = Key{base, rows, box};
+    *id = n_maps++;
+    return 0;
+  };
   P.n_iblk = bwd ? plan.pair_bwd_iblk : plan.pair_fwd_iblk;
   P.n_chunks = bwd ? plan.bwd_chunks : (fwd1 ? plan.fwd1_chunks : plan.fwd_chunks);
   P.tiles_per_chunk = bwd ? plan.bwd_tiles_per_chunk : (fwd1 ? plan.fwd1_tiles_per_chunk : plan.fwd_tiles_per_chunk);
@@ -777,49 +794,46 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
   P.pairs_per_problem = P.n_iblk * P.n_chunks;
   P.small_tiles = bwd ? plan.bwd_small : (fwd1 ? plan.fwd1_small : 0);
   P.n_big = P.n_chunks - (P.small_tiles > 0 ? 1 : 0);
-  P.n_prob = fwd1 ? 1 : 2;
-  P.D = a.D;
-  P.kboxes = a.D / 64;
-  P.nblk = a.D / 256;
-  P.logit_scale = a.logit_scale;
-  P.scale_cap = a.scale_cap;
-  P.scale = a.scale;
-  P.inv_B = 1.0f / (float)a.rows_global;
-  P.ln_B = logf((float)a.rows_global);
+  P.n_prob = L.n_prob;
+  P.D = L.D;
+  P.kboxes = L.D / 64;
+  P.nblk = L.D / 256;
+  P.inv_B = 1.0f / (float)L.rows_global;
+  P.ln_B = logf((float)L.rows_global);
   P.gate = gate;
-  P.colpart = ws.colpart;
-  if (fwd1) P.yflags = a.yflags;
+  if (fwd1) P.yflags = L.yflags;
   if (bwd) {
-    P.aflags = a.aflags;
+    P.aflags = L.aflags;
     // (any rotation covers every tile once; this one starts every unit on the local rank block)
-    if (a.relay || a.aflags.flags) P.rot = (int)((a.row_offset / kBN) % (P.n_tiles > 0 ? P.n_tiles : 1));
+    if (L.relay || L.aflags.flags) P.rot = (int)((L.row_offset / kBN) % (P.n_tiles > 0 ? P.n_tiles : 1));
   }
-  if ((fwd1 || bwd) && a.relay) P.relay = *a.relay;
+  if ((fwd1 || bwd) && L.relay) {
+    VPA_CHECK_ARG(L.n_prob <= 2, "pair kernels: the peer-memory relay serves one InfoNCE pair per launch");
+    P.relay = *L.relay;
+  }
+  for (int q = 0; q < L.n_prob; ++q) {
+    const PairProblem& s = L.p[q];
+    Problem& d = P.p[q];
+    if (int e = map_id(s.x, L.rows_local, Cfg<MODE>::RC, &d.mapx)) return e;
+    if (int e = map_id(s.y, L.rows_global, 128, &d.mapy)) return e;
+    d.n_x = (int)L.rows_local;
+    d.n_y = (int)L.rows_global;
+    d.diag_offset = (int)L.row_offset;
+    d.lse_x = s.lse_x; d.lse_y = s.lse_y;
+    d.out = s.out; d.dscale = s.dscale;
+    d.logit_scale = s.logit_scale; d.scale_cap = s.scale_cap; d.scale = s.scale;
+    d.colpart = s.colpart;
+  }
+  const SmemLayout SL = smem_layout<MODE>(P.kboxes);
+  if (SL.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", SL.total);
   static_assert(kRelaySmemBytes + 1024 <= kSmemLimit, "the relay ring must fit into the forward kernel's shared memory");
-  for (int p = 0; p < 2; ++p) {
-    P.p[p].n_x = (int)a.rows_local;
-    P.p[p].n_y = (int)a.rows_global;
-    P.p[p].diag_offset = (int)a.row_offset;
-    P.p[p].lse_x = a.lse_x[p];
-    P.p[p].lse_y = a.lse_y[p];
-    if (bwd) {
-      P.p[p].out = ws.bwd_part + (int64_t)p * P.n_chunks * a.rows_local * a.D;
-      P.p[p].dscale = p == 0 ? ws.dscale_part : nullptr;
-    } else {
-      P.p[p].out = ws.fwd_part + (int64_t)p * P.n_chunks * a.rows_local * 2;
-      P.p[p].dscale = nullptr;
-    }
-  }
-  const SmemLayout L = smem_layout<MODE>(P.kboxes);
-  if (L.total > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "pair kernel needs %u bytes of shared memory", L.total);
   const uint32_t dyn_smem = kSmemLimit;      // the layout plus whatever pad aligns the dynamic base to 1024 B
   static SmemAttrCache attr_cache[3];
   if (int e = ensure_dynamic_smem(attr_cache[MODE], pair_kernel<MODE>, (int)kSmemLimit)) return e;
-  // FWD1 sweeps one problem only (local x1 rows against all x2 rows)
-  dim3 grid((fwd1 ? 1 : 2) * 2 * P.pairs_per_problem + P.relay.n_ctas), block(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd);
+  dim3 grid(L.n_prob * 2 * P.pairs_per_problem + P.relay.n_ctas), block(MODE == MODE_FWD ? kThreadsFwd : kThreadsBwd);
   const int kind = bwd ? PROF_BWD_SWEEP : (fwd1 ? PROF_FWD_SWEEP : (gate == 2 ? PROF_FWD_GENERAL : PROF_FWD_SWEEP));
   prof_begin(kind, st);
-  VPA_CUDA(launch_kernel(pair_kernel<MODE>, grid, block, dyn_smem, st, maps[0], maps[1], maps[2], maps[3], P));
+  VPA_CUDA(launch_kernel(pair_kernel<MODE>, grid, block, dyn_smem, st, M, P));
   prof_end(kind, st);
   VPA_LAUNCH_CHECK(bwd ? "pair_kernel<BWD>" : (fwd1 ? "pair_kernel<FWD1>" : "pair_kernel<FWD>"));
   return 0;
@@ -827,16 +841,47 @@ static int launch(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan
 
 }  // namespace pr
 
+int pair_launch_fwd1(const PairLaunch& L, const SweepPlan& plan, cudaStream_t st) { return pr::launch<pr::MODE_FWD1>(L, plan, 1, st); }
+int pair_launch_fwd(const PairLaunch& L, const SweepPlan& plan, int gate, cudaStream_t st) { return pr::launch<pr::MODE_FWD>(L, plan, gate, st); }
+int pair_launch_bwd(const PairLaunch& L, const SweepPlan& plan, cudaStream_t st) { return pr::launch<pr::MODE_BWD>(L, plan, 0, st); }
+
+// One pair (the plain CELossHead step): problem 0 sweeps the local x1 rows against all x2 rows, problem 1 the reverse.
+static PairLaunch single_pair(const SweepArgs& a) {
+  PairLaunch L{};
+  L.rows_local = a.rows_local; L.rows_global = a.rows_global; L.row_offset = a.row_offset; L.D = a.D;
+  L.yflags = a.yflags; L.aflags = a.aflags; L.relay = a.relay;
+  for (int p = 0; p < 2; ++p) {
+    L.p[p].x = a.x[p]; L.p[p].y = a.y[p];
+    L.p[p].lse_x = a.lse_x[p]; L.p[p].lse_y = a.lse_y[p];
+    L.p[p].logit_scale = a.logit_scale; L.p[p].scale_cap = a.scale_cap; L.p[p].scale = a.scale;
+  }
+  return L;
+}
+
 // Forward.  In the fast configuration the single-pass kernel (valid while s*log2e <= 62) and the exact two-problem
 // kernel are both enqueued; each checks the DEVICE value of the temperature and returns at once when it is not its regime.
 // which: 0 = exact kernel unconditionally; 1 = single-pass kernel (reads x[0] = local x1 rows and y[0] = all x2 rows
 // only), gated on s*log2e <= 62; 2 = exact kernel gated on the complementary regime.
 int pair_infonce_fwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, int which, cudaStream_t st) {
-  if (which == 1) return pr::launch<pr::MODE_FWD1>(a, ws, plan, 1, st);
-  return pr::launch<pr::MODE_FWD>(a, ws, plan, which == 2 ? 2 : 0, st);
+  PairLaunch L = single_pair(a);
+  if (which == 1) {      // one problem: the local x1 rows against all x2 rows yield both statistics
+    L.n_prob = 1;
+    L.p[0].out = ws.fwd_part;
+    L.p[0].colpart = ws.colpart;
+    return pair_launch_fwd1(L, plan, st);
+  }
+  L.n_prob = 2;
+  for (int p = 0; p < 2; ++p) L.p[p].out = ws.fwd_part + (int64_t)p * plan.fwd_chunks * a.rows_local * 2;
+  return pair_launch_fwd(L, plan, which == 2 ? 2 : 0, st);
 }
 int pair_infonce_bwd(const SweepArgs& a, const Workspace& ws, const SweepPlan& plan, cudaStream_t st) {
-  return pr::launch<pr::MODE_BWD>(a, ws, plan, 0, st);
+  PairLaunch L = single_pair(a);
+  L.n_prob = 2;
+  for (int p = 0; p < 2; ++p) {
+    L.p[p].out = ws.bwd_part + (int64_t)p * plan.bwd_chunks * a.rows_local * a.D;
+    L.p[p].dscale = p == 0 ? ws.dscale_part : nullptr;
+  }
+  return pair_launch_bwd(L, plan, st);
 }
 float pair_fast_s2_limit() { return pr::kFastS2Limit; }
 

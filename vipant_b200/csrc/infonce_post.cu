@@ -275,6 +275,27 @@ __global__ void __launch_bounds__(256) exchange_stats_kernel(const PackArgs P, c
   merge_loss(A, term);
 }
 
+// ---- several InfoNCE pairs in one launch (composite heads) -- blockIdx.y = pair ----------------------------------
+struct PackMulti { PackArgs a[kMaxPairs]; };
+struct MergeMulti { MergeArgs a[kMaxPairs]; };
+__global__ void __launch_bounds__(256) pack_stats_multi_kernel(const PackMulti M) {
+  const PackArgs& A = M.a[blockIdx.y];
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float s = fminf(expf(*A.logit_scale), A.scale_cap);
+  pack_one(A, idx, s, A.fast && s * kLog2e <= A.s2_limit);
+}
+__global__ void __launch_bounds__(256) merge_stats_multi_kernel(const MergeMulti M) {
+  const MergeArgs& A = M.a[blockIdx.y];
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float e = expf(*A.logit_scale);
+  const float s = fminf(e, A.scale_cap);
+  if (j == 0 && A.scale_out) {
+    A.scale_out[0] = s;
+    A.scale_out[1] = (e <= A.scale_cap) ? 1.0f : 0.0f;
+  }
+  merge_loss(A, j < A.B ? merge_one(A, j, s) : 0.0);
+}
+
 // ---- loss = mean(row_lse - diag) + mean(col_lse - diag), fixed-order fp64 reduction ---------------
 __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
@@ -437,6 +458,95 @@ finalize_bwd_kernel(const float* __restrict__ part, int n_chunks, int64_t rows_l
   }
 }
 
+// Several pairs: the gradient of a modality is the sum over every problem that swept ITS rows (a modality shared by two
+// pairs receives both contributions), then ONE normalisation Jacobian -- it is linear, so J(sum) = sum(J).
+struct FinMultiArgs {
+  int n_mod, n_pairs, n_chunks, D, already, n_dscale;
+  int64_t rows;
+  const void* x[kMaxPairs];
+  void* dx[kMaxPairs];
+  int64_t ld[kMaxPairs];
+  const float* inv[kMaxPairs];
+  int n_src[kMaxPairs];                         // problems whose X rows are this modality
+  const float* part[kMaxPairs][2 * kMaxPairs];  // their dX partials [n_chunks][rows][D]
+  int src_pair[kMaxPairs][2 * kMaxPairs];       // the pair each belongs to (its s and upstream gradient)
+  const float* scale[kMaxPairs];                // per pair {s, flows}
+  const float* grad_out;                        // [n_pairs] upstream gradients d L / d loss_p
+  const float* dscale_part[kMaxPairs];
+  float* dlogit_scale;                          // [n_pairs]
+};
+template <int DTYPE, int NV>
+__global__ void __launch_bounds__(kFinWarps * 32, 3) finalize_multi_kernel(const FinMultiArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * kFinWarps + (threadIdx.x >> 5);   // (modality, row)
+  if (gw < (int64_t)A.n_mod * A.rows) {
+    const int m = (int)(gw / A.rows);
+    const int64_t row = gw - (int64_t)m * A.rows;
+    const int nvec = A.D >> 2;
+    float4 v[NV], a[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nvec && !A.already) a[k] = load4<DTYPE>(A.x[m], row * A.ld[m] + 4 * c);
+    }
+    for (int q = 0; q < A.n_src[m]; ++q) {
+      const int pr = A.src_pair[m][q];
+      const float sg = A.scale[pr][0] * A.grad_out[pr];
+      const float* pb = A.part[m][q] + row * A.D;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nvec) {
+          float4 acc = __ldg(reinterpret_cast<const float4*>(pb) + c);
+          for (int ch = 1; ch < A.n_chunks; ++ch) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(pb + (int64_t)ch * A.rows * A.D) + c);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          v[k].x = fmaf(acc.x, sg, v[k].x); v[k].y = fmaf(acc.y, sg, v[k].y);
+          v[k].z = fmaf(acc.z, sg, v[k].z); v[k].w = fmaf(acc.w, sg, v[k].w);
+        }
+      }
+    }
+    const float inv = A.already ? 1.0f : A.inv[m][row];
+    float dot = 0.f;
+    if (!A.already) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        a[k].x *= inv; a[k].y *= inv; a[k].z *= inv; a[k].w *= inv;
+        dot += a[k].x * v[k].x + a[k].y * v[k].y + a[k].z * v[k].z + a[k].w * v[k].w;
+      }
+      dot = warp_sum(dot);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        float4 o = v[k];
+        if (!A.already) {   // (I - a a^T) da / ||x||
+          o.x = (o.x - a[k].x * dot) * inv; o.y = (o.y - a[k].y * dot) * inv;
+          o.z = (o.z - a[k].z * dot) * inv; o.w = (o.w - a[k].w * dot) * inv;
+        }
+        store4<DTYPE>(A.dx[m], row * A.ld[m] + 4 * c, o);
+      }
+    }
+  }
+  if ((int)blockIdx.x < A.n_pairs) {        // d/dl of pair blockIdx.x: g * flows * s * sum G*cos, fixed-order fp64
+    const int pr = blockIdx.x;
+    __shared__ double red[kFinWarps * 32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < A.n_dscale; i += kFinWarps * 32) acc += (double)A.dscale_part[pr][i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kFinWarps * 16; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0)
+      A.dlogit_scale[pr] = (float)(red[0] * (double)A.scale[pr][0] * (double)A.grad_out[pr] * (double)A.scale[pr][1]);
+  }
+}
+
 int colsum_reduce_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows_global, const float* logit_scale,
                          float scale_cap, float* colsum, cudaStream_t st) {
   dim3 grid((unsigned)((rows_global + 255) / 256), kColSumSplit);
@@ -560,6 +670,62 @@ int finalize_bwd_launch(const Workspace& ws, const SweepPlan& plan, int64_t rows
 #undef VPA_FIN_NV
 #undef VPA_FIN
   VPA_LAUNCH_CHECK("finalize_bwd_kernel");
+  return 0;
+}
+
+// ---- multi-pair launchers (api.cu: vpa_infonce_multi_fwd / _bwd) ---------------------------------------------------
+int pack_merge_multi_launch(int n_pairs, const Workspace* ws, const SweepPlan& plan, int64_t rows, const float* const* logit_scale,
+                            const float* scale_cap, const float* const* diag_cos, float* const* msg, float* const* stats_all,
+                            float* const* scale_out, double* const* loss_part, uint32_t* const* loss_counter, float* loss_out,
+                            cudaStream_t st) {
+  VPA_CHECK_ARG(n_pairs >= 1 && n_pairs <= kMaxPairs, "multi: 1..%d pairs", kMaxPairs);
+  PackMulti P{};
+  MergeMulti M{};
+  for (int p = 0; p < n_pairs; ++p) {
+    P.a[p] = make_pack_args(ws[p], plan, rows, rows, logit_scale[p], scale_cap[p], diag_cos[p], 1, nullptr, true, msg[p], nullptr);
+    M.a[p] = make_merge_args(msg[p], 1, rows, rows, logit_scale[p], scale_cap[p], 1, stats_all[p], scale_out[p], nullptr,
+                             loss_part[p], loss_counter[p], loss_out + p);
+  }
+  dim3 grid((unsigned)((rows + 255) / 256), n_pairs);
+  pack_stats_multi_kernel<<<grid, 256, 0, st>>>(P);
+  VPA_LAUNCH_CHECK("pack_stats_multi_kernel");
+  merge_stats_multi_kernel<<<grid, 256, 0, st>>>(M);
+  VPA_LAUNCH_CHECK("merge_stats_multi_kernel");
+  return 0;
+}
+
+int finalize_multi_launch(const FinMultiHost& h, cudaStream_t st) {
+  FinMultiArgs A{};
+  A.n_mod = h.n_mod; A.n_pairs = h.n_pairs; A.n_chunks = h.n_chunks; A.D = h.D; A.already = h.already; A.n_dscale = h.n_dscale;
+  A.rows = h.rows;
+  for (int m = 0; m < h.n_mod; ++m) {
+    A.x[m] = h.x[m]; A.dx[m] = h.dx[m]; A.ld[m] = h.ld[m]; A.inv[m] = h.inv[m]; A.n_src[m] = h.n_src[m];
+    for (int q = 0; q < h.n_src[m]; ++q) { A.part[m][q] = h.part[m][q]; A.src_pair[m][q] = h.src_pair[m][q]; }
+  }
+  for (int p = 0; p < h.n_pairs; ++p) { A.scale[p] = h.scale[p]; A.dscale_part[p] = h.dscale_part[p]; }
+  A.grad_out = h.grad_out; A.dlogit_scale = h.dlogit_scale;
+  VPA_CHECK_ARG(h.D <= 128 * kFinMaxVec, "finalize: D=%d > %d unsupported", h.D, 128 * kFinMaxVec);
+  const int64_t n = (int64_t)h.n_mod * h.rows;
+  int64_t blocks = (n + kFinWarps - 1) / kFinWarps;
+  if (blocks < h.n_pairs) blocks = h.n_pairs;
+  dim3 grid((unsigned)blocks), block(kFinWarps * 32);
+  const int nv = h.D <= 128 ? 1 : (h.D <= 256 ? 2 : (h.D <= 512 ? 4 : 8));
+#define VPA_FINM(DT, NV) finalize_multi_kernel<DT, NV><<<grid, block, 0, st>>>(A)
+#define VPA_FINM_NV(DT)                 \
+  switch (nv) {                         \
+    case 1: VPA_FINM(DT, 1); break;     \
+    case 2: VPA_FINM(DT, 2); break;     \
+    case 4: VPA_FINM(DT, 4); break;     \
+    default: VPA_FINM(DT, 8); break;    \
+  }
+  prof_begin(PROF_FINALIZE, st);
+  if (h.in_dtype == VPA_F32) { VPA_FINM_NV(VPA_F32) }
+  else if (h.in_dtype == VPA_BF16) { VPA_FINM_NV(VPA_BF16) }
+  else { VPA_FINM_NV(VPA_F16) }
+  prof_end(PROF_FINALIZE, st);
+#undef VPA_FINM_NV
+#undef VPA_FINM
+  VPA_LAUNCH_CHECK("finalize_multi_kernel");
   return 0;
 }
 

@@ -166,6 +166,46 @@ diag_cos_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* _
   if (lane == 0) diag_cos[row] = dot;
 }
 
+// ---- several matrices in one launch (the modalities of a composite head: each is normalised ONCE, however many pairs
+// it takes part in) -- blockIdx.y = matrix
+struct NormMultiArgs {
+  const void* x[kMaxPairs];
+  int64_t ld[kMaxPairs];
+  __nv_bfloat16* y[kMaxPairs];
+  float* inv[kMaxPairs];
+  int64_t rows;
+  int D, already;
+};
+template <int DTYPE>
+__global__ void __launch_bounds__(kNormWarps * 32) normalize_multi_kernel(const NormMultiArgs A) {
+  const int lane = threadIdx.x & 31, m = blockIdx.y;
+  const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
+  if (row >= A.rows) return;
+  float4 keep[kMaxVec];
+  float inv;
+  normalize_row<DTYPE, true>(A.x[m], A.ld[m], row, A.D, A.already != 0, A.y[m], nullptr, A.inv[m], lane, keep, inv);
+}
+// diag_cos of several pairs in one launch -- blockIdx.y = pair
+struct DiagMultiArgs {
+  const __nv_bfloat16* a[kMaxPairs];
+  const __nv_bfloat16* t[kMaxPairs];
+  float* out[kMaxPairs];
+  int64_t rows;
+  int D;
+};
+__global__ void __launch_bounds__(kNormWarps * 32) diag_cos_multi_kernel(const DiagMultiArgs A) {
+  const int lane = threadIdx.x & 31, p = blockIdx.y;
+  const int64_t row = (int64_t)blockIdx.x * kNormWarps + (threadIdx.x >> 5);
+  if (row >= A.rows) return;
+  float dot = 0.f;
+  for (int c = lane; c < (A.D >> 2); c += 32) {
+    const float4 u = load4<VPA_BF16>(A.a[p], row * A.D + 4 * c), v = load4<VPA_BF16>(A.t[p], row * A.D + 4 * c);
+    dot += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) A.out[p][row] = dot;
+}
+
 static int check_rows(const void* x, int64_t rows, int D, int64_t ld, int in_dtype) {
   VPA_CHECK_ARG(x != nullptr, "normalize: null input");
   VPA_CHECK_ARG(rows >= 0 && D > 0 && (D % 4) == 0, "normalize: need rows >= 0, D %% 4 == 0 (D=%d)", D);
@@ -200,6 +240,43 @@ int diag_cos_bf16_launch(const void* a_bf16, const void* t_bf16, int64_t rows, i
   diag_cos_bf16_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a_bf16),
                                                reinterpret_cast<const __nv_bfloat16*>(t_bf16), rows, D, diag_cos);
   VPA_LAUNCH_CHECK("diag_cos_bf16_kernel");
+  return 0;
+}
+
+int normalize_multi_launch(const void* const* x, const int64_t* ld, int in_dtype, int64_t rows, int D, int n, int already,
+                           void* const* y_bf16, float* const* inv, cudaStream_t st) {
+  VPA_CHECK_ARG(n >= 1 && n <= kMaxPairs && D <= 128 * kMaxVec, "normalize_multi: 1..%d matrices, D <= %d", kMaxPairs, 128 * kMaxVec);
+  NormMultiArgs A{};
+  for (int m = 0; m < n; ++m) {
+    if (int e = check_rows(x[m], rows, D, ld[m], in_dtype)) return e;
+    A.x[m] = x[m]; A.ld[m] = ld[m]; A.y[m] = reinterpret_cast<__nv_bfloat16*>(y_bf16[m]); A.inv[m] = inv[m];
+  }
+  A.rows = rows; A.D = D; A.already = already;
+  if (rows == 0) return 0;
+  dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps), n), block(kNormWarps * 32);
+  prof_begin(PROF_NORMALIZE, st);
+  if (in_dtype == VPA_F32) normalize_multi_kernel<VPA_F32><<<grid, block, 0, st>>>(A);
+  else if (in_dtype == VPA_BF16) normalize_multi_kernel<VPA_BF16><<<grid, block, 0, st>>>(A);
+  else normalize_multi_kernel<VPA_F16><<<grid, block, 0, st>>>(A);
+  prof_end(PROF_NORMALIZE, st);
+  VPA_LAUNCH_CHECK("normalize_multi_kernel");
+  return 0;
+}
+
+int diag_cos_multi_launch(const void* const* a_bf16, const void* const* t_bf16, float* const* out, int n, int64_t rows, int D,
+                          cudaStream_t st) {
+  VPA_CHECK_ARG(n >= 1 && n <= kMaxPairs, "diag_cos_multi: 1..%d pairs", kMaxPairs);
+  if (rows == 0) return 0;
+  DiagMultiArgs A{};
+  for (int p = 0; p < n; ++p) {
+    A.a[p] = reinterpret_cast<const __nv_bfloat16*>(a_bf16[p]);
+    A.t[p] = reinterpret_cast<const __nv_bfloat16*>(t_bf16[p]);
+    A.out[p] = out[p];
+  }
+  A.rows = rows; A.D = D;
+  dim3 grid((unsigned)((rows + kNormWarps - 1) / kNormWarps), n), block(kNormWarps * 32);
+  diag_cos_multi_kernel<<<grid, block, 0, st>>>(A);
+  VPA_LAUNCH_CHECK("diag_cos_multi_kernel");
   return 0;
 }
 

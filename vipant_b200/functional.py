@@ -506,6 +506,93 @@ def infonce_loss(x1: torch.Tensor, x2: torch.Tensor, logit_scale: torch.Tensor, 
     return fn.apply(x1, x2, ls.reshape(()), scale_max, bool(normalized), prec, group, logit_scale_grad == "sum", segment_key)
 
 
+# ---------------------------------------------------------------------------- several pairs over shared modalities
+class _MultiPairStep(torch.autograd.Function):
+    """vpa_infonce_multi_fwd / _bwd: up to five InfoNCE pairs over up to five feature matrices in one set of launches."""
+
+    @staticmethod
+    def forward(ctx, pairs, scale_maxes, normalized, precision, n_mod, *tensors):
+        lib = _cabi.lib()
+        feats, scales = tensors[:n_mod], tensors[n_mod:]
+        rows, D = feats[0].shape
+        dev = feats[0].device
+        n_pairs = len(pairs)
+        with torch.cuda.device(dev):
+            nbytes = lib.vpa_infonce_multi_state_bytes(rows, D, n_mod, n_pairs, precision)
+            state = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            losses = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
+            xp = (ctypes.c_void_p * n_mod)(*[f.data_ptr() for f in feats])
+            ld = (ctypes.c_int64 * n_mod)(*[f.stride(0) for f in feats])
+            px = (ctypes.c_int32 * n_pairs)(*[p[0] for p in pairs])
+            py = (ctypes.c_int32 * n_pairs)(*[p[1] for p in pairs])
+            lsp = (ctypes.c_void_p * n_pairs)(*[t.data_ptr() for t in scales])
+            caps = (ctypes.c_float * n_pairs)(*[float(c) if c else 0.0 for c in scale_maxes])
+            _cabi.check(lib.vpa_infonce_multi_fwd(xp, ld, _DTYPES[feats[0].dtype], rows, D, n_mod, int(normalized), px, py, n_pairs,
+                                                  lsp, caps, precision, _ptr(state), nbytes, _ptr(losses), _stream()),
+                        "vpa_infonce_multi_fwd")
+        ctx.save_for_backward(state, *feats)
+        ctx.cfg = (pairs, normalized, precision, n_mod)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        pairs, normalized, precision, n_mod = ctx.cfg
+        state, *feats = ctx.saved_tensors
+        lib = _cabi.lib()
+        rows, D = feats[0].shape
+        dev = feats[0].device
+        n_pairs = len(pairs)
+        with torch.cuda.device(dev):
+            g = grad_losses.detach().to(device=dev, dtype=torch.float32).contiguous()
+            dxs = [_grad_like(f) for f in feats]
+            dls = torch.empty((n_pairs,), dtype=torch.float32, device=dev)
+            xp = (ctypes.c_void_p * n_mod)(*[f.data_ptr() for f in feats])
+            ld = (ctypes.c_int64 * n_mod)(*[f.stride(0) for f in feats])
+            dp = (ctypes.c_void_p * n_mod)(*[d.data_ptr() for d in dxs])
+            px = (ctypes.c_int32 * n_pairs)(*[p[0] for p in pairs])
+            py = (ctypes.c_int32 * n_pairs)(*[p[1] for p in pairs])
+            _cabi.check(lib.vpa_infonce_multi_bwd(xp, ld, _DTYPES[feats[0].dtype], rows, D, n_mod, int(normalized), px, py, n_pairs,
+                                                  precision, _ptr(g), _ptr(state), state.numel(), dp, _ptr(dls), _stream()),
+                        "vpa_infonce_multi_bwd")
+        return (None, None, None, None, None) + tuple(dxs) + tuple(dls[k] for k in range(n_pairs))
+
+
+def multi_pair_supported(feats, precision: str = "bf16") -> bool:
+    """Shapes the fused multi-pair step covers: CUDA matrices of one shape (rows <= 8192, D in {256, 512}) and dtype."""
+    if precision != "bf16" or not feats:
+        return False
+    f0 = feats[0]
+    return all(isinstance(f, torch.Tensor) and f.is_cuda and f.dim() == 2 and f.shape == f0.shape and f.dtype == f0.dtype
+               for f in feats) and f0.shape[1] in (256, 512) and 0 < f0.shape[0] <= 8192
+
+
+def infonce_multi_loss(feats, pairs, logit_scales, scale_maxes=None, normalized: bool = False, precision: str = "bf16"):
+    """Per-pair symmetric InfoNCE losses of several pairs over shared feature matrices (the composite heads of the reference,
+    loss_head.py:421-598) in ONE fused step: every matrix is normalised once, all pairs share the sweep launches, and the
+    gradient of a matrix is the sum over the pairs it takes part in.
+
+    feats: list of (rows, D) CUDA tensors (same shape / dtype); pairs: list of (i, j) indices into feats; logit_scales: one
+    0-d fp32 CUDA tensor per pair.  Returns a (len(pairs),) tensor of losses, differentiable w.r.t. feats and logit_scales.
+    """
+    feats = [_rows2d(f) for f in feats]
+    if not multi_pair_supported(feats, precision):
+        raise _cabi.VipantB200Error("infonce_multi_loss: needs CUDA matrices of one shape with rows <= 8192 and D in {256, 512} "
+                                    "(precision 'bf16'); run the pairs one by one with infonce_loss otherwise")
+    if not 1 <= len(pairs) <= 5 or len(feats) > 5 or len(logit_scales) != len(pairs):
+        raise ValueError("infonce_multi_loss: 1..5 pairs over at most 5 matrices, one logit_scale per pair")
+    dev = feats[0].device
+    scales = []
+    for ls in logit_scales:
+        if not isinstance(ls, torch.Tensor):
+            ls = torch.tensor(float(ls))
+        if ls.device != dev or ls.dtype != torch.float32:
+            ls = _device_scalar(ls, dev) if (ls.device.type == "cpu" and not ls.requires_grad) else ls.to(device=dev, dtype=torch.float32)
+        scales.append(ls.reshape(()))
+    caps = list(scale_maxes) if scale_maxes is not None else [None] * len(pairs)
+    return _MultiPairStep.apply(tuple((int(i), int(j)) for i, j in pairs), tuple(caps), bool(normalized), PRECISIONS[precision],
+                                len(feats), *feats, *scales)
+
+
 def _gt_matrix(gt, rows, upper, dev, what):
     """(rows,) or (rows, g <= 8) integer ground-truth indices -> int32 (rows, g), validated on the host side of the call:
     an index outside [0, upper) would make the kernel compare against another row's memory."""

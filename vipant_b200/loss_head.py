@@ -347,7 +347,9 @@ class ClassificationHead(LossHead):
 
 
 class _PairwiseCE(LossHead):
-    """Shared machinery of the composite heads: a dict of named CELossHeads plus running loss sums."""
+    """Shared machinery of the composite heads: a dict of named CELossHeads plus running loss sums.  In training the enabled
+    pairs run as ONE fused multi-pair step (functional.infonce_multi_loss: every modality normalised once, one launch per
+    sweep for all pairs) when the shapes allow it, and one after the other otherwise -- same values either way."""
 
     _pairs = ()          # ((key, attr_name), ...)
 
@@ -375,6 +377,34 @@ class _PairwiseCE(LossHead):
         self._total_loss[key] += loss.detach()
         return loss
 
+    def _train_terms(self, spec, *args, **kwargs):
+        """spec: [(key, attr, xa, xb)] in the reference's order.  Returns the per-pair losses (0. for a disabled pair)."""
+        live = [(k, a, xa, xb) for k, a, xa, xb in spec if getattr(self, a) is not None and xa is not None and xb is not None]
+        heads = [getattr(self, a) for _, a, _, _ in live]
+        fused = (len(live) >= 2 and all(h.precision == "bf16" and not (h.gather and dist.is_initialized() and dist.get_world_size() > 1)
+                                        for h in heads))
+        if fused:
+            feats, index = [], {}
+            for _, _, xa, xb in live:
+                for x in (xa, xb):
+                    if id(x) not in index:
+                        index[id(x)] = len(feats)
+                        feats.append(x)
+            fused = len(feats) <= 5 and len(live) <= 5 and F_.multi_pair_supported(feats)
+        out = {}
+        if fused:
+            losses = F_.infonce_multi_loss(
+                feats, [(index[id(xa)], index[id(xb)]) for _, _, xa, xb in live], [h.logit_scale for h in heads],
+                [None if h.scale_max == float("inf") else h.scale_max for h in heads],
+                normalized=bool(kwargs.get("normalized", False)))
+            for i, (key, _, _, _) in enumerate(live):
+                self._total_loss[key] += losses[i].detach()
+                out[key] = losses[i]
+        else:
+            for key, attr, xa, xb in live:
+                out[key] = self._run(key, attr, xa, xb, True, *args, **kwargs)
+        return [out.get(k, 0.) for k, _, _, _ in spec]
+
 
 @LOSS_HEADS_REGISTRY.register()
 class VALCELossHead(_PairwiseCE):
@@ -387,6 +417,10 @@ class VALCELossHead(_PairwiseCE):
         self._build(cfg, **kwargs)
 
     def _all(self, x1, x2, x3, train, *args, **kwargs):
+        if train:
+            va, lv, al = self._train_terms([("va", "loss_head_va", x1, x2), ("lv", "loss_head_lv", x1, x3),
+                                            ("al", "loss_head_al", x2, x3)], *args, **kwargs)
+            return va + lv + al
         return (self._run("va", "loss_head_va", x1, x2, train, *args, **kwargs) +
                 self._run("lv", "loss_head_lv", x1, x3, train, *args, **kwargs) +
                 self._run("al", "loss_head_al", x2, x3, train, *args, **kwargs))
@@ -422,6 +456,10 @@ class VACELossHead(_PairwiseCE):
         self.vp_w, self.ap_w, self.va_w, self.vv_w, self.aa_w = cfg.vp_w, cfg.ap_w, cfg.va_w, cfg.vv_w, cfg.aa_w
 
     def _terms(self, images, images_v1, audios_v1, images_v2, audios_v2, train, *args, **kwargs):
+        if train:
+            return tuple(self._train_terms([("vp", "loss_head_vp", images_v1, images), ("ap", "loss_head_ap", audios_v1, images),
+                                            ("va", "loss_head_va", images_v1, audios_v1), ("vv", "loss_head_vv", images_v1, images_v2),
+                                            ("aa", "loss_head_aa", audios_v1, audios_v2)], *args, **kwargs))
         return (self._run("vp", "loss_head_vp", images_v1, images, train, *args, **kwargs),
                 self._run("ap", "loss_head_ap", audios_v1, images, train, *args, **kwargs),
                 self._run("va", "loss_head_va", images_v1, audios_v1, train, *args, **kwargs),

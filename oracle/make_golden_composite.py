@@ -23,7 +23,7 @@ from oracle.reference_loader import Cfg, load_reference_loss_head  # noqa: E402
 
 B, D, SEED = 320, 512, 1213
 VAL_SCALES = {"va": 2.0, "lv": 2.659260036932778, "al": 3.2}            # ln of the temperatures (one per pair)
-VA_SCALES = {"vp": 2.1, "ap": 2.659260036932778, "va": 3.0, "vv": 2.4, "aa": 3.5}
+VA_SCALES = {"vp": 2.1, "ap": 2.659260036932778, "va": 2.9, "vv": 2.4, "aa": 3.5}
 VA_WEIGHTS = dict(vp_w=1.0, ap_w=0.5, va_w=2.0, vv_w=0.25, aa_w=0.75)
 GRAD_OUT = 128.0
 ROWS = np.arange(3, B, 7)                   # sampled gradient rows kept in the fixture (+ the Frobenius norm of every matrix)

@@ -61,6 +61,7 @@ const char* vpa_last_error_string(void);
 #define VPA_PROF_FINALIZE 6
 #define VPA_PROF_PUSH 7 /* peer-memory transport: the stand-alone operand relay kernel (shapes without the fused forward) */
 int vpa_profile_enable(int on);
+int vpa_profile_hold(int hold); /* pause (1) / resume (0) the bracketing without discarding what was recorded */
 /* Kernel launches of this library since it was loaded (every launch site counts itself): bench.py's `gpu_launches`. */
 unsigned long long vpa_launch_count(void);
 /* Work decomposition chosen for a shape (diagnostics / tests; host only, no device needed): out10 = n_tiles, single-pass

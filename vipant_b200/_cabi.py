@@ -20,6 +20,7 @@ _SIGNATURES = {
     "vpa_last_error_string": (c_char_p, []),
     "vpa_plan_query": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(c_int)]),
     "vpa_profile_enable": (c_int, [c_int]),
+    "vpa_profile_hold": (c_int, [c_int]),
     "vpa_launch_count": (ctypes.c_ulonglong, []),
     "vpa_profile_read": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),
     "vpa_normalize_cast": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -32,6 +32,7 @@ void note_launch() { ++g_launches; }
 constexpr int kProfSlots = 512;
 struct ProfState {
   bool on = false;
+  bool hold = false;      // enabled but paused: launches are not bracketed (vpa_profile_hold)
   cudaEvent_t ev[PROF_KINDS][kProfSlots][2];
   bool made[PROF_KINDS][kProfSlots];
   int n[PROF_KINDS];
@@ -39,7 +40,7 @@ struct ProfState {
 static ProfState g_prof;
 
 void prof_begin(int kind, cudaStream_t st) {
-  if (!g_prof.on || g_prof.n[kind] >= kProfSlots) return;
+  if (!g_prof.on || g_prof.hold || g_prof.n[kind] >= kProfSlots) return;
   const int i = g_prof.n[kind];
   if (!g_prof.made[kind][i]) {
     if (cudaEventCreate(&g_prof.ev[kind][i][0]) != cudaSuccess || cudaEventCreate(&g_prof.ev[kind][i][1]) != cudaSuccess) return;
@@ -48,7 +49,7 @@ void prof_begin(int kind, cudaStream_t st) {
   cudaEventRecord(g_prof.ev[kind][i][0], st);
 }
 void prof_end(int kind, cudaStream_t st) {
-  if (!g_prof.on || g_prof.n[kind] >= kProfSlots) return;
+  if (!g_prof.on || g_prof.hold || g_prof.n[kind] >= kProfSlots) return;
   const int i = g_prof.n[kind];
   if (!g_prof.made[kind][i]) return;
   cudaEventRecord(g_prof.ev[kind][i][1], st);
@@ -269,10 +270,6 @@ static SweepPlan plan_sweep_uncached(int64_t rows_local, int64_t rows_global, in
   p.n_tiles = (int)((rows_global + 127) / 128);
   p.halves = D > 256 ? 2 : 1;
   p.cluster = p.n_iblk >= 2 ? 2 : 1;      // measured on B200 at B=32768: 2 is best (4 strands SMs, 1 doubles L2 reads)
-  if (const char* e = getenv("VPA_CLUSTER")) {       // tuning knob for measurements: 1, 2 or 4
-    const int c = atoi(e);
-    if (c == 1 || c == 2 || c == 4) p.cluster = c;
-  }
   const int padded = (p.n_iblk + p.cluster - 1) / p.cluster * p.cluster;
   pick_chunks(2 * padded, p.n_tiles, 2, &p.fwd_chunks, &p.fwd_tiles_per_chunk);
   pick_chunks(2 * padded * p.halves, p.n_tiles, 3, &p.bwd_chunks, &p.bwd_tiles_per_chunk);
@@ -342,8 +339,14 @@ int vpa_plan_query(int64_t rows_local, int64_t rows_global, int D, int precision
 
 unsigned long long vpa_launch_count(void) { return g_launches; }
 
+int vpa_profile_hold(int hold) {
+  g_prof.hold = hold != 0;
+  return 0;
+}
+
 int vpa_profile_enable(int on) {
   g_prof.on = on != 0;
+  g_prof.hold = false;
   for (int k = 0; k < PROF_KINDS; ++k) g_prof.n[k] = 0;
   return 0;
 }

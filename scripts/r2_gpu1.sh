@@ -13,6 +13,6 @@ timeout 300 python scripts/score_bench.py > gpurun_out/scoring.json 2> gpurun_ou
 if [ -n "$NCU" ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-eager > gpurun_out/ncu_bench.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"sim_|rank_topk|normalize_pair" -c 12 -f -o gpurun_out/prof_scoring \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"sim_rank_tile|sim_gt_ref|normalize_pair|ap_class|micro_ap_kernel|finalize_multi|rank_topk" -c 14 -f -o gpurun_out/prof_scoring \
       python scripts/score_bench.py > gpurun_out/ncu_scoring.log 2>&1
 fi

@@ -75,6 +75,45 @@ lib.vpa_profile_enable(0)
 t0 = time.perf_counter(); ro.zero_shot_report(audios, text, labels); cpu_zs = (time.perf_counter() - t0) * 1e3
 out["c5_zero_shot"] = {"call_ms": ms_zs, "fused_kernels_us": sim_us, "cpu_oracle_numpy_ms": cpu_zs}
 
+# ---- Z2: AudioSet-shaped multi-label scoring, 20371 clips x 527 label prompts (per-class AP / AUC / PR middle + micro AP)
+from vipant_b200.loss_more import multilabel_scores, similarity_matrix
+from oracle import map_oracle as mo
+rng = np.random.default_rng(1213)
+NA, CA = 20371, 527
+text_a = rng.standard_normal((CA, 512)).astype(np.float32)
+Ya = np.zeros((NA, CA), np.float32)
+for _ in range(2):
+    Ya[np.arange(NA), rng.integers(0, CA, NA)] = 1.0
+aud_a = (Ya @ text_a * 0.35 + rng.standard_normal((NA, 512))).astype(np.float32)
+ag, tg, yg = vb.l2_normalize(torch.from_numpy(aud_a).cuda()), vb.l2_normalize(torch.from_numpy(text_a).cuda()), torch.from_numpy(Ya).cuda()
+ms_sim, Sg = timed(lambda: similarity_matrix(ag, tg), reps=10)
+ms_ml, m = timed(lambda: multilabel_scores(Sg, yg), reps=10)
+t0 = time.perf_counter()
+Sc = Sg.cpu().numpy()
+ap_cpu = np.array([mo.average_precision(Ya[:, k], Sc[:, k]) for k in range(CA)])
+auc_cpu = np.array([mo.roc_auc(Ya[:, k], Sc[:, k]) for k in range(CA)])
+micro_cpu = mo.average_precision_multilabel(Ya, Sc, "micro")
+cpu_ml = (time.perf_counter() - t0) * 1e3
+out["z2_audioset_multilabel"] = {"N": NA, "C": CA, "similarity_call_ms": ms_sim, "scoring_call_ms": ms_ml, "cpu_oracle_numpy_ms": cpu_ml,
+                                 "max_abs_ap_diff": float(np.abs(m["ap"] - ap_cpu).max()), "max_abs_auc_diff": float(np.abs(m["auc"] - auc_cpu).max()),
+                                 "micro_ap_diff": abs(m["micro_ap"] - micro_cpu), "mAP": float(m["ap"].mean())}
+
+# ---- composite head: three pairs fused vs pair by pair at B = 4096
+import math
+gen = torch.Generator().manual_seed(5)
+base = torch.randn(4096, 512, generator=gen)
+feats = [(0.4 * base + torch.randn(4096, 512, generator=gen)).cuda().requires_grad_(True) for _ in range(3)]
+lss = [torch.tensor(v, device="cuda", requires_grad=True) for v in (2.0, 2.66, 3.2)]
+pairs = [(0, 1), (0, 2), (1, 2)]
+def fused_step():
+    for f in feats: f.grad = None
+    vb.infonce_multi_loss(feats, pairs, lss).sum().backward()
+def seq_step():
+    for f in feats: f.grad = None
+    sum(vb.infonce_loss(feats[i], feats[j], lss[k]) for k, (i, j) in enumerate(pairs)).backward()
+ms_f, _ = timed(fused_step, reps=30); ms_s, _ = timed(seq_step, reps=30)
+out["composite_val_b4096"] = {"fused_ms_per_step": ms_f, "pair_by_pair_ms_per_step": ms_s, "speedup": ms_s / ms_f}
+
 # ---- normalise kernel alone at the training shape (HBM roofline row)
 x = torch.randn(32768, 512, device="cuda")
 lib.vpa_profile_enable(1)

@@ -44,6 +44,7 @@ out["c4_t2a"] = {"call_ms": ms21, "sim_kernel_us": sim_us, "rank_topk_kernel_us"
                  "rank_gbs": (4 * N * M + 4 * M) / (rank_us * 1e-6) / 1e9}
 # fused path: the similarity tile is consumed in registers (vpa_sim_rank_fused); kernel time = reference + tile kernels
 from vipant_b200 import functional as F_
+F_.sim_rank_fused(an, tn, gt_q=gt12); prof(3)          # (first call: one-time kernel attribute set-up, not timed)
 ms_a2t, _ = timed(lambda: F_.sim_rank_fused(an, tn, gt_q=gt12))
 fa2t_us, _ = prof(3)
 ms_both, _ = timed(lambda: F_.sim_rank_fused(an, tn, gt_q=gt12, gt_k=gt21))
@@ -84,7 +85,7 @@ text_a = rng.standard_normal((CA, 512)).astype(np.float32)
 Ya = np.zeros((NA, CA), np.float32)
 for _ in range(2):
     Ya[np.arange(NA), rng.integers(0, CA, NA)] = 1.0
-aud_a = (Ya @ text_a * 0.35 + rng.standard_normal((NA, 512))).astype(np.float32)
+aud_a = (Ya @ text_a * 0.08 + rng.standard_normal((NA, 512))).astype(np.float32)
 ag, tg, yg = vb.l2_normalize(torch.from_numpy(aud_a).cuda()), vb.l2_normalize(torch.from_numpy(text_a).cuda()), torch.from_numpy(Ya).cuda()
 ms_sim, Sg = timed(lambda: similarity_matrix(ag, tg), reps=10)
 ms_ml, m = timed(lambda: multilabel_scores(Sg, yg), reps=10)

@@ -91,7 +91,7 @@ def test_audioset_shape_zero_shot():
     Y = np.zeros((N, C), np.float32)
     for _ in range(2):
         Y[np.arange(N), rng.integers(0, C, N)] = 1.0
-    audios = (Y @ text * 0.35 + rng.standard_normal((N, D))).astype(np.float32)
+    audios = (Y @ text * 0.08 + rng.standard_normal((N, D))).astype(np.float32)
     head = BCELossHead(Cfg(embed_dim=D, width=D, layers=[], bias=True, scaling=True), output_dim=C).cuda().eval()
     with torch.no_grad():
         for i in range(0, N, 4096):

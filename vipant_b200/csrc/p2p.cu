@@ -1,13 +1,13 @@
 // Peer-memory transport of the row-sharded step: the gathered operand matrices, the per-rank statistics messages and the
 // d logit_scale partials live in a SYMMETRIC segment (same layout on every rank, cudaMalloc + CUDA IPC), and every
 // exchange is done by kernels reading / writing the peers' segments over NVLink, published with system-scope epoch flags:
-//   * operands: RELAY CTAs (p2p.cuh) -- the first CTAs of the single-pass forward's own grid -- pull the peers' normalised
-//     rows with TMA bulk copies through a shared-memory ring (x2 operands first, 256-row chunks, chunk-major over the
-//     peers) and raise one local arrival flag per chunk.  The sweep CTAs of the same kernel poll the flag of every tile
-//     before loading it, so the contraction starts on the local block and consumes remote rows as they land: ONE kernel
-//     is the all-gather and the GEMM.  The x1 operands (read by the backward only) follow in the same relay CTAs; when the
-//     kernel has finished everything has landed -- no wait kernel, no side stream.  The only remote store of the pull is
-//     one "my rows are complete" flag per peer and step.
+//   * operands: RELAY CTAs (p2p.cuh) -- the first CTAs of a sweep kernel's own grid -- pull the peers' normalised rows with
+//     TMA bulk copies through a shared-memory ring (256-row chunks) and raise one local arrival flag per chunk.  The sweep CTAs
+//     of the same kernel poll the flags of the tiles ahead of them, so the contraction starts on the local block and consumes
+//     remote rows as they land: ONE kernel is the all-gather and the GEMM.  The forward kernel fetches the x2 operands (all it
+//     reads; chunk-major over the peers), the backward kernel the x1 operands (read by its second problem only; peer after
+//     peer) while its first problem runs -- no wait kernel, no side stream.  The only remote store of the pull is one "my rows
+//     are complete" flag per peer and step.
 //   * statistics: one kernel writes this rank's message into every peer, waits for the R messages and merges them;
 //   * d logit_scale: finalize_bwd stores {epoch, partial} into every rank's slot and sums the R partials in rank order
 //     (bitwise identical on every rank).

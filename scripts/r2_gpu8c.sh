@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round 2, eight-GPU visit #4: multi-GPU parity over NVLink (short), then N = 8 / 4 / 2 lines with the lookahead polling.
+# Round 2, eight-GPU visit: the N = 8 / 4 / 2 lines of the final build (default transport; the driver's SCALE run does the same).
+#   gpurun --gpus 8 --timeout 500 -- 'bash scripts/r2_gpu8c.sh'
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_multi.py -q -m gpu --timeout 150 -k "sharded_matches_global_batch and p2p or fifty or three_pairs" > gpurun_out/pytest_gpu8.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu8.log
 run() {  # n, name, extra bench args, env...
   n=$1; name=$2; extra=$3; shift 3
   env "$@" timeout ${TMO:-100} python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n \
@@ -17,9 +17,4 @@ for l in open('gpurun_out/n${n}_$name.json'):
 if not ok: print(open('gpurun_out/n${n}_$name.err').read()[-1200:])
 PY
 }
-P="VIPANT_TRANSPORT=p2p VIPANT_REQUIRE_P2P=1"
-run 8 look --no-e2e $P
-run 8 look_bwd8 --no-e2e $P VPA_P2P_RELAY_CTAS_BWD=8
-run 4 look --no-e2e $P
-run 2 look --no-e2e $P
-run 8 look_full "" $P
+for n in ${NS:-8 4 2}; do run $n final "${EXTRA:---no-e2e}" X=1; done

@@ -202,3 +202,122 @@ def test_gold_file_class_stats_match_reference(strings, tmp_path):
     msg_21 = head._class_stats(torch.from_numpy(g["top1_21"].astype(np.int64)), by_class, by_sample, len(ids), "A->I")
     expected = strings["retrieval_nn_goldfile"].split("\n")[1]
     assert f"{msg_12} {msg_21}" == expected
+
+
+# ---- host logic of the scoring reports with checker kernels standing in for the CUDA calls ---------------------------------
+class _CheckerScoring:
+    """numpy / fp64 stand-ins (the oracle's definitions) for the three CUDA entry points `report()` uses.  Installed with
+    monkeypatch in the tests below ONLY: the package itself has no such path."""
+
+    @staticmethod
+    def l2_normalize(x, already_normalized=False):
+        x = x.float()
+        return x if already_normalized else x / x.norm(dim=-1, keepdim=True)
+
+    @staticmethod
+    def sim_rank_fused(q, k, gt_q=None, gt_k=None, top1_q=False, top1_k=False):
+        from oracle import retrieval_oracle as ro
+        S = q.double().numpy() @ k.double().numpy().T
+        out = {}
+        if gt_q is not None:
+            out["ranks_q"] = torch.from_numpy(ro.rank_of(S, gt_q.numpy()))
+        if gt_k is not None:
+            out["ranks_k"] = torch.from_numpy(ro.rank_of(S.T, gt_k.numpy()))
+        if top1_q:
+            out["top1_q"] = (torch.from_numpy(S.argmax(1)), torch.from_numpy(S.max(1)).float())
+        if top1_k:
+            out["top1_k"] = (torch.from_numpy(S.argmax(0)), torch.from_numpy(S.max(0)).float())
+        return out
+
+
+@pytest.fixture
+def checker_scoring(monkeypatch):
+    monkeypatch.setattr(F_, "_require_cuda", lambda *a: None)
+    monkeypatch.setattr(F_, "l2_normalize", _CheckerScoring.l2_normalize)
+    monkeypatch.setattr(F_, "sim_rank_fused", _CheckerScoring.sim_rank_fused)
+
+
+def test_report_host_logic_reproduces_the_reference_strings(checker_scoring, strings, tmp_path):
+    """LossHead.infer / _stash / report (1-vs-5, N == M, N == M with a gold file, fallback shapes) fed by the checker: the
+    strings must be the reference's (tests/golden/report_strings.json) -- this is the part of R1-R4 that is host Python."""
+    from oracle.make_golden import gold_file_case, retrieval_inputs_1v5, retrieval_inputs_nn
+
+    def run(a, t, batch, gold=None, names=None):
+        head = vb.CELossHead(Cfg(scaling=True, scale_max=None)).eval()
+        k = t.shape[0] // a.shape[0]
+        for i in range(0, a.shape[0], batch):
+            assert head(torch.from_numpy(a[i:i + batch]), torch.from_numpy(t[i * k:(i + batch) * k]), normalized=False,
+                        names=None if names is None else names[i:i + batch]) is None
+        rep = head.report(gold_file=gold)
+        assert not hasattr(head, "x1s") and not hasattr(head, "_stash_normalized")
+        return rep
+
+    g = load_golden("retrieval_1v5_small")
+    a, t = retrieval_inputs_1v5(n=150, seed=int(g["seed"]))
+    assert run(a, t, 64) == strings["retrieval_1v5_small"]
+    g = load_golden("retrieval_nn")
+    a, t = retrieval_inputs_nn(seed=int(g["seed"]))
+    assert run(a, t, 50) == strings["retrieval_nn"]
+    a, t, ids, lines = gold_file_case()
+    path = tmp_path / "gold.json"
+    path.write_text("\n".join(lines) + "\n")
+    assert run(a, t, 50, gold=str(path), names=ids) == strings["retrieval_nn_goldfile"]
+    head = vb.CELossHead(Cfg(scaling=True, scale_max=None)).eval()
+    torch.manual_seed(0)
+    head(torch.randn(6, 16), torch.randn(9, 16))
+    assert head.report() == strings["retrieval_fallback_6x9x16"]
+
+
+def test_stash_keeps_views_compact():
+    """A batch that is a view into something larger (the CLS token of a hidden state) is copied; a tensor that owns its
+    storage is kept as it is (no extra kernel per batch)."""
+    from vipant_b200.loss_head import _compact
+    hidden = torch.randn(8, 5, 16)
+    cls = hidden[:, 0, :]
+    kept = _compact(cls)
+    assert kept.is_contiguous() and kept.untyped_storage().nbytes() == 8 * 16 * 4 and torch.equal(kept, cls)
+    own = torch.randn(8, 16)
+    assert _compact(own).data_ptr() == own.data_ptr()
+
+
+def test_bce_head_report_host_logic(monkeypatch):
+    """BCELossHead.report: macro / weighted / mean fields and the Err flag from the per-class numbers (here supplied by the
+    oracle) -- identical to the oracle's restatement of the reference's string, degenerate classes included."""
+    from oracle import map_oracle as mo
+    from vipant_b200 import loss_more as lm
+    rng = np.random.default_rng(4)
+    Y = (rng.random((400, 7)) < 0.2).astype(np.float32)
+    Y[:, 2] = 0.0
+    S = (Y + rng.standard_normal(Y.shape)).astype(np.float32)
+
+    def fake(scores, labels, truncate_pr=True, micro=True):
+        s, y = scores.numpy(), labels.numpy()
+        _, parts = mo.report(s, y, truncate=truncate_pr)
+        ap = np.array([mo.average_precision(y[:, k], s[:, k]) for k in range(y.shape[1])])
+        auc = []
+        for k in range(y.shape[1]):
+            try:
+                auc.append(mo.roc_auc(y[:, k], s[:, k]))
+            except ValueError:
+                auc.append(np.nan)
+        return dict(ap=ap, auc=np.array(auc), p_mid=np.array(parts["p_mid"]), r_mid=np.array(parts["r_mid"]),
+                    support=y.sum(0).astype(np.int64), flags=None, micro_ap=mo.average_precision_multilabel(y, s, "micro"))
+    monkeypatch.setattr(lm, "multilabel_scores", fake)
+    head = lm.BCELossHead(Cfg(embed_dim=16, width=16, layers=[8], bias=False, scaling=False), output_dim=7).eval()
+    assert [type(m).__name__ for m in head.linear] == ["_LayerNormF32", "Linear", "_LayerNormF32", "Linear"]
+    head.audios, head.x1s, head.x2s, head.ids = [], [], [], []
+    got = head.report(x1s=torch.from_numpy(S), x2s=torch.from_numpy(Y))
+    want, _ = mo.report(S, Y, truncate=True)
+    assert got == want and "Err(True)" in got
+
+
+def test_multi_pair_argument_checks():
+    from vipant_b200 import functional as F
+    assert not F.multi_pair_supported([torch.randn(4, 512)])                       # CPU tensors: no fused step, no fallback
+    with pytest.raises(_cabi.VipantB200Error):
+        vb.infonce_multi_loss([torch.randn(4, 512), torch.randn(4, 512)], [(0, 1)], [torch.tensor(1.0)])
+    with pytest.raises(ValueError):
+        F.check_gt_range(torch.tensor([[0, 7]]), 7)
+    F.check_gt_range(torch.tensor([[0, 6]]), 7)
+    with pytest.raises(ValueError):
+        F._gt_matrix(torch.zeros(3, 9, dtype=torch.long), 3, 10, torch.device("cpu"), "gt")

@@ -190,6 +190,24 @@ int vpa_sim_rank_fused(const float* Q, const float* K, int64_t N, int64_t M, int
                        size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Encoder tail fused up to the InfoNCE operand.  Replaces the last ops of the reference's towers
+ *     x = ln_post(x[:, 0, :]);  x = x @ proj;  x = x / x.norm(dim=-1, keepdim=True)
+ *   /root/reference/cvap/module/val.py:288-290 (ViTPostEncoder), :143-146 (GPTPostEncoder); the normalisation in
+ *   cvap/module/encoder/clip_head.py:117-118, audio_head.py:209-210 -- and the cast to the bf16 operand rows the sweeps read.
+ * x: (rows, width) CLS rows, row stride ld (the view hidden[:, 0, :] is read in place), dtype in_dtype; ln_gamma / ln_beta:
+ * fp32 (width,); proj_t_bf16: the projection TRANSPOSED, (N, width) bf16 row-major.  LayerNorm in fp32 (biased variance, eps),
+ * projection on the tensor cores (bf16 operands, fp32 accumulate), one CTA per 128 rows holding all N columns in tensor
+ * memory so that the row norm and the cast happen in the GEMM's epilogue.
+ * Outputs: a_bf16 (rows, N) normalised operand rows; inv_norm (rows,) = 1 / ||y||; optional y_f32 (rows, N) = the
+ * un-normalised projected features (what the backward's normalisation Jacobian needs), optional mean / rstd (rows,) of the
+ * LayerNorm.  ln_scratch_bf16: (rows, width) bf16 scratch (the LayerNorm output, also needed by the backward of proj).
+ * width % 64 == 0, 64 <= width <= 1024; N in {256, 512}.
+ * ------------------------------------------------------------------------------------------ */
+int vpa_encoder_tail(const void* x, int in_dtype, int64_t rows, int width, int64_t ld, const float* ln_gamma,
+                     const float* ln_beta, float eps, const void* proj_t_bf16, int N, void* ln_scratch_bf16, float* mean,
+                     float* rstd, void* a_bf16, float* y_f32, float* inv_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-label ranking metrics of the AudioSet zero-shot / tagging evaluation.  Replaces the per-class scikit-learn calls of
  *   /root/reference/cvap/module/decoder/loss_more.py:92-123 (BCELossHead.report, reached from BCELossHead.zero_shot :77-84 and
  *   cvap/monitor/audioset_clf.py:377-404): average_precision_score, roc_auc_score and the middle point of

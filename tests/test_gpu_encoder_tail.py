@@ -1,0 +1,153 @@
+"""Encoder tail (LayerNorm -> projection -> L2 normalise -> bf16 operand rows) against a plain PyTorch fp32 restatement of the
+reference's three lines (cvap/module/val.py:288-290 `x = self.ln(x[:, 0, :]); x = x @ self.proj`, clip_head.py:117-118
+`x = x / x.norm(dim=-1, keepdim=True)`).
+
+Floating point.  The kernel rounds the LayerNorm output and the projection to bf16 and accumulates in fp32 on the tensor cores:
+  * against the SAME rounding done in torch (bf16 operands, fp32 matmul) the features agree to 2e-3 of a row's norm;
+  * against the pure fp32 restatement the tolerance is the bf16 operand rounding: 1.5e-2 of a row's norm;
+  * LayerNorm statistics, 1/||y|| and the emitted bf16 operand rows are tight (1e-5 relative / one bf16 ulp).
+"""
+import pytest
+import torch
+import torch.nn.functional as TF
+
+pytestmark = pytest.mark.gpu
+
+from vipant_b200.encoder_tail import FusedPostEncoder, encoder_tail  # noqa: E402
+
+
+def _ref(x, gamma, beta, proj, eps=1e-5, round_bf16=False):
+    ln = TF.layer_norm(x.float(), (x.shape[-1],), gamma.float(), beta.float(), eps)
+    p = proj.float()
+    if round_bf16:
+        ln = ln.to(torch.bfloat16).float()
+        p = p.to(torch.bfloat16).float()
+    y = ln @ p
+    return ln, y
+
+
+def _mk(rows, width, N, seed, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(rows, width, device="cuda", generator=g) * 1.7 + 0.3).to(dtype)
+    gamma = 1.0 + 0.2 * torch.randn(width, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(width, device="cuda", generator=g)
+    proj = width ** -0.5 * torch.randn(width, N, device="cuda", generator=g)
+    return x, gamma, beta, proj
+
+
+def _check_forward(x, gamma, beta, proj):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    y, a, inv = encoder_tail(x, gamma, beta, proj, need_grad=False)
+    torch.cuda.synchronize()
+    _, y_r = _ref(x, gamma, beta, proj, round_bf16=True)
+    _, y_f = _ref(x, gamma, beta, proj)
+    norm = y_f.norm(dim=-1, keepdim=True)
+    assert y.shape == y_f.shape and y.dtype == torch.float32
+    assert ((y - y_r).abs().max(dim=-1, keepdim=True).values / norm).max().item() < 2e-3
+    assert ((y - y_f).norm(dim=-1, keepdim=True) / norm).max().item() < 1.5e-2
+    torch.testing.assert_close(inv, 1.0 / y.norm(dim=-1), rtol=1e-5, atol=0)
+    unit = (y * inv[:, None])
+    assert a.dtype == torch.bfloat16
+    # one bf16 ulp around the fp32 unit rows (values < 1: ulp <= 2^-8 relative)
+    assert ((a.float() - unit).abs() <= unit.abs() * 2 ** -8 + 1e-30).all()
+    return y, a, inv
+
+
+@pytest.mark.parametrize("rows,width,N", [(1, 768, 512), (100, 768, 512), (128, 512, 512), (333, 1024, 512), (1024, 768, 256),
+                                           (4096, 768, 512), (257, 64, 256)])
+def test_forward_matches_fp32_reference(rows, width, N):
+    _check_forward(*_mk(rows, width, N, seed=rows + width))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_half_inputs(dtype):
+    _check_forward(*_mk(300, 768, 512, seed=7, dtype=dtype))
+
+
+def test_cls_token_view_is_read_in_place():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    hidden = torch.randn(200, 5, 768, device="cuda", generator=g)
+    _, gamma, beta, proj = _mk(1, 768, 512, seed=4)
+    cls = hidden[:, 0, :]
+    assert not cls.is_contiguous()
+    y, a, inv = _check_forward(cls, gamma, beta, proj)
+    y2, a2, inv2 = encoder_tail(cls.contiguous(), gamma, beta, proj, need_grad=False)
+    assert torch.equal(y, y2) and torch.equal(a, a2) and torch.equal(inv, inv2)
+
+
+def test_layernorm_statistics_and_determinism():
+    from vipant_b200.encoder_tail import _prep, _run_tail
+    x, gamma, beta, proj = _mk(500, 768, 512, seed=11)
+    xc, g, b, pt = _prep(x, gamma, beta, proj)
+    a, inv, y, ln, stats = _run_tail(xc, g, b, pt, 1e-5, True, True)
+    ln_r, _ = _ref(x, gamma, beta, proj)
+    torch.testing.assert_close(stats[0], x.mean(-1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(stats[1], torch.rsqrt(x.var(-1, unbiased=False) + 1e-5), rtol=1e-5, atol=0)
+    assert ((ln.float() - ln_r).abs() <= ln_r.abs() * 2 ** -8 + 1e-6).all()
+    a2, inv2, y2, _, _ = _run_tail(xc, g, b, pt, 1e-5, True, False)
+    assert torch.equal(a, a2) and torch.equal(inv, inv2) and torch.equal(y, y2)
+
+
+def test_gradients_match_autograd_of_the_reference():
+    x, gamma, beta, proj = _mk(384, 768, 512, seed=21)
+    w = torch.randn(384, 512, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    leaves = [t.clone().requires_grad_(True) for t in (x, gamma, beta, proj)]
+    y, a, inv = encoder_tail(*leaves)
+    assert y.requires_grad and not a.requires_grad and not inv.requires_grad
+    # a loss through the normalised rows, like the head's:  sum(w * y / ||y||)
+    ((y / y.norm(dim=-1, keepdim=True)) * w).sum().backward()
+    ref = [t.clone().requires_grad_(True) for t in (x, gamma, beta, proj)]
+    _, y_r = _ref(*ref)
+    ((y_r / y_r.norm(dim=-1, keepdim=True)) * w).sum().backward()
+    for got, want, name in zip(leaves, ref, ("x", "ln.weight", "ln.bias", "proj")):
+        rel = (got.grad - want.grad).norm() / want.grad.norm()
+        assert rel.item() < 1.5e-2, (name, rel.item())
+
+
+def test_module_mirrors_the_reference_post_encoder():
+    torch.manual_seed(0)
+    m = FusedPostEncoder(None, width=768, embed_dim=512).cuda()
+    assert sorted(m.state_dict()) == ["ln.bias", "ln.weight", "proj"]      # the reference's checkpoint keys (val.py:270-273)
+    hidden = torch.randn(64, 7, 768, device="cuda")
+    out = m(hidden, normalized=True)
+    _, y_f = _ref(hidden[:, 0, :], m.ln.weight, m.ln.bias, m.proj)
+    want = y_f / y_f.norm(dim=-1, keepdim=True)
+    assert (out - want).norm(dim=-1).max().item() < 1.5e-2
+    # EOT selection (GPTPostEncoder, val.py:143-146)
+    eot = torch.randint(0, 7, (64,), device="cuda")
+    out = m(hidden, mask=eot)
+    _, y_f = _ref(hidden[torch.arange(64, device="cuda"), eot], m.ln.weight, m.ln.bias, m.proj)
+    assert ((out - y_f).norm(dim=-1) / y_f.norm(dim=-1)).max().item() < 1.5e-2
+    out.sum().backward()
+    assert m.proj.grad is not None and m.ln.weight.grad is not None
+
+
+def test_operands_feed_the_loss_head():
+    """The emitted bf16 rows are unit rows in the layout the loss reads: the InfoNCE loss on them (normalized=True) equals the
+    closed form on the fp32 restatement's unit rows within the bf16 tolerance of the loss tests (2e-2 absolute at scale 14)."""
+    import vipant_b200
+    B = 512
+    xa, ga, ba, pa = _mk(B, 768, 512, seed=31)
+    xt, gt, bt, pt = _mk(B, 512, 512, seed=32)
+    _, a, _ = encoder_tail(xa, ga, ba, pa, need_grad=False)
+    _, t, _ = encoder_tail(xt, gt, bt, pt, need_grad=False)
+    ls = torch.tensor(2.0, device="cuda")
+    loss = vipant_b200.infonce_loss(a, t, ls, normalized=True)
+    ya = _ref(xa, ga, ba, pa)[1].double()
+    yt = _ref(xt, gt, bt, pt)[1].double()
+    ya = ya / ya.norm(dim=-1, keepdim=True)
+    yt = yt / yt.norm(dim=-1, keepdim=True)
+    logits = ls.double().exp() * ya @ yt.t()
+    lab = torch.arange(B, device="cuda")
+    want = TF.cross_entropy(logits, lab) + TF.cross_entropy(logits.t(), lab)
+    assert abs(loss.item() - want.item()) < 2e-2
+
+
+def test_unsupported_shapes_fail_loudly():
+    from vipant_b200._cabi import VipantB200Error
+    x, gamma, beta, proj = _mk(16, 768, 384, seed=1)
+    with pytest.raises(VipantB200Error):
+        encoder_tail(x, gamma, beta, proj, need_grad=False)
+    x, gamma, beta, proj = _mk(16, 1088, 512, seed=1)
+    with pytest.raises(VipantB200Error):
+        encoder_tail(x, gamma, beta, proj, need_grad=False)

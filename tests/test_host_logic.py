@@ -321,3 +321,18 @@ def test_multi_pair_argument_checks():
     F.check_gt_range(torch.tensor([[0, 6]]), 7)
     with pytest.raises(ValueError):
         F._gt_matrix(torch.zeros(3, 9, dtype=torch.long), 3, 10, torch.device("cpu"), "gt")
+
+
+def test_fused_post_encoder_mirrors_reference_parameters_and_refuses_cpu():
+    """FusedPostEncoder keeps the reference's checkpoint keys (ViTPostEncoder: `ln`, `proj`, cvap/module/val.py:270-273)
+    and, like every product path here, has no CPU fallback."""
+    import torch
+    from vipant_b200._cabi import VipantB200Error
+    from vipant_b200.encoder_tail import FusedPostEncoder, encoder_tail
+    m = FusedPostEncoder(None, width=768, embed_dim=512)
+    assert sorted(m.state_dict()) == ["ln.bias", "ln.weight", "proj"]
+    assert tuple(m.proj.shape) == (768, 512) and m.ln.normalized_shape == (768,)
+    with pytest.raises(VipantB200Error):
+        m(torch.randn(4, 3, 768))
+    with pytest.raises(VipantB200Error):
+        encoder_tail(torch.randn(4, 768), m.ln.weight, m.ln.bias, m.proj)

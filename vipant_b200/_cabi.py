@@ -67,6 +67,8 @@ _SIGNATURES = {
     "vpa_sim_fused_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "vpa_sim_rank_fused": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vpa_encoder_tail": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vpa_multilabel_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "vpa_multilabel_scores": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

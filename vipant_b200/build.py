@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvipant_b200.so")
-SOURCES = ["api.cu", "normalize.cu", "infonce_post.cu", "infonce_simt.cu", "infonce_tc.cu", "infonce_pair.cu", "retrieval.cu", "retrieval_fused.cu", "multilabel.cu", "comm.cu", "p2p.cu"]
+SOURCES = ["api.cu", "normalize.cu", "infonce_post.cu", "infonce_simt.cu", "infonce_tc.cu", "infonce_pair.cu", "retrieval.cu", "retrieval_fused.cu", "multilabel.cu", "encoder_tail.cu", "comm.cu", "p2p.cu"]
 HEADERS = ["common.cuh", "simt_dot.cuh", "p2p.cuh", os.path.join("..", "..", "include", "vipant_b200.h")]
 
 NVCC_FLAGS = [

@@ -100,6 +100,10 @@ int multilabel_scores_launch(const float* S, int64_t ld_s, const void* Y, int y_
                              int truncate_pr, double* per_class, int32_t* flags, int32_t* support, double* micro_ap,
                              void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+int encoder_tail_launch(const void* x, int in_dtype, int64_t rows, int width, int64_t ld, const float* gamma, const float* beta,
+                        float eps, const void* proj_t_bf16, int N, void* ln_bf16, float* mean, float* rstd, void* a_bf16,
+                        float* y_f32, float* inv_norm, cudaStream_t st);
+
 static int sm_count() {      // of the CURRENT device (a process may drive several)
   static int cached[64] = {};
   int dev = 0, v = 0;
@@ -539,6 +543,13 @@ int vpa_sim_rank_fused(const float* Q, const float* K, int64_t N, int64_t M, int
                        size_t workspace_bytes, void* stream) {
   return sim_rank_fused_launch(Q, K, N, M, D, ldq, ldk, gt_q, g_q, gt_k, g_k, ranks_q, ranks_k, top1_q, top1_val_q, top1_k,
                                top1_val_k, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int vpa_encoder_tail(const void* x, int in_dtype, int64_t rows, int width, int64_t ld, const float* ln_gamma,
+                     const float* ln_beta, float eps, const void* proj_t_bf16, int N, void* ln_scratch_bf16, float* mean,
+                     float* rstd, void* a_bf16, float* y_f32, float* inv_norm, void* stream) {
+  return encoder_tail_launch(x, in_dtype, rows, width, ld, ln_gamma, ln_beta, eps, proj_t_bf16, N, ln_scratch_bf16, mean, rstd,
+                             a_bf16, y_f32, inv_norm, static_cast<cudaStream_t>(stream));
 }
 
 size_t vpa_multilabel_workspace_bytes(int64_t N, int C) { return multilabel_workspace_bytes(N, C); }

@@ -151,3 +151,73 @@ def test_unsupported_shapes_fail_loudly():
     x, gamma, beta, proj = _mk(16, 1088, 512, seed=1)
     with pytest.raises(VipantB200Error):
         encoder_tail(x, gamma, beta, proj, need_grad=False)
+
+
+# ---------------------------------------------------------------- against the reference's own post-encoders (golden) and the oracle
+GOLDEN_CASES = {"vit": dict(seed=4101, rows=72, tokens=3, width=768, embed=512),
+                "gpt": dict(seed=4102, rows=40, tokens=6, width=512, embed=512),
+                "vit256": dict(seed=4103, rows=130, tokens=2, width=1024, embed=256)}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_module_matches_reference_post_encoder_golden(name):
+    """FusedPostEncoder against tests/golden/encoder_tail.npz (outputs of the reference's ViTPostEncoder / GPTPostEncoder and the
+    heads' normalisation, fp32 CPU; oracle/make_golden_encoder_tail.py).  Tolerance = bf16 operand rounding: 1.5e-2 of a row's
+    norm for the features, 1.5e-2 absolute L2 distance for the unit rows; 1/||y|| within 1e-2 relative."""
+    import numpy as np
+    from conftest import load_golden
+    from oracle import encoder_tail_oracle as eo
+    c = GOLDEN_CASES[name]
+    fx = load_golden("encoder_tail")
+    inp = eo.golden_inputs(**c)
+    m = FusedPostEncoder(None, width=c["width"], embed_dim=c["embed"]).cuda()
+    with torch.no_grad():
+        m.ln.weight.copy_(torch.from_numpy(inp["gamma"]))
+        m.ln.bias.copy_(torch.from_numpy(inp["beta"]))
+        m.proj.copy_(torch.from_numpy(inp["proj"]))
+    hidden = torch.from_numpy(inp["hidden"]).cuda()
+    mask = torch.from_numpy(inp["eot"]).cuda() if name == "gpt" else None
+    with torch.no_grad():
+        y = m(hidden, mask=mask)
+        unit = m(hidden, mask=mask, normalized=True)
+        a, inv, _ = m.operands(hidden, mask=mask)
+    want_y = torch.from_numpy(fx[f"{name}_y"]).cuda()
+    want_norm = torch.from_numpy(fx[f"{name}_norm"]).cuda()
+    assert ((y - want_y).norm(dim=-1) / want_norm).max().item() < 1.5e-2
+    assert ((unit - want_y / want_norm[:, None]).norm(dim=-1)).max().item() < 1.5e-2
+    assert ((a.float() - want_y / want_norm[:, None]).norm(dim=-1)).max().item() < 2e-2
+    assert (inv * want_norm - 1).abs().max().item() < 1e-2
+    # and against the float64 oracle (same bound: the oracle agrees with the golden to 2e-5)
+    y64, _ = eo.encoder_tail(inp["hidden"], inp["gamma"], inp["beta"], inp["proj"], mask=inp["eot"] if name == "gpt" else None)
+    assert (np.linalg.norm(y.cpu().numpy() - y64, axis=-1) / np.linalg.norm(y64, axis=-1)).max() < 1.5e-2
+
+
+def test_gradients_match_reference_autograd_golden():
+    """Gradients of sum(w * y/||y||) through the fused tail against the reference autograd's (golden, ViT case)."""
+    import numpy as np
+    from conftest import load_golden
+    from oracle import encoder_tail_oracle as eo
+    from oracle.make_golden_encoder_tail import GRAD_ROWS
+    c = GOLDEN_CASES["vit"]
+    fx = load_golden("encoder_tail")
+    inp = eo.golden_inputs(**c)
+    m = FusedPostEncoder(None, width=c["width"], embed_dim=c["embed"]).cuda()
+    with torch.no_grad():
+        m.ln.weight.copy_(torch.from_numpy(inp["gamma"]))
+        m.ln.bias.copy_(torch.from_numpy(inp["beta"]))
+        m.proj.copy_(torch.from_numpy(inp["proj"]))
+    hidden = torch.from_numpy(inp["hidden"]).cuda().requires_grad_(True)
+    unit = m(hidden, normalized=True)
+    (unit * torch.from_numpy(inp["w"]).cuda()).sum().backward()
+    assert hidden.grad[:, 1:, :].abs().max().item() == 0.0
+    dx = hidden.grad[:, 0, :].cpu().numpy()
+    rows = np.asarray(GRAD_ROWS)
+
+    def rel(got, want):
+        return float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    assert rel(dx[rows], fx["vit_dx_rows"]) < 1.5e-2
+    assert abs(np.linalg.norm(dx) / float(fx["vit_dx_norm"]) - 1) < 1e-2
+    assert rel(m.ln.weight.grad.cpu().numpy(), fx["vit_dgamma"]) < 1.5e-2
+    assert rel(m.ln.bias.grad.cpu().numpy(), fx["vit_dbeta"]) < 1.5e-2
+    assert rel(m.proj.grad.cpu().numpy()[rows], fx["vit_dproj_rows"]) < 1.5e-2
+    assert abs(np.linalg.norm(m.proj.grad.cpu().numpy()) / float(fx["vit_dproj_norm"]) - 1) < 1e-2

@@ -156,3 +156,49 @@ def test_bench_parity_fixture_generator_matches_closed_form():
     assert int(fx["B"]) == 32768 and int(fx["block"]) == mb.BLOCK
     assert np.array_equal(fx["rows"], mb.sample_rows(32768)) and fx["dx1_rows"].shape == (8 * mb.SAMPLES, 512)
     assert fx["dx1_block_norm"].shape == (8,) and abs(float(fx["loss"]) - 9.96007) < 1e-4
+
+
+# ---------------------------------------------------------------- encoder tail
+ENCODER_TAIL_CASES = {"vit": dict(seed=4101, rows=72, tokens=3, width=768, embed=512),
+                      "gpt": dict(seed=4102, rows=40, tokens=6, width=512, embed=512),
+                      "vit256": dict(seed=4103, rows=130, tokens=2, width=1024, embed=256)}
+
+
+@pytest.mark.parametrize("name", sorted(ENCODER_TAIL_CASES))
+def test_encoder_tail_oracle_matches_reference_post_encoders(name):
+    """The numpy restatement against the outputs of the reference's own ViTPostEncoder / GPTPostEncoder (+ the heads'
+    normalisation), fp32 on CPU: 2e-5 of a row's norm (fp32 accumulation over width <= 1024 against float64)."""
+    from oracle import encoder_tail_oracle as eo
+    fx = load_golden("encoder_tail")
+    inp = eo.golden_inputs(**ENCODER_TAIL_CASES[name])
+    sums = [float(np.asarray(inp[k], np.float64).sum()) for k in ("hidden", "gamma", "beta", "proj")]
+    assert np.allclose(sums, fx[f"{name}_checksum"], rtol=1e-12, atol=0)              # same inputs as the generator's
+    y, unit = eo.encoder_tail(inp["hidden"], inp["gamma"], inp["beta"], inp["proj"], mask=inp["eot"] if name == "gpt" else None)
+    norm = fx[f"{name}_norm"].astype(np.float64)
+    assert (np.linalg.norm(y - fx[f"{name}_y"], axis=-1) / norm).max() < 2e-5
+    assert np.abs(np.linalg.norm(y, axis=-1) / norm - 1).max() < 1e-5
+    assert np.abs(unit[::8] - fx[f"{name}_unit_rows"]).max() < 2e-6
+    if name == "vit":
+        from oracle.make_golden_encoder_tail import GRAD_ROWS
+        dx, dgamma, dbeta, dproj = eo.encoder_tail_grads(inp["hidden"][:, 0, :], inp["gamma"], inp["beta"], inp["proj"], inp["w"])
+        assert float(fx["vit_dx_other_tokens_absmax"]) == 0.0                          # only the CLS token carries gradient
+        assert abs(np.linalg.norm(dx) / float(fx["vit_dx_norm"]) - 1) < 1e-5
+        assert np.linalg.norm(dx[GRAD_ROWS] - fx["vit_dx_rows"]) < 2e-5 * np.linalg.norm(fx["vit_dx_rows"])
+        assert np.linalg.norm(dgamma - fx["vit_dgamma"]) < 2e-5 * np.linalg.norm(fx["vit_dgamma"])
+        assert np.linalg.norm(dbeta - fx["vit_dbeta"]) < 2e-5 * np.linalg.norm(fx["vit_dbeta"])
+        assert abs(np.linalg.norm(dproj) / float(fx["vit_dproj_norm"]) - 1) < 1e-5
+        assert np.linalg.norm(dproj[GRAD_ROWS] - fx["vit_dproj_rows"]) < 2e-5 * np.linalg.norm(fx["vit_dproj_rows"])
+
+
+def test_encoder_tail_golden_generator_reproduces_fixture():
+    """With the reference mounted (build container), running its post-encoders again gives the committed fixture."""
+    from oracle import reference_loader as rl
+    if not rl.available():
+        pytest.skip("reference not mounted")
+    from oracle import make_golden_encoder_tail as mg
+    assert mg.CASES == ENCODER_TAIL_CASES
+    res = mg.build()
+    fx = load_golden("encoder_tail")
+    assert sorted(res) == sorted(fx.files)
+    for k in fx.files:
+        np.testing.assert_allclose(res[k], fx[k], rtol=1e-6, atol=1e-7)

@@ -121,5 +121,7 @@ class FusedPostEncoder(nn.Module):
     def forward(self, x, positional_embedding=None, class_embedding=None, mask=None, normalized: bool = False, **kwargs):
         y, a, inv = encoder_tail(self._select(x, mask), self.ln.weight, self.ln.bias, self.proj, self.ln.eps)
         if normalized:
-            return y * inv[:, None]                    # (differentiable through y; inv is recomputed by the loss's own Jacobian)
+            if y.requires_grad:                        # training: the normalisation's Jacobian belongs to autograd
+                return y / y.norm(dim=-1, keepdim=True)
+            return y * inv[:, None]
         return y

@@ -196,7 +196,7 @@ int vpa_sim_rank_fused(const float* Q, const float* K, int64_t N, int64_t M, int
  *   cvap/module/encoder/clip_head.py:117-118, audio_head.py:209-210 -- and the cast to the bf16 operand rows the sweeps read.
  * x: (rows, width) CLS rows, row stride ld (the view hidden[:, 0, :] is read in place), dtype in_dtype; ln_gamma / ln_beta:
  * fp32 (width,); proj_t_bf16: the projection TRANSPOSED, (N, width) bf16 row-major.  LayerNorm in fp32 (biased variance, eps),
- * projection on the tensor cores (bf16 operands, fp32 accumulate), one CTA per 128 rows holding all N columns in tensor
+ * projection on the tensor cores (bf16 operands, fp32 accumulate), one CTA pair per 256 rows holding all N columns in tensor
  * memory so that the row norm and the cast happen in the GEMM's epilogue.
  * Outputs: a_bf16 (rows, N) normalised operand rows; inv_norm (rows,) = 1 / ||y||; optional y_f32 (rows, N) = the
  * un-normalised projected features (what the backward's normalisation Jacobian needs), optional mean / rstd (rows,) of the

@@ -4,13 +4,16 @@
 // audio_head.py:209-210) produce the rows the loss head contracts.  Here:
 //   ln_cast_kernel     CLS rows (any row stride: `hidden[:, 0, :]` is read in place) -> LayerNorm in fp32 (CLIP's LayerNorm
 //                      computes in fp32) -> bf16 rows, + mean / rstd for the backward.  One warp per row, HBM-bound.
-//   proj_norm_kernel   Y = LN(x) . proj on the tensor cores: one CTA owns 128 rows and ALL N <= 512 output columns, so the
-//                      accumulator (128 lanes x N fp32) fills tensor memory and the L2 norm of a row is a reduction over the
-//                      thread's own TMEM lane: the epilogue normalises in place and writes the bf16 operand rows (what the
-//                      sweeps' TMA maps read), 1/||y||, and -- for training -- the un-normalised fp32 features the backward's
-//                      normalisation Jacobian needs.  A / proj k-slices stream through a 2-stage TMA ring (80 KB per stage),
-//                      tcgen05.mma M128 N128 K16, fp32 accumulate.
+//   proj_norm_pair_kernel   Y = LN(x) . proj on the tensor cores.  A CTA pair (tcgen05 cta_group::2) owns 256 rows and ALL
+//                      N <= 512 output columns: each CTA's accumulator (128 lanes x N fp32) fills its tensor memory, so the L2
+//                      norm of a row is a reduction over the thread's own TMEM lane and the epilogue normalises in place: it
+//                      writes the bf16 operand rows (what the sweeps' TMA maps read), 1/||y||, and -- for training -- the
+//                      un-normalised fp32 features the backward's normalisation Jacobian needs.  LN(x) / proj k-slices stream
+//                      through a 4-stage TMA ring (48 KB per stage and CTA), MMAs M256 N256 K16, fp32 accumulate.
 // The projected features never make a round trip through HBM between the GEMM and the normalise + cast.
+// Measured (B200, 32768 x 768 -> 512, profiles/r02_encoder_tail.md): LayerNorm 28.5 us (HBM-bound, 5.3 TB/s), projection 40 us,
+// 77 us for the pair against 654 us (fp32) / 261 us (bf16 autocast) of the same span in PyTorch eager.  A/B history: single-CTA
+// kernel (cta_group::1, 2 stages of 80 KB) 46 us; direct per-thread row stores instead of the transposed epilogue 61-63 us.
 #include <cuda.h>
 
 #include <cstdio>
@@ -24,7 +27,6 @@ constexpr int kLnWarps = 8;
 constexpr int kLnMaxVec = 8;                  // float4 chunks per lane -> width <= 1024
 constexpr int kBM = 128, kBoxK = 64;
 constexpr int kBoxBytes = kBM * kBoxK * 2;    // 16 KB: one [128 rows][64 elems] bf16 TMA box
-constexpr int kStages = 2;
 constexpr int kThreads = 192;                 // warp 0: TMA, warp 1: MMA issue + TMEM alloc, warps 2..5: epilogue
 constexpr uint32_t kSmemLimit = 232448;
 
@@ -115,33 +117,11 @@ __device__ __forceinline__ bool elect_one() {
       : "+r"(pred) : "r"(0xffffffffu));
   return pred != 0;
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -175,127 +155,202 @@ struct ProjParams {
   float* y_out;                // (rows, N) un-normalised fp32 features (nullptr: not wanted)
   float* inv_out;              // (rows,) 1 / ||y||
 };
-enum { B_DONE = 0, B_FULL = 1, B_EMPTY = 1 + kStages, B_COUNT = 1 + 2 * kStages };
 
-__global__ void __launch_bounds__(kThreads, 1)
-proj_norm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ProjParams P) {
+// Epilogue of one warp: thread = row (its TMEM lane holds all N columns of that row).  Pass 1: sum of squares (+ the raw fp32
+// features for the backward); pass 2: normalise, cast, store the bf16 operand row.  A thread's 32 columns are 128 contiguous
+// bytes of ITS row, so storing them directly makes every warp store touch 32 lines with half a sector each (measured: twice the
+// sectors into L2, the epilogue 2/3 of the kernel).  They are transposed through a 4 KB shared-memory tile per warp (the operand
+// ring is idle by then; 16-byte chunks XOR-swizzled by row: conflict-free both ways) and leave as 4 full lines (fp32) / 8 rows x
+// 64 bytes (bf16) per warp store.
+__device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int row0, int sub, int lane, int N, const ProjParams& P,
+                                              uint8_t* stage_smem) {
+  const int64_t rbase = row0 + sub * 32;
+  const bool row_ok = rbase + lane < P.rows;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(sub * 32) << 16);
+  uint4* s4 = reinterpret_cast<uint4*>(stage_smem + sub * 4096);
+  float ss = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_lane + c * 32, r);
+    tmem_ld_wait();
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]), v2 = __uint_as_float(r[e + 2]), v3 = __uint_as_float(r[e + 3]);
+      a0 = fmaf(v0, v0, a0); a1 = fmaf(v1, v1, a1); a2 = fmaf(v2, v2, a2); a3 = fmaf(v3, v3, a3);
+    }
+    ss += (a0 + a1) + (a2 + a3);
+    if (P.y_out) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s4[lane * 8 + (q ^ (lane & 7))] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+        const uint4 v = s4[rr * 8 + (ch ^ (rr & 7))];
+        if (rbase + rr < P.rows) *reinterpret_cast<uint4*>(P.y_out + (rbase + rr) * N + c * 32 + ch * 4) = v;
+      }
+      __syncwarp();
+    }
+  }
+  const float inv = 1.0f / sqrtf(ss);
+  if (row_ok && P.inv_out) P.inv_out[rbase + lane] = inv;
+#pragma unroll 1
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(t_lane + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        w[h] = pack_bf16x2(__uint_as_float(r[q * 8 + 2 * h]) * inv, __uint_as_float(r[q * 8 + 2 * h + 1]) * inv);
+      s4[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
+      const uint4 v = s4[rr * 4 + (ch ^ ((rr >> 1) & 3))];
+      if (rbase + rr < P.rows) *reinterpret_cast<uint4*>(P.a_out + (rbase + rr) * N + c * 32 + ch * 8) = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- projection + normalise on a CTA pair (tcgen05 cta_group::2)
+// Two CTAs (one TPC) own 256 rows.  Every MMA is M = 256 (128 rows per CTA) x N = 256, and each CTA stages only HALF of the
+// projection's rows of a 256-column block, so a stage is 48 KB and the ring is 4 deep.  Protocol as in infonce_pair.cu: both
+// producers account their bytes on the LEADER's full barrier, the leader issues, commits are multicast to both CTAs.
+constexpr int kPairStages = 4;
+enum { Q_DONE = 0, Q_FULL = 1, Q_EMPTY = 1 + kPairStages, Q_COUNT = 1 + 2 * kPairStages };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+proj_norm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const ProjParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = (uint32_t)(1 + P.nblk) * kBoxBytes;
-  const uint32_t bar0 = sbase + kStages * stage_bytes;
-  auto bar = [&](int i) { return bar0 + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sptr + kStages * stage_bytes + 8 * B_COUNT);
-  const uint32_t tmem_cols = P.nblk * 128 <= 256 ? 256u : 512u;
+  const uint32_t crank = cluster_ctarank();            // 0 = leader (issues the MMAs), 1 = peer
+  const bool is_leader = crank == 0;
   const int N = P.nblk * 128;
+  const int nb2 = N / 256;                             // 256-column blocks
+  const uint32_t stage_bytes = (uint32_t)(1 + nb2) * kBoxBytes;
+  const uint32_t bar0 = sbase + kPairStages * stage_bytes;
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  auto lbar = [&](int i) { return mapa(bar0 + 8u * i, 0); };     // the leader's copy (cluster address)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sptr + kPairStages * stage_bytes + 8 * Q_COUNT);
+  const uint32_t tmem_cols = N <= 256 ? 256u : 512u;
   if (threadIdx.x == 0) {
-    mbar_init(bar(B_DONE), 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+    mbar_init(bar(Q_DONE), 1);
+    for (int s = 0; s < kPairStages; ++s) { mbar_init(bar(Q_FULL + s), 1); mbar_init(bar(Q_EMPTY + s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w);
   }
-  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
+  if (warp == 1) tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int row0 = blockIdx.x * kBM;
+  const int row0 = (int)(blockIdx.x >> 1) * 2 * kBM + (int)crank * kBM;
 
   if (warp == 0) {
-    // ---- TMA producer: per k-slice one box of LN'd rows and nblk boxes of the (transposed) projection
-    const bool leader = elect_one();
+    // ---- TMA producer (both CTAs): own 128 rows of LN(x), and this CTA's 128 of every 256 projection rows
+    const bool elected = elect_one();
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < P.kboxes; ++kb) {
-      mbar_wait(bar(B_EMPTY + stage), phase ^ 1);
-      if (leader) {
-        mbar_arrive_expect_tx(bar(B_FULL + stage), stage_bytes);
+      mbar_wait(bar(Q_EMPTY + stage), phase ^ 1);
+      if (elected) {
+        if (is_leader) mbar_arrive_expect_tx(bar(Q_FULL + stage), 2 * stage_bytes);
+        const uint32_t fb = lbar(Q_FULL + stage);
         const uint32_t dst = sbase + stage * stage_bytes;
-        tma_load_2d(dst, &map_a, kb * kBoxK, row0, bar(B_FULL + stage));
-        for (int nb = 0; nb < P.nblk; ++nb) tma_load_2d(dst + (1 + nb) * kBoxBytes, &map_w, kb * kBoxK, nb * 128, bar(B_FULL + stage));
+        tma_load_2sm(dst, &map_a, kb * kBoxK, row0, fb);
+        for (int nb = 0; nb < nb2; ++nb) tma_load_2sm(dst + (1 + nb) * kBoxBytes, &map_w, kb * kBoxK, nb * 256 + (int)crank * 128, fb);
       }
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      if (++stage == kPairStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: acc[:, nb*128 .. +128) += A_k . W_k^T for every 128-column block
-    const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc(kBM, 128);
-    const uint64_t dk = make_desc(sbase, 16, 1024);
-    constexpr uint32_t box_u = kBoxBytes >> 4;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = 0; kb < P.kboxes; ++kb) {
-      mbar_wait(bar(B_FULL + stage), phase);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t st_u = (stage * stage_bytes) >> 4;
-        const uint64_t da0 = dk + (uint64_t)st_u;
-        for (int nb = 0; nb < P.nblk; ++nb) {
-          const uint64_t db0 = dk + (uint64_t)(st_u + (1 + nb) * box_u);
+    // ---- MMA issuer (leader CTA only)
+    if (is_leader) {
+      const bool elected = elect_one();
+      constexpr uint32_t idesc = make_idesc(256, 256);
+      const uint64_t dk = make_desc(sbase, 16, 1024);
+      constexpr uint32_t box_u = kBoxBytes >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < P.kboxes; ++kb) {
+        mbar_wait(bar(Q_FULL + stage), phase);
+        tc_fence_after();
+        if (elected) {
+          const uint32_t st_u = (stage * stage_bytes) >> 4;
+          const uint64_t da0 = dk + (uint64_t)st_u;
+          for (int nb = 0; nb < nb2; ++nb) {
+            const uint64_t db0 = dk + (uint64_t)(st_u + (1 + nb) * box_u);
 #pragma unroll
-          for (int k = 0; k < kBoxK / 16; ++k)
-            umma_f16(tmem_base + nb * 128, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBoxK / 16; ++k)
+              umma2_f16(tmem_base + nb * 256, da0 + (uint64_t)(k * 2), db0 + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma2_commit(bar(Q_EMPTY + stage));
+          if (kb == P.kboxes - 1) umma2_commit(bar(Q_DONE));
         }
-        umma_commit(bar(B_EMPTY + stage));
-        if (kb == P.kboxes - 1) umma_commit(bar(B_DONE));
+        __syncwarp();
+        if (++stage == kPairStages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ---- epilogue: thread = row (its TMEM lane holds all N columns): ||y||, then normalise + cast in place
-    const int sub = warp & 3;
-    const int64_t row = row0 + sub * 32 + lane;
-    const bool row_ok = row < P.rows;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(sub * 32) << 16);
-    mbar_wait(bar(B_DONE), 0);
+    mbar_wait(bar(Q_DONE), 0);
     tc_fence_after();
-    float ss = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < N / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(t_lane + c * 32, r);
-      tmem_ld_wait();
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        const float v0 = __uint_as_float(r[e]), v1 = __uint_as_float(r[e + 1]), v2 = __uint_as_float(r[e + 2]), v3 = __uint_as_float(r[e + 3]);
-        a0 = fmaf(v0, v0, a0); a1 = fmaf(v1, v1, a1); a2 = fmaf(v2, v2, a2); a3 = fmaf(v3, v3, a3);
-      }
-      ss += (a0 + a1) + (a2 + a3);
-      if (P.y_out && row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(P.y_out + row * N + c * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-      }
-    }
-    const float inv = 1.0f / sqrtf(ss);
-    if (row_ok && P.inv_out) P.inv_out[row] = inv;
-#pragma unroll 1
-    for (int c = 0; c < N / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(t_lane + c * 32, r);
-      tmem_ld_wait();
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(P.a_out + row * N + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h)
-            w[h] = pack_bf16x2(__uint_as_float(r[q * 8 + 2 * h]) * inv, __uint_as_float(r[q * 8 + 2 * h + 1]) * inv);
-          dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
-    }
+    epilogue_rows(tmem_base, row0, warp & 3, lane, N, P, sptr);
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                    // neither CTA frees tensor memory / exits while the pair may still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    tmem_dealloc2(tmem_base, tmem_cols);
   }
 }
 
@@ -354,12 +409,12 @@ int encoder_tail_launch(const void* x, int in_dtype, int64_t rows, int width, in
   ProjParams P{};
   P.rows = rows; P.kboxes = width / 64; P.nblk = N / 128;
   P.a_out = reinterpret_cast<__nv_bfloat16*>(a_bf16); P.y_out = y_f32; P.inv_out = inv_norm;
-  const uint32_t smem = kStages * (1 + P.nblk) * kBoxBytes + 8 * B_COUNT + 16 + 1024;
+  const uint32_t smem = kPairStages * (1 + N / 256) * kBoxBytes + 8 * Q_COUNT + 16 + 1024;
   if (smem > kSmemLimit) return set_error(VPA_E_UNSUPPORTED, "encoder_tail: %u bytes of shared memory", smem);
   static SmemAttrCache attr_cache;
-  if (int e = ensure_dynamic_smem(attr_cache, proj_norm_kernel, (int)kSmemLimit)) return e;
-  proj_norm_kernel<<<(unsigned)((rows + kBM - 1) / kBM), kThreads, smem, st>>>(map_a, map_w, P);
-  VPA_LAUNCH_CHECK("proj_norm_kernel");
+  if (int e = ensure_dynamic_smem(attr_cache, proj_norm_pair_kernel, (int)kSmemLimit)) return e;
+  proj_norm_pair_kernel<<<2 * (unsigned)((rows + 2 * kBM - 1) / (2 * kBM)), kThreads, smem, st>>>(map_a, map_w, P);
+  VPA_LAUNCH_CHECK("proj_norm_pair_kernel");
   return 0;
 }
 

@@ -221,3 +221,43 @@ def test_gradients_match_reference_autograd_golden():
     assert rel(m.ln.bias.grad.cpu().numpy(), fx["vit_dbeta"]) < 1.5e-2
     assert rel(m.proj.grad.cpu().numpy()[rows], fx["vit_dproj_rows"]) < 1.5e-2
     assert abs(np.linalg.norm(m.proj.grad.cpu().numpy()) / float(fx["vit_dproj_norm"]) - 1) < 1e-2
+
+
+def test_tail_and_loss_chain_gradients():
+    """Hidden states -> fused tails -> InfoNCE loss -> backward, against the same chain in PyTorch fp32 (the reference's
+    arithmetic: LayerNorm, matmul, normalise, scaled logits, two cross entropies).  Tolerances: loss 1e-3 relative (the loss
+    tests' bf16 bar), gradients 5e-2 relative -- a composition check (bf16 operands in the projection AND in the loss sweeps; each stage
+    has its own tighter test above / in test_gpu_infonce.py)."""
+    import vipant_b200
+    B = 256
+    xa, ga, ba, pa = _mk(B, 768, 512, seed=41)
+    xt, gt, bt, pt = _mk(B, 512, 512, seed=42)
+    xt = 0.6 * xt + 0.4 * xa[:, :512]                     # correlated pairs: a non-trivial diagonal
+    ls0 = 2.3
+
+    def run(fused):
+        leaves = [t.clone().requires_grad_(True) for t in (xa, ga, ba, pa, xt, gt, bt, pt)]
+        ls = torch.tensor(ls0, device="cuda", requires_grad=True)
+        if fused:
+            ya = encoder_tail(*leaves[:4])[0]
+            yt = encoder_tail(*leaves[4:])[0]
+            loss = vipant_b200.infonce_loss(ya, yt, ls)
+        else:
+            ya = _ref(*leaves[:4])[1]
+            yt = _ref(*leaves[4:])[1]
+            ya = ya / ya.norm(dim=-1, keepdim=True)
+            yt = yt / yt.norm(dim=-1, keepdim=True)
+            logits = ls.exp() * ya @ yt.t()
+            lab = torch.arange(B, device="cuda")
+            loss = TF.cross_entropy(logits, lab) + TF.cross_entropy(logits.t(), lab)
+        loss.backward()
+        return loss.item(), [t.grad for t in leaves] + [ls.grad]
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    loss_f, grads_f = run(True)
+    loss_r, grads_r = run(False)
+    assert abs(loss_f - loss_r) < 1e-3 * abs(loss_r) + 1e-3
+    names = ("x_a", "ln_a.weight", "ln_a.bias", "proj_a", "x_t", "ln_t.weight", "ln_t.bias", "proj_t", "logit_scale")
+    for got, want, name in zip(grads_f, grads_r, names):
+        rel = ((got - want).norm() / want.norm()).item()
+        assert rel < 5e-2, (name, rel)

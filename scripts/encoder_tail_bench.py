@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as TF
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vipant_b200.encoder_tail import _prep, _run_tail  # noqa: E402
+from vipant_b200.encoder_tail import FusedPostEncoder  # noqa: E402
 
 
 def timed(fn, flush, iters=20, warm=3):
@@ -47,13 +47,18 @@ def main():
         gamma = torch.rand(W, device=dev) + 0.5
         beta = torch.randn(W, device=dev) * 0.1
         proj = torch.randn(W, N, device=dev) * W ** -0.5
-        xc, g, b, pt = _prep(hidden, gamma, beta, proj)
+        post = FusedPostEncoder(None, width=W, embed_dim=N).to(dev)      # the public module (parameters require grad)
+        with torch.no_grad():
+            post.ln.weight.copy_(gamma)
+            post.ln.bias.copy_(beta)
+            post.proj.copy_(proj)
 
-        def fused_train():
-            return _run_tail(xc, g, b, pt, 1e-5, True, True)
+        def fused_train():                              # forward as a training step calls it (autograd state kept)
+            return post(hidden)
 
         def fused_infer():
-            return _run_tail(xc, g, b, pt, 1e-5, False, False)
+            with torch.no_grad():
+                return post.operands(hidden, features=False)
 
         def eager_fp32():
             y = TF.layer_norm(hidden, (W,), gamma, beta) @ proj
@@ -78,7 +83,7 @@ def main():
         print(json.dumps(r), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/encoder_tail.json", "w") as f:
-        json.dump({"device": torch.cuda.get_device_name(0), "note": "median of 20, L2 flushed between iterations", "results": out}, f,
+        json.dump({"device": torch.cuda.get_device_name(0), "note": "median of 20, L2 flushed between iterations; fused_* = FusedPostEncoder.forward (grad mode) / .operands (no_grad)", "results": out}, f,
                   indent=1)
 
 

@@ -261,3 +261,28 @@ def test_tail_and_loss_chain_gradients():
     for got, want, name in zip(grads_f, grads_r, names):
         rel = ((got - want).norm() / want.norm()).item()
         assert rel < 5e-2, (name, rel)
+
+
+def test_module_refreshes_its_projection_operand_when_the_parameter_changes():
+    """The module keeps the transposed bf16 projection per parameter version: an optimiser step (in place), load_state_dict
+    and a freshly assigned .data must all be picked up."""
+    torch.manual_seed(1)
+    m = FusedPostEncoder(None, width=512, embed_dim=256).cuda()
+    x = torch.randn(40, 512, device="cuda")
+    with torch.no_grad():
+        y0 = m(x).clone()
+        assert m._proj_t is not None
+        a_only, inv_only, none = m.operands(x, features=False)   # inference: the fp32 features are not written
+        a_full, inv_full, y_full = m.operands(x)
+        assert none is None and torch.equal(a_only, a_full) and torch.equal(inv_only, inv_full) and torch.equal(y_full, y0)
+        cached = m._proj_t[1]
+        assert m._proj_operand() is cached                       # unchanged parameter: reused
+        m.proj.mul_(2.0)                                         # in-place update
+        y1 = m(x)
+        torch.testing.assert_close(y1, 2.0 * y0, rtol=1e-6, atol=1e-6)      # exact: a power of two commutes with the bf16 rounding
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        sd["proj"] = sd["proj"] * 0.5
+        m.load_state_dict(sd)
+        torch.testing.assert_close(m(x), y0, rtol=1e-6, atol=1e-6)
+        m.proj.data = (4.0 * m.proj.data).clone()
+        torch.testing.assert_close(m(x), 4.0 * y0, rtol=1e-6, atol=1e-6)

@@ -45,21 +45,28 @@ def _run_tail(x, gamma, beta, proj_t_bf16, eps, want_y, want_stats):
     return a, inv, y, ln, stats
 
 
-def _prep(x, gamma, beta, proj):
+def transposed_bf16(proj):
+    """(embed_dim, width) bf16, K-major: what the TMA map of the projection (the B operand) reads."""
+    return proj.detach().t().contiguous().to(torch.bfloat16)
+
+
+def _prep(x, gamma, beta, proj, proj_t_bf16=None):
     F_._require_cuda(x, gamma, beta, proj)
     x = F_._rows2d(x)                                  # row-strided CLS views are read in place
     if proj.dim() != 2 or proj.shape[0] != x.shape[1]:
         raise ValueError(f"proj must be (width={x.shape[1]}, embed_dim), got {tuple(proj.shape)}")
     g = gamma.detach().float().contiguous()
     b = beta.detach().float().contiguous()
-    pt = proj.detach().t().contiguous().to(torch.bfloat16)      # (N, width), K-major: what the TMA map of the B operand reads
+    pt = transposed_bf16(proj) if proj_t_bf16 is None else proj_t_bf16
+    if pt.dtype != torch.bfloat16 or tuple(pt.shape) != (proj.shape[1], proj.shape[0]) or not pt.is_contiguous():
+        raise ValueError("proj_t_bf16 must be the contiguous bf16 transpose of proj")
     return x, g, b, pt
 
 
 class _TailFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, proj, eps):
-        xc, g, b, pt = _prep(x, gamma, beta, proj)
+    def forward(ctx, x, gamma, beta, proj, eps, proj_t_bf16):
+        xc, g, b, pt = _prep(x, gamma, beta, proj, proj_t_bf16)
         a, inv, y, ln, stats = _run_tail(xc, g, b, pt, eps, True, True)
         ctx.save_for_backward(xc, gamma, proj, ln, stats)
         ctx.mark_non_differentiable(a, inv)
@@ -78,18 +85,20 @@ class _TailFunction(torch.autograd.Function):
         dbeta = dln.sum(0).to(gamma.dtype)
         dxh = dln * gamma.detach().float()
         dx = rstd * (dxh - dxh.mean(-1, keepdim=True) - xhat * (dxh * xhat).mean(-1, keepdim=True))
-        return dx.to(xc.dtype), dgamma, dbeta, dproj, None
+        return dx.to(xc.dtype), dgamma, dbeta, dproj, None, None
 
 
-def encoder_tail(x, gamma, beta, proj, eps: float = 1e-5, need_grad: bool = None):
+def encoder_tail(x, gamma, beta, proj, eps: float = 1e-5, need_grad: bool = None, proj_t_bf16=None, features: bool = True):
     """LayerNorm(x) @ proj, L2-normalised and cast: returns ``(y, a_bf16, inv_norm)`` -- y (rows, N) fp32 un-normalised features
-    (differentiable), a_bf16 the unit rows as bf16 operands, inv_norm = 1 / ||y||.  x: (rows, width) CUDA, any row stride."""
+    (differentiable), a_bf16 the unit rows as bf16 operands, inv_norm = 1 / ||y||.  x: (rows, width) CUDA, any row stride.
+    proj_t_bf16: ``transposed_bf16(proj)`` computed by the caller (the module keeps it per parameter version); by default it
+    is made here, two small launches per call.  features=False (inference only): y is not written and comes back as None."""
     if need_grad is None:
         need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (x, gamma, beta, proj))
     if need_grad:
-        return _TailFunction.apply(x, gamma, beta, proj, eps)
-    xc, g, b, pt = _prep(x, gamma, beta, proj)
-    a, inv, y, _, _ = _run_tail(xc, g, b, pt, eps, True, False)
+        return _TailFunction.apply(x, gamma, beta, proj, eps, proj_t_bf16)
+    xc, g, b, pt = _prep(x, gamma, beta, proj, proj_t_bf16)
+    a, inv, y, _, _ = _run_tail(xc, g, b, pt, eps, bool(features), False)
     return y, a, inv
 
 
@@ -105,6 +114,18 @@ class FusedPostEncoder(nn.Module):
         super().__init__()
         self.ln = nn.LayerNorm(width)
         self.proj = nn.Parameter(width ** -0.5 * torch.randn(width, embed_dim))
+        self._proj_t = None                            # (key, bf16 transpose): redone when the parameter changes
+
+    def _proj_operand(self):
+        p = self.proj
+        key = (p.data_ptr(), p._version, p.device)     # in-place optimiser steps / load_state_dict bump _version
+        if self._proj_t is None or self._proj_t[0] != key:
+            self._proj_t = (key, transposed_bf16(p))
+        return self._proj_t[1]
+
+    def _tail(self, x, mask, features=True):
+        return encoder_tail(self._select(x, mask), self.ln.weight, self.ln.bias, self.proj, self.ln.eps,
+                            proj_t_bf16=self._proj_operand(), features=features)
 
     def _select(self, x, mask):
         if x.dim() == 2:
@@ -113,13 +134,14 @@ class FusedPostEncoder(nn.Module):
             return x[:, 0, :]
         return x[torch.arange(x.shape[0], device=x.device), mask]
 
-    def operands(self, x, mask=None):
-        """(a_bf16, inv_norm, y): the unit rows as the sweep kernels read them, 1/||y||, and the raw projected features."""
-        y, a, inv = encoder_tail(self._select(x, mask), self.ln.weight, self.ln.bias, self.proj, self.ln.eps)
+    def operands(self, x, mask=None, features: bool = True):
+        """(a_bf16, inv_norm, y): the unit rows as the sweep kernels read them, 1/||y||, and the raw projected features
+        (None with features=False under no_grad: the fp32 features are then never written)."""
+        y, a, inv = self._tail(x, mask, features)
         return a, inv, y
 
     def forward(self, x, positional_embedding=None, class_embedding=None, mask=None, normalized: bool = False, **kwargs):
-        y, a, inv = encoder_tail(self._select(x, mask), self.ln.weight, self.ln.bias, self.proj, self.ln.eps)
+        y, a, inv = self._tail(x, mask)
         if normalized:
             if y.requires_grad:                        # training: the normalisation's Jacobian belongs to autograd
                 return y / y.norm(dim=-1, keepdim=True)

@@ -336,3 +336,29 @@ def test_fused_post_encoder_mirrors_reference_parameters_and_refuses_cpu():
         m(torch.randn(4, 3, 768))
     with pytest.raises(VipantB200Error):
         encoder_tail(torch.randn(4, 768), m.ln.weight, m.ln.bias, m.proj)
+
+
+def test_encoder_tail_backward_formulas_match_the_oracle():
+    """tail_backward (the torch side of the fused tail's autograd: two GEMMs + LayerNorm backward from kept statistics) against
+    the float64 closed forms of oracle/encoder_tail_oracle.py, on CPU tensors (the function is device-agnostic; the kernels'
+    forward outputs are stood in for by the oracle's)."""
+    import numpy as np
+    import torch
+    from oracle import encoder_tail_oracle as eo
+    from vipant_b200.encoder_tail import tail_backward
+    inp = eo.golden_inputs(seed=99, rows=48, tokens=1, width=256, embed=256)
+    x = inp["hidden"][:, 0, :]
+    x64 = x.astype(np.float64)
+    mean = x64.mean(-1)
+    rstd = 1.0 / np.sqrt(((x64 - mean[:, None]) ** 2).mean(-1) + eo.EPS)
+    ln = eo.layer_norm(x, inp["gamma"], inp["beta"])
+    y, unit = eo.encoder_tail(x, inp["gamma"], inp["beta"], inp["proj"])
+    w = inp["w"].astype(np.float64)
+    nrm = np.linalg.norm(y, axis=-1, keepdims=True)
+    dy = (w - unit * (w * unit).sum(-1, keepdims=True)) / nrm                       # d sum(w * y/||y||) / dy
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float32))                       # noqa: E731
+    got = tail_backward(t(x), t(inp["gamma"]), t(inp["proj"]), t(ln), t(mean), t(rstd), t(dy))
+    want = eo.encoder_tail_grads(x, inp["gamma"], inp["beta"], inp["proj"], inp["w"])
+    for g, r, name in zip(got, want, ("x", "ln.weight", "ln.bias", "proj")):
+        rel = np.linalg.norm(g.numpy() - r) / np.linalg.norm(r)
+        assert rel < 2e-5, (name, rel)

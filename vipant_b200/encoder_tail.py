@@ -75,17 +75,22 @@ class _TailFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _da, _dinv):
         xc, gamma, proj, ln, stats = ctx.saved_tensors
-        dy = dy.float()
-        lnf = ln.float()
-        dproj = (lnf.t() @ dy).to(proj.dtype)                   # plain library GEMMs, as the reference's autograd runs them
-        dln = dy @ proj.detach().float().t()
-        mean, rstd = stats[0][:, None], stats[1][:, None]
-        xhat = (xc.detach().float() - mean) * rstd
-        dgamma = (dln * xhat).sum(0).to(gamma.dtype)
-        dbeta = dln.sum(0).to(gamma.dtype)
-        dxh = dln * gamma.detach().float()
-        dx = rstd * (dxh - dxh.mean(-1, keepdim=True) - xhat * (dxh * xhat).mean(-1, keepdim=True))
-        return dx.to(xc.dtype), dgamma, dbeta, dproj, None, None
+        return tail_backward(xc, gamma, proj, ln, stats[0], stats[1], dy) + (None, None)
+
+
+def tail_backward(x, gamma, proj, ln, mean, rstd, dy):
+    """Gradients of the tail w.r.t. (x, ln.weight, ln.bias, proj) from d/dy: two plain library GEMMs (as the reference's autograd
+    runs them) and the LayerNorm backward from the statistics the forward kept.  ln: the forward's bf16 LayerNorm output."""
+    dy = dy.float()
+    dproj = (ln.float().t() @ dy).to(proj.dtype)
+    dln = dy @ proj.detach().float().t()
+    mean, rstd = mean[:, None], rstd[:, None]
+    xhat = (x.detach().float() - mean) * rstd
+    dgamma = (dln * xhat).sum(0).to(gamma.dtype)
+    dbeta = dln.sum(0).to(gamma.dtype)
+    dxh = dln * gamma.detach().float()
+    dx = rstd * (dxh - dxh.mean(-1, keepdim=True) - xhat * (dxh * xhat).mean(-1, keepdim=True))
+    return dx.to(x.dtype), dgamma, dbeta, dproj
 
 
 def encoder_tail(x, gamma, beta, proj, eps: float = 1e-5, need_grad: bool = None, proj_t_bf16=None, features: bool = True):
